@@ -1,0 +1,69 @@
+/* oracle.h - C interface shared by the two CPU checkers of the render hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is on the product path: only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load these libraries, and only as the checker / reported baseline.
+ *
+ *   oracle/liboracle.so        - oracle.c, a plain-C restatement of the reference's
+ *                                per-pixel path (kernel.cu:1614-1690 and callees).
+ *   oracle/_ref/libref_oracle.so - the reference's OWN code (kernel.cu read in place
+ *                                from /root/reference, mechanically patched into
+ *                                oracle/_ref/, compiled as host C++) behind the
+ *                                same entry point.  Used to pin the restatement.
+ *
+ * Both export `oracle_render` with the descriptor below.
+ */
+#ifndef ORE_ORACLE_H
+#define ORE_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct oracle_frame {
+    int32_t width, height;   /* full frame size (dx,dy use the full size, kernel.cu:1624-1625) */
+    int32_t y0, y1;          /* rows rendered: [y0,y1), row 0 = first row of `pixels`          */
+    int32_t y_step;          /* render rows y0, y0+y_step, ... (<y1); 1 = every row            */
+    float cam_org[3];        /* camera::Org   (kernel.cu:1695)                                 */
+    float cam_yaw, cam_pitch;/* camera::Camyaw/Campitch in degrees (kernel.cu:261)             */
+    float aspect;            /* global `aspect` = (float)tan(90*0.5*3.1415/180) (kernel.cu:1701)*/
+    int32_t n_spheres;
+    const float* spheres;    /* n x 4: cx,cy,cz, radius MEMBER (= ctor r*r, kernel.cu:287)     */
+    int32_t n_lights;
+    const float* lights;     /* n x 7: pos.xyz,size,r,g,b (kernel.cu:1246-1261)                */
+    int32_t tex_w, tex_h;    /* object texture, sprite planes (sprite.h:29-45)                 */
+    const float *tex_r, *tex_g, *tex_b;   /* tex_w*tex_h floats each, row-major                */
+    int32_t sky_w, sky_h;    /* skybox texture                                                 */
+    const float *sky_r, *sky_g, *sky_b;
+    float sky_size;          /* skybox ctor arg (10000, kernel.cu:1700)                        */
+} oracle_frame;
+
+/* Renders the selected rows.  Outputs are packed by rendered row (row k of the
+ * output = image row y0 + k*y_step), `width` entries per row; any may be NULL.
+ *   pixels : 0x00RRGGBB                         (rgbToInt, kernel.cu:546-556)
+ *   hit_id : nearest sphere index, -1 = miss    (castRay sphere loop, kernel.cu:1330-1342)
+ *   hit_t  : nearest t (bit pattern matters), +inf on miss
+ *   counts : [0] primary sphere::intersect calls, [1] shadow-phase calls in the
+ *            reference's loop order incl. early break (kernel.cu:1501-1510),
+ *            [2] sky-sphere calls, [3] hit pixels.  liboracle only; the _ref
+ *            build leaves counts zero (it is the unmodified arithmetic, uninstrumented).
+ * Returns 0 on success.  n_threads <= 0 means all host threads (OpenMP). */
+int oracle_render(const oracle_frame* f, uint32_t* pixels, int32_t* hit_id, float* hit_t,
+                  uint64_t* counts, int n_threads);
+
+/* Single ray-sphere test exactly as sphere::intersect (kernel.cu:293-354).
+ * radius_member is the stored member (ctor r*r).  Returns the bool; *t as written. */
+int oracle_sphere_intersect(const float org[3], const float dir[3], const float centre[3],
+                            float radius_member, float* t);
+
+/* rgbToInt (kernel.cu:546-556) */
+uint32_t oracle_rgb_to_int(int r, int g, int b);
+
+/* "reference" or "port" */
+const char* oracle_kind(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
