@@ -1,0 +1,141 @@
+/* ore_render.h - C ABI of the B200-native render hot path (libore_b200.so).
+ *
+ * Drop-in boundary for ONE path of OpenRayAi (leonZtiger/Ray-Tracer-engine): the
+ * per-pixel render kernel `rayTrace` and the host code that launches it.  Plain C
+ * types only (pointers + sizes); no torch / C++ types cross this boundary.
+ *
+ * Each entry point names the reference interface it replaces (file:line in the
+ * reference tree).  The C++ shims that keep the reference's own symbols
+ * (`onStart()`, `update()`, `memManager`, `sprite`) on top of this ABI live in
+ * ray-tracer-engine_b200/host/; INTEGRATION.md shows the binding a maintainer adds.
+ *
+ * Error convention: every call returns an int status (ORE_OK == 0).  The reference
+ * prints and exit(99)s on any CUDA error (memManager.cpp:3-11); that behaviour is
+ * kept in the C++ shim layer, not here.  There is NO CPU fallback: if no CUDA
+ * device / kernel image is usable the calls fail with ORE_ERR_CUDA.
+ */
+#ifndef ORE_RENDER_H
+#define ORE_RENDER_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORE_ABI_VERSION 1
+
+enum ore_status {
+    ORE_OK = 0,
+    ORE_ERR_INVALID = 1, /* bad argument / call order            */
+    ORE_ERR_CUDA = 2,    /* CUDA runtime error (see ore_last_error) */
+    ORE_ERR_NOMEM = 3
+};
+
+/* render flags */
+enum ore_flags {
+    ORE_FLAG_NONE = 0,
+    /* Debug: evaluate the reference's exact intersection sequence for EVERY ray/sphere
+     * pair instead of filter + exact re-adjudication.  Same results, much slower; used
+     * by the parity tests to prove the filter never drops a hit. */
+    ORE_FLAG_EXHAUSTIVE = 1,
+    /* Also count, per frame, the sphere::intersect calls the REFERENCE's loop order
+     * would make in castLightRay (first blocker index + 1, or N) - the roofline's
+     * "tests" (SURVEY.md 8d).  Costs one extra kernel; off on the timed path. */
+    ORE_FLAG_COUNT_REFERENCE_TESTS = 2
+};
+
+typedef struct ore_context ore_context; /* opaque; owns device buffers, streams, pinned staging */
+
+/* Layout-compatible with the reference's `camera` passed BY VALUE to rayTrace
+ * (kernel.cu:237-262,1615): ray::Org @0, ray::Dir @12, aspect @24, Camyaw @28,
+ * Campitch @32 - 36 bytes.  Dir and aspect are never read by the kernel. */
+typedef struct ore_camera {
+    float org[3];
+    float dir[3];
+    float aspect;
+    float yaw;   /* degrees */
+    float pitch; /* degrees */
+} ore_camera;
+
+/* One frame (or one row band of it).  Rows rendered: y0, y0+y_step, ... < y1, in
+ * GLOBAL image coordinates (dy depends on the global row, kernel.cu:1625); output
+ * row k is image row y0 + k*y_step, `width` pixels each, 0x00RRGGBB (rgbToInt,
+ * kernel.cu:546-556), row 0 = bottom scanline on screen (window.cpp:43). */
+typedef struct ore_frame {
+    int32_t width, height;
+    int32_t y0, y1, y_step; /* full frame: 0, height, 1 */
+    float aspect;           /* the global `aspect`, kernel.cu:1701 */
+    uint32_t flags;         /* ore_flags */
+} ore_frame;
+
+/* counters of the last ore_render* call */
+typedef struct ore_counters {
+    uint64_t pixels;          /* pixels rendered                                          */
+    uint64_t hit_pixels;      /* pixels whose primary ray hit a sphere                    */
+    uint64_t primary_tests;   /* pixels * n_spheres (reference count, data independent)   */
+    uint64_t shadow_tests_ref;/* reference-order shadow tests (only with COUNT flag)      */
+    uint64_t sky_tests;       /* miss pixels (one sky-sphere test each)                   */
+    uint64_t exact_primary;   /* exact re-adjudications executed, primary phase           */
+    uint64_t exact_shadow;    /* exact re-adjudications executed, shadow phase            */
+    uint64_t kernel_launches; /* kernels launched by the call                             */
+} ore_counters;
+
+/* ---- lifetime ---------------------------------------------------------------------
+ * Replaces the static initialisers + onStart() that build the global scene
+ * (kernel.cu:1692-1714) and the implicit default-stream context. `device` is the CUDA
+ * ordinal.  One context per GPU; calls on one context must not overlap. */
+int ore_create(ore_context** out, int device);
+int ore_destroy(ore_context* ctx);
+int ore_abi_version(void);
+const char* ore_last_error(const ore_context* ctx); /* "" if none */
+
+/* ---- scene upload (memManager / object side) --------------------------------------
+ * All uploads copy from caller memory through the context's pinned staging buffer
+ * into structure-of-arrays device buffers; the caller's memory is not retained. */
+
+/* Replaces object::sphereAllocMem (kernel.cu:1208-1212): n records of cx,cy,cz and the
+ * stored `radius` MEMBER (= ctor r*r, kernel.cu:287; squared again in the test :334). */
+int ore_set_spheres(ore_context* ctx, const float* xyz_radius, int32_t n);
+/* Same, from the reference's own 32-byte AoS records (vptr@0, orgin@8, reflective@20,
+ * radius@24; `sizeof(float)*8` per sphere, kernel.cu:1218-1220). */
+int ore_set_spheres_aos32(ore_context* ctx, const void* records, int32_t n);
+/* Replaces cudaMalloc+cudaMemcpy of `lights` in update() (kernel.cu:1776-1778):
+ * n x {pos.xyz, size, r, g, b} (kernel.cu:1246-1261). */
+int ore_set_lights(ore_context* ctx, const float* lights7, int32_t n);
+/* Replaces `objs->texture = new sprite(tex)` (kernel.cu:1201): sprite planes
+ * (sprite.h:29-45; value = byte/255, row-major y*width+x, Sprite.cpp:41-46). */
+int ore_set_texture(ore_context* ctx, const float* r, const float* g, const float* b,
+                    int32_t width, int32_t height);
+/* Replaces `new skybox(img, size)` (kernel.cu:1120-1123,1700). */
+int ore_set_sky(ore_context* ctx, const float* r, const float* g, const float* b,
+                int32_t width, int32_t height, float size);
+
+/* ---- render ------------------------------------------------------------------------
+ * Replaces the body of update(): rayTrace<<<...>>> + cudaDeviceSynchronize +
+ * setPixelBuff (kernel.cu:1780-1788, window.cpp:130-132).
+ *
+ * ore_render        : `out_host` is HOST memory (pageable or pinned); synchronous; the
+ *                     device->host copy of the band is part of the call.
+ * ore_render_device : `out_device` is DEVICE memory on the context's GPU (or a peer-
+ *                     mapped pointer); asynchronous on `stream` (a cudaStream_t, NULL =
+ *                     the context's own stream); no host copies. */
+int ore_render(ore_context* ctx, const ore_camera* cam, const ore_frame* frame, uint32_t* out_host);
+int ore_render_device(ore_context* ctx, const ore_camera* cam, const ore_frame* frame,
+                      uint32_t* out_device, void* stream);
+int ore_synchronize(ore_context* ctx);
+
+/* ---- introspection of the LAST render (parity tests, roofline accounting) ---------
+ * hit_id: nearest sphere index or -1 (castRay, kernel.cu:1330-1342); hit_t: nearest t,
+ * +inf on miss.  Packed like the pixels.  Either pointer may be NULL. */
+int ore_get_hits(ore_context* ctx, int32_t* hit_id_host, float* hit_t_host);
+int ore_get_counters(ore_context* ctx, ore_counters* out);
+/* average device time (ms) of each kernel of the last render, measured with CUDA events
+ * on the launching stream: [0] frame prep, [1] primary, [2] shadow+shade, [3] count */
+int ore_get_kernel_ms(ore_context* ctx, float ms[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORE_RENDER_H */

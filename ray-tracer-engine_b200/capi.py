@@ -1,0 +1,210 @@
+"""ctypes binding of the C ABI in include/ore_render.h (libore_b200.so).
+
+This is the only way Python reaches the render path: plain pointers and sizes, exactly the
+calls a C/C++ host makes.  There is no CPU fallback - if the library is missing or no
+sm_100 device is usable, construction fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+ORE_FLAG_EXHAUSTIVE = 1
+ORE_FLAG_COUNT_REFERENCE_TESTS = 2
+
+EXPORTS = [
+    "ore_create", "ore_destroy", "ore_abi_version", "ore_last_error",
+    "ore_set_spheres", "ore_set_spheres_aos32", "ore_set_lights", "ore_set_texture", "ore_set_sky",
+    "ore_render", "ore_render_device", "ore_synchronize",
+    "ore_get_hits", "ore_get_counters", "ore_get_kernel_ms",
+]
+
+
+class OreCamera(C.Structure):
+    _fields_ = [("org", C.c_float * 3), ("dir", C.c_float * 3), ("aspect", C.c_float),
+                ("yaw", C.c_float), ("pitch", C.c_float)]
+
+
+class OreFrame(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("y0", C.c_int32), ("y1", C.c_int32),
+                ("y_step", C.c_int32), ("aspect", C.c_float), ("flags", C.c_uint32)]
+
+
+class OreCounters(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in (
+        "pixels", "hit_pixels", "primary_tests", "shadow_tests_ref", "sky_tests",
+        "exact_primary", "exact_shadow", "kernel_launches")]
+
+
+class OreError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library(path: str | None = None) -> C.CDLL:
+    """Load libore_b200.so; raise if it is absent (never falls back to anything else)."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or _build.LIB_PATH
+    if not os.path.isfile(path):
+        raise OreError(f"{path} not built - run `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = C.CDLL(path)
+    vp, fp, i32 = C.c_void_p, C.POINTER(C.c_float), C.c_int32
+    lib.ore_create.argtypes = [C.POINTER(vp), C.c_int]
+    lib.ore_destroy.argtypes = [vp]
+    lib.ore_abi_version.argtypes = []
+    lib.ore_last_error.argtypes = [vp]
+    lib.ore_last_error.restype = C.c_char_p
+    lib.ore_set_spheres.argtypes = [vp, fp, i32]
+    lib.ore_set_spheres_aos32.argtypes = [vp, vp, i32]
+    lib.ore_set_lights.argtypes = [vp, fp, i32]
+    lib.ore_set_texture.argtypes = [vp, fp, fp, fp, i32, i32]
+    lib.ore_set_sky.argtypes = [vp, fp, fp, fp, i32, i32, C.c_float]
+    lib.ore_render.argtypes = [vp, C.POINTER(OreCamera), C.POINTER(OreFrame), vp]
+    lib.ore_render_device.argtypes = [vp, C.POINTER(OreCamera), C.POINTER(OreFrame), vp, vp]
+    lib.ore_synchronize.argtypes = [vp]
+    lib.ore_get_hits.argtypes = [vp, vp, vp]
+    lib.ore_get_counters.argtypes = [vp, C.POINTER(OreCounters)]
+    lib.ore_get_kernel_ms.argtypes = [vp, C.POINTER(C.c_float * 4)]
+    for name in EXPORTS:
+        if name != "ore_last_error":
+            getattr(lib, name).restype = C.c_int
+    if path == _build.LIB_PATH:
+        _lib = lib
+    return lib
+
+
+def _fptr(a: np.ndarray):
+    assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+class Renderer:
+    """One render context on one GPU (mirrors the reference's global scene + update())."""
+
+    def __init__(self, device: int = 0, lib: C.CDLL | None = None):
+        self.lib = lib or load_library()
+        self.ctx = C.c_void_p()
+        rc = self.lib.ore_create(C.byref(self.ctx), int(device))
+        if rc != 0:
+            msg = self.lib.ore_last_error(self.ctx).decode() if self.ctx else "allocation failed"
+            if self.ctx:
+                self.lib.ore_destroy(self.ctx)
+                self.ctx = C.c_void_p()
+            raise OreError(f"ore_create(device={device}) failed rc={rc}: {msg}")
+        self.device = device
+        self.scene = None
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise OreError(f"{what} failed rc={rc}: {self.lib.ore_last_error(self.ctx).decode()}")
+
+    def close(self):
+        if self.ctx:
+            self.lib.ore_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- scene ----
+    def set_spheres(self, xyz_radius: np.ndarray):
+        a = np.ascontiguousarray(xyz_radius, dtype=np.float32).reshape(-1, 4)
+        self._check(self.lib.ore_set_spheres(self.ctx, _fptr(a.reshape(-1)) if a.size else None, a.shape[0]), "ore_set_spheres")
+
+    def set_spheres_aos32(self, records: np.ndarray):
+        a = np.ascontiguousarray(records)
+        assert a.nbytes % 32 == 0
+        self._check(self.lib.ore_set_spheres_aos32(self.ctx, a.ctypes.data, a.nbytes // 32), "ore_set_spheres_aos32")
+
+    def set_lights(self, lights7: np.ndarray):
+        a = np.ascontiguousarray(lights7, dtype=np.float32).reshape(-1, 7)
+        self._check(self.lib.ore_set_lights(self.ctx, _fptr(a.reshape(-1)) if a.size else None, a.shape[0]), "ore_set_lights")
+
+    def set_texture(self, sprite):
+        self._check(self.lib.ore_set_texture(self.ctx, _fptr(sprite.r), _fptr(sprite.g), _fptr(sprite.b),
+                                             sprite.width, sprite.height), "ore_set_texture")
+
+    def set_sky(self, sprite, size: float):
+        self._check(self.lib.ore_set_sky(self.ctx, _fptr(sprite.r), _fptr(sprite.g), _fptr(sprite.b),
+                                         sprite.width, sprite.height, float(size)), "ore_set_sky")
+
+    def set_scene(self, scene, n_lights: int | None = None):
+        self.set_spheres(scene.spheres)
+        lights = scene.lights if n_lights is None else scene.lights[:n_lights]
+        self.set_lights(lights)
+        self.set_texture(scene.texture)
+        self.set_sky(scene.sky, scene.sky_size)
+        self.scene = scene
+
+    # ---- render ----
+    @staticmethod
+    def _cam(camera) -> OreCamera:
+        c = OreCamera()
+        c.org = (C.c_float * 3)(*[float(v) for v in camera.org])
+        c.dir = (C.c_float * 3)(0.0, 0.0, 1.0)
+        c.aspect = 0.0
+        c.yaw, c.pitch = float(camera.yaw), float(camera.pitch)
+        return c
+
+    def _frame(self, width, height, y0, y1, y_step, aspect, flags) -> OreFrame:
+        f = OreFrame()
+        f.width, f.height = int(width), int(height)
+        f.y0, f.y1, f.y_step = int(y0), int(height if y1 is None else y1), int(y_step)
+        f.aspect = float(self.scene.aspect if aspect is None else aspect)
+        f.flags = int(flags)
+        return f
+
+    @staticmethod
+    def rows(height, y0=0, y1=None, y_step=1) -> int:
+        y1 = height if y1 is None else y1
+        return max(0, (y1 - y0 + y_step - 1) // y_step)
+
+    def render(self, camera, width, height, y0=0, y1=None, y_step=1, aspect=None, flags=0, out=None) -> np.ndarray:
+        """Render into HOST memory (device->host copy inside the call). Returns uint32 [rows, W]."""
+        f = self._frame(width, height, y0, y1, y_step, aspect, flags)
+        rows = self.rows(height, y0, y1, y_step)
+        if out is None:
+            out = np.empty((rows, width), dtype=np.uint32)
+        assert out.dtype == np.uint32 and out.size == rows * width and out.flags["C_CONTIGUOUS"]
+        cam = self._cam(camera)
+        self._check(self.lib.ore_render(self.ctx, C.byref(cam), C.byref(f), out.ctypes.data if out.size else None)
+                    if out.size else 0, "ore_render")
+        return out
+
+    def render_device(self, camera, width, height, out_ptr: int, stream: int = 0, y0=0, y1=None, y_step=1,
+                      aspect=None, flags=0):
+        """Render into DEVICE memory at `out_ptr` (asynchronous on `stream`)."""
+        f = self._frame(width, height, y0, y1, y_step, aspect, flags)
+        cam = self._cam(camera)
+        self._check(self.lib.ore_render_device(self.ctx, C.byref(cam), C.byref(f), C.c_void_p(out_ptr),
+                                               C.c_void_p(stream) if stream else None), "ore_render_device")
+
+    def synchronize(self):
+        self._check(self.lib.ore_synchronize(self.ctx), "ore_synchronize")
+
+    def hits(self, rows, width):
+        ids = np.empty((rows, width), dtype=np.int32)
+        t = np.empty((rows, width), dtype=np.float32)
+        self._check(self.lib.ore_get_hits(self.ctx, ids.ctypes.data, t.ctypes.data), "ore_get_hits")
+        return ids, t
+
+    def counters(self) -> dict:
+        c = OreCounters()
+        self._check(self.lib.ore_get_counters(self.ctx, C.byref(c)), "ore_get_counters")
+        return {n: int(getattr(c, n)) for n, _ in OreCounters._fields_}
+
+    def kernel_ms(self):
+        ms = (C.c_float * 4)()
+        self._check(self.lib.ore_get_kernel_ms(self.ctx, C.byref(ms)), "ore_get_kernel_ms")
+        return [float(v) for v in ms]

@@ -1,0 +1,487 @@
+// ore_capi.cu - C ABI (include/ore_render.h) over the sm_100a render kernels.
+//
+// Replaces the host half of the reference's kernel.cu for this path: the global scene
+// set-up of onStart() (kernel.cu:1704-1714), object::sphereAllocMem (:1208-1212) and the
+// per-frame body of update() (:1762-1792).  Where the reference allocates and frees
+// managed memory every frame, the context keeps persistent SoA device buffers, a pinned
+// host staging buffer for uploads / read-back and its own stream.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo --fmad=false -shared
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ore_render.h"
+#include "ore_kernels.cuh"
+
+using namespace ore;
+
+struct ore_context {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool ev_valid = false;
+    bool ran_count = false;
+    std::string err;
+
+    // pinned staging (uploads and read-back)
+    void* pinned = nullptr;
+    size_t pinned_cap = 0;
+
+    // scene (structure of arrays on the device)
+    int n_spheres = 0, n_spheres_pad = 0;
+    float4* sph_exact = nullptr;
+    float4* sph_prim = nullptr;
+    float4* sph_shad = nullptr;
+    size_t sph_cap = 0;
+    int n_lights = 0;
+    LightP lights[MAX_LIGHTS];
+    float* tex[3] = {nullptr, nullptr, nullptr};
+    int tex_w = 0, tex_h = 0;
+    float* sky[3] = {nullptr, nullptr, nullptr};
+    int sky_w = 0, sky_h = 0;
+    float sky_radius = 0.f;
+
+    // per-frame buffers
+    float* dx_tab = nullptr;
+    size_t dx_cap = 0;
+    float* dy_tab = nullptr;
+    size_t dy_cap = 0;
+    int32_t* hit_id = nullptr;
+    float* hit_t = nullptr;
+    uint32_t* hit_list = nullptr;
+    uint32_t* pixels = nullptr;
+    size_t px_cap = 0;
+    unsigned long long* counters = nullptr;
+
+    // last frame
+    size_t last_px = 0;
+    int last_n_spheres = 0;
+    uint64_t last_launches = 0;
+};
+
+#define ORE_CUDA(ctx, expr)                                                                         \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            char _b[512];                                                                           \
+            snprintf(_b, sizeof _b, "CUDA error = %u at %s:%d '%s' (%s)", (unsigned)_e, __FILE__,   \
+                     __LINE__, #expr, cudaGetErrorString(_e));                                      \
+            (ctx)->err = _b;                                                                        \
+            return ORE_ERR_CUDA;                                                                    \
+        }                                                                                           \
+    } while (0)
+
+static int fail(ore_context* ctx, int code, const char* msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+static int ensure_pinned(ore_context* ctx, size_t bytes) {
+    if (bytes <= ctx->pinned_cap) return ORE_OK;
+    if (ctx->pinned) ORE_CUDA(ctx, cudaFreeHost(ctx->pinned));
+    ctx->pinned = nullptr;
+    ctx->pinned_cap = 0;
+    size_t cap = bytes + bytes / 4 + 4096;
+    ORE_CUDA(ctx, cudaMallocHost(&ctx->pinned, cap));
+    ctx->pinned_cap = cap;
+    return ORE_OK;
+}
+
+template <typename T>
+static int ensure_dev(ore_context* ctx, T** p, size_t* cap, size_t n) {
+    if (n <= *cap && *p) return ORE_OK;
+    if (*p) ORE_CUDA(ctx, cudaFree(*p));
+    *p = nullptr;
+    *cap = 0;
+    size_t want = n + n / 8 + 64;
+    ORE_CUDA(ctx, cudaMalloc((void**)p, want * sizeof(T)));
+    *cap = want;
+    return ORE_OK;
+}
+
+extern "C" int ore_abi_version(void) { return ORE_ABI_VERSION; }
+
+extern "C" const char* ore_last_error(const ore_context* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int ore_create(ore_context** out, int device) {
+    if (!out) return ORE_ERR_INVALID;
+    *out = nullptr;
+    ore_context* ctx = new (std::nothrow) ore_context();
+    if (!ctx) return ORE_ERR_NOMEM;
+    *out = ctx;  // returned even on failure so the caller can read ore_last_error
+    ctx->device = device;
+    ORE_CUDA(ctx, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    ORE_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        char b[160];
+        snprintf(b, sizeof b, "device %d is sm_%d%d; this library only carries an sm_100a image (no fallback)", device,
+                 prop.major, prop.minor);
+        return fail(ctx, ORE_ERR_CUDA, b);
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    ORE_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 5; i++) ORE_CUDA(ctx, cudaEventCreate(&ctx->ev[i]));
+    ORE_CUDA(ctx, cudaMalloc((void**)&ctx->counters, CNT_SLOTS * sizeof(unsigned long long)));
+    ORE_CUDA(ctx, cudaMemset(ctx->counters, 0, CNT_SLOTS * sizeof(unsigned long long)));
+    // kernel.cu:1454,1462-1463: phi = (float)j/10 * 2.f * 3.1415f; cosf(phi), sinf(phi)
+    float cphi[10], sphi[10];
+    for (int j = 0; j < 10; j++) {
+        float phi = (float)j / 10 * 2.f * 3.1415f;
+        cphi[j] = cosf(phi);
+        sphi[j] = sinf(phi);
+    }
+    ORE_CUDA(ctx, cudaMemcpyToSymbol(c_cos_phi, cphi, sizeof cphi));
+    ORE_CUDA(ctx, cudaMemcpyToSymbol(c_sin_phi, sphi, sizeof sphi));
+    return ORE_OK;
+}
+
+extern "C" int ore_destroy(ore_context* ctx) {
+    if (!ctx) return ORE_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    void* dev[] = {ctx->sph_exact, ctx->sph_prim, ctx->sph_shad, ctx->tex[0], ctx->tex[1], ctx->tex[2],
+                   ctx->sky[0],    ctx->sky[1],   ctx->sky[2],   ctx->dx_tab, ctx->dy_tab, ctx->hit_id,
+                   ctx->hit_t,     ctx->hit_list, ctx->pixels,   ctx->counters};
+    for (void* p : dev)
+        if (p) cudaFree(p);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (int i = 0; i < 5; i++)
+        if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return ORE_OK;
+}
+
+// ---- scene upload -----------------------------------------------------------------------
+
+static int upload_spheres(ore_context* ctx, const float* src, size_t stride_floats, size_t first, int32_t n) {
+    if (!ctx || n < 0 || (n > 0 && !src)) return fail(ctx, ORE_ERR_INVALID, "ore_set_spheres: bad arguments");
+    ORE_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int n_pad = ((n + SPHERE_PAD - 1) / SPHERE_PAD) * SPHERE_PAD + SPHERE_PAD;  // >= 1 pad block
+    size_t cap_e = ctx->sph_cap, cap_p = ctx->sph_cap, cap_s = ctx->sph_cap;
+    int rc;
+    if ((rc = ensure_dev(ctx, &ctx->sph_exact, &cap_e, (size_t)n_pad))) return rc;
+    if ((rc = ensure_dev(ctx, &ctx->sph_prim, &cap_p, (size_t)n_pad))) return rc;
+    if ((rc = ensure_dev(ctx, &ctx->sph_shad, &cap_s, (size_t)n_pad))) return rc;
+    ctx->sph_cap = cap_e < cap_p ? (cap_e < cap_s ? cap_e : cap_s) : (cap_p < cap_s ? cap_p : cap_s);
+    if ((rc = ensure_pinned(ctx, 2 * (size_t)n_pad * sizeof(float4)))) return rc;
+    float4* ex = (float4*)ctx->pinned;
+    float4* sh = ex + n_pad;
+    for (int i = 0; i < n_pad; i++) {
+        if (i < n) {
+            const float* s = src + (size_t)i * stride_floats + first;
+            ex[i] = make_float4(s[0], s[1], s[2], s[3]);
+            const float r4 = s[3] * s[3];  // the test squares the stored member, kernel.cu:334
+            float r4p = (float)((double)r4 * (1.0 + (double)ORE_KAPPA_SHADOW));
+            r4p = nextafterf(r4p, INFINITY);
+            sh[i] = make_float4(s[0], s[1], s[2], r4p);
+        } else {
+            ex[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            sh[i] = make_float4(0.f, 0.f, 0.f, -1e30f);  // filter value sqrt(LL+1e30) > |L|: never a candidate
+        }
+    }
+    ORE_CUDA(ctx, cudaMemcpyAsync(ctx->sph_exact, ex, (size_t)n_pad * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    ORE_CUDA(ctx, cudaMemcpyAsync(ctx->sph_shad, sh, (size_t)n_pad * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    ORE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->n_spheres = n;
+    ctx->n_spheres_pad = n_pad;
+    return ORE_OK;
+}
+
+extern "C" int ore_set_spheres(ore_context* ctx, const float* xyz_radius, int32_t n) {
+    return upload_spheres(ctx, xyz_radius, 4, 0, n);
+}
+
+extern "C" int ore_set_spheres_aos32(ore_context* ctx, const void* records, int32_t n) {
+    // reference record: vptr@0, orgin@8 (3 floats), reflective@20, radius@24, pad@28 (kernel.cu:265-358)
+    // => floats 2,3,4 = centre; float 6 = radius.  Repack to x,y,z,radius through a temporary.
+    if (!ctx || n < 0 || (n > 0 && !records)) return fail(ctx, ORE_ERR_INVALID, "ore_set_spheres_aos32: bad arguments");
+    std::vector<float> tmp((size_t)n * 4);
+    const float* f = (const float*)records;
+    for (int i = 0; i < n; i++) {
+        tmp[4 * (size_t)i + 0] = f[8 * (size_t)i + 2];
+        tmp[4 * (size_t)i + 1] = f[8 * (size_t)i + 3];
+        tmp[4 * (size_t)i + 2] = f[8 * (size_t)i + 4];
+        tmp[4 * (size_t)i + 3] = f[8 * (size_t)i + 6];
+    }
+    return upload_spheres(ctx, tmp.data(), 4, 0, n);
+}
+
+extern "C" int ore_set_lights(ore_context* ctx, const float* lights7, int32_t n) {
+    if (!ctx || n < 0 || n > MAX_LIGHTS || (n > 0 && !lights7))
+        return fail(ctx, ORE_ERR_INVALID, "ore_set_lights: 0..16 lights of 7 floats");
+    for (int i = 0; i < n; i++) {
+        const float* l = lights7 + 7 * (size_t)i;
+        ctx->lights[i] = LightP{l[0], l[1], l[2], l[3], l[4], l[5], l[6]};
+    }
+    ctx->n_lights = n;
+    return ORE_OK;
+}
+
+static int upload_planes(ore_context* ctx, float* dst[3], const float* r, const float* g, const float* b, int32_t w,
+                         int32_t h) {
+    if (!ctx || w <= 0 || h <= 0 || !r || !g || !b) return fail(ctx, ORE_ERR_INVALID, "sprite planes: bad arguments");
+    ORE_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)w * h;
+    int rc;
+    if ((rc = ensure_pinned(ctx, n * sizeof(float)))) return rc;
+    const float* src[3] = {r, g, b};
+    for (int c = 0; c < 3; c++) {
+        if (dst[c]) ORE_CUDA(ctx, cudaFree(dst[c]));
+        dst[c] = nullptr;
+        ORE_CUDA(ctx, cudaMalloc((void**)&dst[c], n * sizeof(float)));
+        memcpy(ctx->pinned, src[c], n * sizeof(float));
+        ORE_CUDA(ctx, cudaMemcpyAsync(dst[c], ctx->pinned, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        ORE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return ORE_OK;
+}
+
+extern "C" int ore_set_texture(ore_context* ctx, const float* r, const float* g, const float* b, int32_t width,
+                               int32_t height) {
+    int rc = upload_planes(ctx, ctx ? ctx->tex : nullptr, r, g, b, width, height);
+    if (rc) return rc;
+    ctx->tex_w = width;
+    ctx->tex_h = height;
+    return ORE_OK;
+}
+
+extern "C" int ore_set_sky(ore_context* ctx, const float* r, const float* g, const float* b, int32_t width,
+                           int32_t height, float size) {
+    int rc = upload_planes(ctx, ctx ? ctx->sky : nullptr, r, g, b, width, height);
+    if (rc) return rc;
+    ctx->sky_w = width;
+    ctx->sky_h = height;
+    ctx->sky_radius = size * size;  // sphere ctor stores r*r (kernel.cu:287)
+    return ORE_OK;
+}
+
+// ---- render -------------------------------------------------------------------------------
+
+static constexpr int PRIMARY_P = 8;
+static constexpr size_t RESIDENT_BYTES = 96 * 1024;
+static constexpr int STREAM_CHUNK = 2048;
+static constexpr int STREAM_STAGES = 3;
+
+template <typename K>
+static int grid_for(ore_context* ctx, K kernel, size_t smem, int* grid) {
+    int occ = 0;
+    ORE_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ORE_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, CTA_THREADS, smem));
+    if (occ < 1) return fail(ctx, ORE_ERR_CUDA, "kernel does not fit on an SM");
+    *grid = occ * ctx->sm_count;
+    return ORE_OK;
+}
+
+static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame* fr, uint32_t* out_device,
+                       cudaStream_t stream) {
+    if (!ctx) return ORE_ERR_INVALID;
+    if (!cam || !fr) return fail(ctx, ORE_ERR_INVALID, "ore_render: null camera/frame");
+    if (fr->width <= 0 || fr->height <= 0 || fr->y_step <= 0 || fr->y0 < 0 || fr->y1 < fr->y0)
+        return fail(ctx, ORE_ERR_INVALID, "ore_render: bad frame geometry");
+    if (!ctx->tex[0] || !ctx->sky[0]) return fail(ctx, ORE_ERR_INVALID, "ore_render: texture and sky must be set first");
+    if (!ctx->sph_exact) {
+        int rc = upload_spheres(ctx, nullptr, 4, 0, 0);
+        if (rc) return rc;
+    }
+    ORE_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int W = fr->width;
+    const int n_rows = (fr->y1 - fr->y0 + fr->y_step - 1) / fr->y_step;
+    const size_t n_px = (size_t)n_rows * W;
+    if (n_px >= (size_t)1 << 31) return fail(ctx, ORE_ERR_INVALID, "ore_render: band too large");
+    ctx->last_px = n_px;
+    ctx->last_n_spheres = ctx->n_spheres;
+    ctx->last_launches = 0;
+    ctx->ev_valid = false;
+    ctx->ran_count = false;
+    if (n_px == 0) return ORE_OK;
+
+    int rc;
+    if ((rc = ensure_dev(ctx, &ctx->dx_tab, &ctx->dx_cap, (size_t)W))) return rc;
+    if ((rc = ensure_dev(ctx, &ctx->dy_tab, &ctx->dy_cap, (size_t)n_rows))) return rc;
+    if (n_px > ctx->px_cap || !ctx->hit_id) {
+        size_t c1 = ctx->hit_id ? ctx->px_cap : 0, c2 = c1, c3 = c1, c4 = c1;
+        if ((rc = ensure_dev(ctx, &ctx->hit_id, &c1, n_px))) return rc;
+        if ((rc = ensure_dev(ctx, &ctx->hit_t, &c2, n_px))) return rc;
+        if ((rc = ensure_dev(ctx, &ctx->hit_list, &c3, n_px))) return rc;
+        if ((rc = ensure_dev(ctx, &ctx->pixels, &c4, n_px))) return rc;
+        ctx->px_cap = c1;
+    }
+
+    FrameParams prm;
+    memset(&prm, 0, sizeof prm);
+    prm.W = W;
+    prm.H = fr->height;
+    prm.y0 = fr->y0;
+    prm.y_step = fr->y_step;
+    prm.n_rows = n_rows;
+    prm.n_spheres = ctx->n_spheres;
+    prm.n_spheres_pad = ctx->n_spheres_pad;
+    prm.n_lights = ctx->n_lights;
+    prm.flags = fr->flags;
+    prm.aspect = fr->aspect;
+    prm.ez = (-1 / fr->aspect);  // kernel.cu:1629
+    prm.fz = 0.f - prm.ez;
+    prm.Ox = 0.f + cam->org[0];  // add(eyePos, cam.Org), kernel.cu:1631
+    prm.Oy = 0.f + cam->org[1];
+    prm.Oz = prm.ez + cam->org[2];
+    {
+        // camera::rotateDir, kernel.cu:249-255: frame-uniform, evaluated once on the host
+        float yawRad = cam->yaw * (3.1415 / 180);
+        float pitchRad = cam->pitch * (3.1415 / 180);
+        prm.cp = cosf(pitchRad);
+        prm.sp = sinf(pitchRad);
+        prm.cy = cosf(yawRad);
+        prm.sy = sinf(yawRad);
+    }
+    if ((size_t)ctx->n_spheres_pad * sizeof(float4) <= RESIDENT_BYTES) {
+        prm.resident = 1;
+        prm.chunk = ctx->n_spheres_pad;
+        prm.stages = 1;
+        prm.n_chunks = 1;
+    } else {
+        prm.resident = 0;
+        prm.chunk = STREAM_CHUNK;
+        prm.stages = STREAM_STAGES;
+        prm.n_chunks = (ctx->n_spheres_pad + STREAM_CHUNK - 1) / STREAM_CHUNK;
+    }
+    const size_t smem = (size_t)prm.stages * prm.chunk * sizeof(float4);
+    prm.dx_tab = ctx->dx_tab;
+    prm.dy_tab = ctx->dy_tab;
+    prm.sph_exact = ctx->sph_exact;
+    prm.sph_prim = ctx->sph_prim;
+    prm.sph_shad = ctx->sph_shad;
+    prm.tex_r = ctx->tex[0];
+    prm.tex_g = ctx->tex[1];
+    prm.tex_b = ctx->tex[2];
+    prm.tex_w = ctx->tex_w;
+    prm.tex_h = ctx->tex_h;
+    prm.sky_r = ctx->sky[0];
+    prm.sky_g = ctx->sky[1];
+    prm.sky_b = ctx->sky[2];
+    prm.sky_w = ctx->sky_w;
+    prm.sky_h = ctx->sky_h;
+    prm.sky_radius = ctx->sky_radius;
+    prm.hit_id = ctx->hit_id;
+    prm.hit_t = ctx->hit_t;
+    prm.hit_list = ctx->hit_list;
+    prm.counters = ctx->counters;
+    prm.pixels = out_device ? out_device : ctx->pixels;
+    for (int i = 0; i < ctx->n_lights; i++) prm.lights[i] = ctx->lights[i];
+
+    ORE_CUDA(ctx, cudaEventRecord(ctx->ev[0], stream));
+    {
+        int m = W > n_rows ? W : n_rows;
+        if (ctx->n_spheres_pad > m) m = ctx->n_spheres_pad;
+        if (m < CNT_SLOTS) m = CNT_SLOTS;
+        prep_frame_kernel<<<(m + 255) / 256, 256, 0, stream>>>(prm);
+        ORE_CUDA(ctx, cudaGetLastError());
+        ctx->last_launches++;
+    }
+    ORE_CUDA(ctx, cudaEventRecord(ctx->ev[1], stream));
+    {
+        int grid = 0;
+        if ((rc = grid_for(ctx, primary_kernel<PRIMARY_P>, smem, &grid))) return rc;
+        const int strips_per_row = (W + 32 * PRIMARY_P - 1) / (32 * PRIMARY_P);
+        const long long n_batches = ((long long)n_rows * strips_per_row + CTA_WARPS - 1) / CTA_WARPS;
+        if (grid > n_batches) grid = (int)n_batches;
+        primary_kernel<PRIMARY_P><<<grid, CTA_THREADS, smem, stream>>>(prm);
+        ORE_CUDA(ctx, cudaGetLastError());
+        ctx->last_launches++;
+    }
+    ORE_CUDA(ctx, cudaEventRecord(ctx->ev[2], stream));
+    {
+        int grid = 0;
+        const int nl = ctx->n_lights >= 3 ? 3 : (ctx->n_lights == 2 ? 2 : 1);
+        if (nl == 3) {
+            if ((rc = grid_for(ctx, shadow_kernel<3>, smem, &grid))) return rc;
+            shadow_kernel<3><<<grid, CTA_THREADS, smem, stream>>>(prm);
+        } else if (nl == 2) {
+            if ((rc = grid_for(ctx, shadow_kernel<2>, smem, &grid))) return rc;
+            shadow_kernel<2><<<grid, CTA_THREADS, smem, stream>>>(prm);
+        } else {
+            if ((rc = grid_for(ctx, shadow_kernel<1>, smem, &grid))) return rc;
+            shadow_kernel<1><<<grid, CTA_THREADS, smem, stream>>>(prm);
+        }
+        ORE_CUDA(ctx, cudaGetLastError());
+        ctx->last_launches++;
+    }
+    ORE_CUDA(ctx, cudaEventRecord(ctx->ev[3], stream));
+    ctx->ev_valid = true;
+    return ORE_OK;
+}
+
+extern "C" int ore_render_device(ore_context* ctx, const ore_camera* cam, const ore_frame* frame,
+                                 uint32_t* out_device, void* stream) {
+    if (!ctx) return ORE_ERR_INVALID;
+    if (!out_device) return fail(ctx, ORE_ERR_INVALID, "ore_render_device: null output");
+    return render_impl(ctx, cam, frame, out_device, stream ? (cudaStream_t)stream : ctx->stream);
+}
+
+extern "C" int ore_render(ore_context* ctx, const ore_camera* cam, const ore_frame* frame, uint32_t* out_host) {
+    if (!ctx) return ORE_ERR_INVALID;
+    if (!out_host) return fail(ctx, ORE_ERR_INVALID, "ore_render: null output");
+    int rc = render_impl(ctx, cam, frame, nullptr, ctx->stream);
+    if (rc) return rc;
+    if (ctx->last_px) {
+        // device -> host of the band; CUDA stages pageable destinations through its own pinned pool
+        ORE_CUDA(ctx, cudaMemcpyAsync(out_host, ctx->pixels, ctx->last_px * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                      ctx->stream));
+    }
+    ORE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ORE_OK;
+}
+
+extern "C" int ore_synchronize(ore_context* ctx) {
+    if (!ctx) return ORE_ERR_INVALID;
+    ORE_CUDA(ctx, cudaSetDevice(ctx->device));
+    ORE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ORE_CUDA(ctx, cudaDeviceSynchronize());
+    return ORE_OK;
+}
+
+extern "C" int ore_get_hits(ore_context* ctx, int32_t* hit_id_host, float* hit_t_host) {
+    if (!ctx) return ORE_ERR_INVALID;
+    ORE_CUDA(ctx, cudaSetDevice(ctx->device));
+    ORE_CUDA(ctx, cudaDeviceSynchronize());
+    if (ctx->last_px == 0) return ORE_OK;
+    if (hit_id_host)
+        ORE_CUDA(ctx, cudaMemcpy(hit_id_host, ctx->hit_id, ctx->last_px * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (hit_t_host)
+        ORE_CUDA(ctx, cudaMemcpy(hit_t_host, ctx->hit_t, ctx->last_px * sizeof(float), cudaMemcpyDeviceToHost));
+    return ORE_OK;
+}
+
+extern "C" int ore_get_counters(ore_context* ctx, ore_counters* out) {
+    if (!ctx || !out) return ORE_ERR_INVALID;
+    ORE_CUDA(ctx, cudaSetDevice(ctx->device));
+    ORE_CUDA(ctx, cudaDeviceSynchronize());
+    unsigned long long c[CNT_SLOTS];
+    ORE_CUDA(ctx, cudaMemcpy(c, ctx->counters, sizeof c, cudaMemcpyDeviceToHost));
+    memset(out, 0, sizeof *out);
+    out->pixels = ctx->last_px;
+    out->hit_pixels = ctx->last_px ? c[CNT_HITS] : 0;
+    out->primary_tests = (uint64_t)ctx->last_px * (uint64_t)ctx->last_n_spheres;
+    out->shadow_tests_ref = c[CNT_SHADOW_TESTS_REF];
+    out->sky_tests = ctx->last_px ? ctx->last_px - c[CNT_HITS] : 0;
+    out->exact_primary = c[CNT_EXACT_PRIMARY];
+    out->exact_shadow = c[CNT_EXACT_SHADOW];
+    out->kernel_launches = ctx->last_launches;
+    return ORE_OK;
+}
+
+extern "C" int ore_get_kernel_ms(ore_context* ctx, float ms[4]) {
+    if (!ctx || !ms) return ORE_ERR_INVALID;
+    ms[0] = ms[1] = ms[2] = ms[3] = 0.f;
+    if (!ctx->ev_valid) return ORE_OK;
+    ORE_CUDA(ctx, cudaSetDevice(ctx->device));
+    ORE_CUDA(ctx, cudaEventSynchronize(ctx->ev[3]));
+    for (int i = 0; i < 3; i++) ORE_CUDA(ctx, cudaEventElapsedTime(&ms[i], ctx->ev[i], ctx->ev[i + 1]));
+    return ORE_OK;
+}

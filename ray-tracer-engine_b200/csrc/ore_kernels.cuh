@@ -1,0 +1,559 @@
+// ore_kernels.cuh - the three kernels of the render hot path (sm_100a, --fmad=false).
+//
+//   prep_frame_kernel : per-frame tables (dx per column, dy per row, in the reference's
+//                       double arithmetic) and per-sphere PRIMARY filter coefficients
+//                       (all primary rays share one origin, so L = O - c and C are per-
+//                       sphere constants of the frame).
+//   primary_kernel<P> : nearest hit for P pixels per thread (one warp = one 32*P pixel
+//                       strip of a row); sphere tiles staged in shared memory by TMA bulk
+//                       copies; sky lookup + packed store for miss pixels; hit pixels are
+//                       compacted into a list.                      (kernel.cu:1614-1640,
+//                                                                    1330-1342, 1146-1166)
+//   shadow_kernel<NL> : one thread per HIT pixel: shading set-up, 10*NL soft-shadow rays
+//                       held in registers, any-hit over the staged sphere tiles, light
+//                       accumulation and the packed pixel store.     (kernel.cu:1396-1405,
+//                                                                    1643-1684, 1432-1544)
+#pragma once
+#include "ore_device.cuh"
+
+namespace ore {
+
+constexpr int MAX_LIGHTS = 16;
+constexpr int CTA_THREADS = 256;
+constexpr int CTA_WARPS = CTA_THREADS / 32;
+constexpr int MAX_STAGES = 4;
+constexpr int SPHERE_PAD = 16;  // device sphere arrays are padded to a multiple of this
+
+// conservative filter margins (see DESIGN.md "Filter soundness")
+#define ORE_KAPPA_SHADOW 3.814697265625e-06f /* 2^-18 */
+#define ORE_KAPPA_PRIMARY 7.62939453125e-06  /* 2^-17 */
+#define ORE_BIG 3.0e38f
+
+enum CounterSlot {
+    CNT_HITS = 0,          // hit-list length
+    CNT_SHADOW_CURSOR = 1, // dynamic batch cursor of the shadow kernel
+    CNT_EXACT_PRIMARY = 2,
+    CNT_EXACT_SHADOW = 3,
+    CNT_SHADOW_TESTS_REF = 4,
+    CNT_COUNT_CURSOR = 5,
+    CNT_SLOTS = 8
+};
+
+struct LightP {
+    float px, py, pz, size, r, g, b;
+};
+
+struct FrameParams {
+    int W, H, y0, y_step, n_rows;
+    int n_spheres, n_spheres_pad, n_lights;
+    uint32_t flags;
+    float aspect, ez, fz;  // ez = -1/aspect (kernel.cu:1629), fz = 0 - ez
+    float Ox, Oy, Oz;      // add(eyePos, cam.Org), kernel.cu:1631
+    float cp, sp, cy, sy;  // cosf/sinf of pitchRad / yawRad (kernel.cu:249-255), host libm
+    int chunk, stages, n_chunks, resident;  // sphere tile pipeline
+    const float* dx_tab;
+    const float* dy_tab;
+    const float4* sph_exact;  // cx,cy,cz,radius member
+    float4* sph_prim;         // primary filter coefficients a',b',c',0 (per frame)
+    const float4* sph_shad;   // cx,cy,cz,(1+k)*radius^2 (shadow filter)
+    const float *tex_r, *tex_g, *tex_b;
+    int tex_w, tex_h;
+    const float *sky_r, *sky_g, *sky_b;
+    int sky_w, sky_h;
+    float sky_radius;  // skybox sphere member = size*size (kernel.cu:287,1122)
+    int32_t* hit_id;
+    float* hit_t;
+    uint32_t* hit_list;
+    unsigned long long* counters;
+    uint32_t* pixels;
+    LightP lights[MAX_LIGHTS];
+};
+
+// cosf/sinf((float)j/10*2.f*3.1415f), kernel.cu:1454,1462-1463 - ten frame-independent
+// values, evaluated once on the host (same libm as the oracle) at context creation
+__constant__ float c_cos_phi[10];
+__constant__ float c_sin_phi[10];
+
+// ------------------------------------------------------------------------------------
+// primary ray of pixel (x, row k): kernel.cu:1624-1631 with dx/dy from the tables
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ v3 primary_dir(const FrameParams& prm, float dx, float dy) {
+    v3 v = mk(dx - 0.f, dy - 0.f, 0.f - prm.ez);  // sub(dir, eyePos)
+    v3 n = ref_normalise(v);
+    // camera::rotateDir, kernel.cu:252-255
+    float y = n.y * prm.cp - n.z * prm.sp;
+    float z = n.y * prm.sp + n.z * prm.cp;
+    float x = n.x * prm.cy + z * prm.sy;
+    z = -n.x * prm.sy + z * prm.cy;
+    return mk(x, y, z);
+}
+
+__device__ __forceinline__ int clamp_index(int idx, int n) { return idx < 0 ? 0 : (idx >= n ? n - 1 : idx); }
+
+// ------------------------------------------------------------------------------------
+// prep_frame_kernel
+// ------------------------------------------------------------------------------------
+__global__ void prep_frame_kernel(const FrameParams prm) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < CNT_SLOTS) prm.counters[i] = 0ull;
+    if (i < prm.W) {
+        // kernel.cu:1624  float dx = aspect * (2 * (x + 0.5) / (float)width) - 1;   (double)
+        double v = (double)prm.aspect * (2 * (i + 0.5) / (double)(float)prm.W) - 1;
+        const_cast<float*>(prm.dx_tab)[i] = (float)v;
+    }
+    if (i < prm.n_rows) {
+        // kernel.cu:1625  float dy = aspect * (2 * (y + 0.5) / (float)height)*((float)height/width) - 1;
+        const int y = prm.y0 + i * prm.y_step;
+        float hw = (float)prm.H / (float)prm.W;
+        double v = (double)prm.aspect * (2 * (y + 0.5) / (double)(float)prm.H) * (double)hw - 1;
+        const_cast<float*>(prm.dy_tab)[i] = (float)v;
+    }
+    if (i < prm.n_spheres_pad) {
+        float4 out = make_float4(0.f, 0.f, ORE_BIG, 0.f);  // padding: never a candidate
+        if (i < prm.n_spheres) {
+            const float4 s = prm.sph_exact[i];
+            // L exactly as the reference forms it (float), then the filter works in double
+            const double Lx = (double)(prm.Ox - s.x), Ly = (double)(prm.Oy - s.y), Lz = (double)(prm.Oz - s.z);
+            const double LL = Lx * Lx + Ly * Ly + Lz * Lz;
+            const double r4 = (double)(s.w * s.w);
+            const double Cm = LL * (1.0 - ORE_KAPPA_PRIMARY) - r4 * (1.0 + ORE_KAPPA_PRIMARY);
+            if (!(Cm > 1e-9 * LL) || !(Cm > 1e-30)) {
+                out = make_float4(0.f, 0.f, -ORE_BIG, 0.f);  // origin in/near the sphere: always exact
+            } else {
+                const double sv = sqrt(Cm);
+                const double cp = prm.cp, sp = prm.sp, cy = prm.cy, sy = prm.sy;
+                const double Mx = cy * Lx - sy * Lz;
+                const double My = sp * sy * Lx + cp * Ly + sp * cy * Lz;
+                const double Mz = cp * sy * Lx - sp * Ly + cp * cy * Lz;
+                out = make_float4((float)(Mx / sv), (float)(My / sv), (float)((double)prm.fz * Mz / sv), 0.f);
+            }
+        }
+        prm.sph_prim[i] = out;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// sphere tile pipeline: chunks of `chunk` float4 records, `stages` shared-memory slots,
+// filled by TMA bulk copies that complete on an mbarrier.  Resident mode (whole array in
+// one slot) loads once per CTA; streaming mode re-streams the chunks for every batch.
+// ------------------------------------------------------------------------------------
+struct TilePipe {
+    float4* slots;
+    uint64_t* bars;
+    const float4* src;
+    int chunk, stages, n_chunks, n_pad;
+    uint32_t phase_bits;
+    bool resident, loaded;
+
+    __device__ __forceinline__ int count(int c) const {
+        int rem = n_pad - c * chunk;
+        return rem < chunk ? rem : chunk;
+    }
+    __device__ __forceinline__ void issue(int c) {  // one thread
+        const int st = c % stages;
+        const uint32_t bytes = (uint32_t)count(c) * 16u;
+        mbar_expect_tx(&bars[st], bytes);
+        tma_bulk_g2s(slots + (size_t)st * chunk, src + (size_t)c * chunk, bytes, &bars[st]);
+    }
+    // start of a round (one pass over all chunks)
+    __device__ __forceinline__ void begin_round() {
+        if (resident && loaded) return;
+        if (threadIdx.x == 0) {
+            const int n0 = n_chunks < stages ? n_chunks : stages;
+            for (int c = 0; c < n0; c++) issue(c);
+        }
+    }
+    __device__ __forceinline__ const float4* acquire(int c) {
+        const int st = c % stages;
+        if (!(resident && loaded)) {
+            mbar_wait(&bars[st], (phase_bits >> st) & 1u);
+            phase_bits ^= (1u << st);
+        }
+        return slots + (size_t)st * chunk;
+    }
+    // all threads of the CTA must call this after consuming chunk c
+    __device__ __forceinline__ void release(int c) {
+        if (resident) {
+            loaded = true;
+            return;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && c + stages < n_chunks) issue(c + stages);
+    }
+};
+
+__device__ __forceinline__ void pipe_init(TilePipe& tp, const FrameParams& prm, const float4* src, float4* slots,
+                                          uint64_t* bars) {
+    tp.slots = slots;
+    tp.bars = bars;
+    tp.src = src;
+    tp.chunk = prm.chunk;
+    tp.stages = prm.stages;
+    tp.n_chunks = prm.n_chunks;
+    tp.n_pad = prm.n_spheres_pad;
+    tp.phase_bits = 0;
+    tp.resident = prm.resident != 0;
+    tp.loaded = false;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < prm.stages; s++) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------
+// primary_kernel
+// ------------------------------------------------------------------------------------
+template <int P>
+__global__ void __launch_bounds__(CTA_THREADS) primary_kernel(const FrameParams prm) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bars[MAX_STAGES];
+    __shared__ uint32_t warp_tot[CTA_WARPS];
+    __shared__ uint32_t cta_base;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    TilePipe tp;
+    pipe_init(tp, prm, prm.sph_prim, reinterpret_cast<float4*>(smem_raw), bars);
+
+    const int strip_px = 32 * P;
+    const int strips_per_row = (prm.W + strip_px - 1) / strip_px;
+    const int total_strips = prm.n_rows * strips_per_row;
+    const int n_batches = (total_strips + CTA_WARPS - 1) / CTA_WARPS;
+    const v3 O = mk(prm.Ox, prm.Oy, prm.Oz);
+    const bool exhaustive = (prm.flags & 1u) != 0;
+    unsigned long long n_exact = 0;
+
+    for (int batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
+        const int strip = batch * CTA_WARPS + warp;
+        const bool strip_ok = strip < total_strips;
+        const int k = strip_ok ? strip / strips_per_row : 0;
+        const int sx = strip_ok ? strip % strips_per_row : 0;
+        const float dy = prm.dy_tab[k];
+
+        float dxp[P], negn[P], best_t[P];
+        int best_id[P];
+        v3 D[P];
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+            const int x = sx * strip_px + p * 32 + lane;
+            const bool ok = strip_ok && x < prm.W;
+            dxp[p] = ok ? prm.dx_tab[x] : 0.f;
+            D[p] = primary_dir(prm, dxp[p], dy);
+            // filter threshold: candidate iff g' <= -|v| (shrunk a little: more candidates)
+            const float nv = sqrtf(fmaf(dxp[p], dxp[p], fmaf(dy, dy, prm.fz * prm.fz)));
+            negn[p] = ok ? (exhaustive ? INFINITY : -nv * 0.99999905f) : -INFINITY;
+            best_t[p] = INFINITY;
+            best_id[p] = -1;
+        }
+
+        tp.begin_round();
+        for (int c = 0; c < tp.n_chunks; c++) {
+            const float4* tile = tp.acquire(c);
+            const int cnt = tp.count(c);
+            const int base = c * tp.chunk;
+#pragma unroll 1
+            for (int s = 0; s < cnt; s += 4) {
+                const float4 q0 = tile[s], q1 = tile[s + 1], q2 = tile[s + 2], q3 = tile[s + 3];
+                const float e0 = fmaf(dy, q0.y, q0.z), e1 = fmaf(dy, q1.y, q1.z);
+                const float e2 = fmaf(dy, q2.y, q2.z), e3 = fmaf(dy, q3.y, q3.z);
+                bool any = false;
+#pragma unroll
+                for (int p = 0; p < P; p++) {
+                    any |= (fmaf(dxp[p], q0.x, e0) <= negn[p]);
+                    any |= (fmaf(dxp[p], q1.x, e1) <= negn[p]);
+                    any |= (fmaf(dxp[p], q2.x, e2) <= negn[p]);
+                    any |= (fmaf(dxp[p], q3.x, e3) <= negn[p]);
+                }
+                if (any) {
+                    // exact re-adjudication in ascending sphere index (strict '<' keeps the
+                    // lowest index on ties, kernel.cu:1335)
+#pragma unroll 1
+                    for (int u = 0; u < 4; u++) {
+                        const int idx = base + s + u;
+                        if (idx >= prm.n_spheres) break;
+                        const float4 q = tile[s + u];
+                        const float e = fmaf(dy, q.y, q.z);
+                        float4 ex = make_float4(0.f, 0.f, 0.f, 0.f);
+                        bool have = false;
+#pragma unroll
+                        for (int p = 0; p < P; p++) {
+                            if (fmaf(dxp[p], q.x, e) <= negn[p]) {
+                                if (!have) {
+                                    ex = __ldg(&prm.sph_exact[idx]);
+                                    have = true;
+                                }
+                                float t;
+                                n_exact++;
+                                if (ref_intersect(O, D[p], ex.x, ex.y, ex.z, ex.w, t)) {
+                                    if (t < best_t[p]) {
+                                        best_t[p] = t;
+                                        best_id[p] = idx;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            tp.release(c);
+        }
+
+        // ---- epilogue: records, sky for misses, hit-list compaction ----
+        uint32_t warp_hits = 0;   // warp-uniform
+        uint32_t my_off[P];
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+            const int x = sx * strip_px + p * 32 + lane;
+            const bool ok = strip_ok && x < prm.W;
+            const bool hit = ok && best_id[p] >= 0;
+            if (ok) {
+                const size_t o = (size_t)k * prm.W + x;
+                prm.hit_id[o] = best_id[p];
+                prm.hit_t[o] = best_t[p];
+                if (!hit) {
+                    // skybox::getFColor, kernel.cu:1146-1166
+                    float t;
+                    ref_intersect(O, D[p], 0.f, 0.f, 0.f, prm.sky_radius, t);
+                    v3 hp = ref_add(O, ref_scale(D[p], t));
+                    v3 n = ref_sub(hp, mk(0.f, 0.f, 0.f));
+                    ref_normalise(n);
+                    int tx = (int)((1.f + atan2f(n.z, n.x) / 3.1415f) * 0.5f * (float)prm.sky_w);
+                    int ty = (int)(acosf(n.y) / 3.1415f * (float)prm.sky_h);
+                    int index = clamp_index(ty * prm.sky_w + tx, prm.sky_w * prm.sky_h);
+                    float r = __ldg(&prm.sky_r[index]), g = __ldg(&prm.sky_g[index]), b = __ldg(&prm.sky_b[index]);
+                    prm.pixels[o] = ref_rgb_to_int((int)(r * 254.f), (int)(g * 254.f), (int)(b * 254.f));
+                }
+            }
+            // hit-list order inside a warp: p-major, then lane => 32 neighbouring pixels stay together
+            const uint32_t bal = __ballot_sync(0xffffffffu, hit);
+            my_off[p] = warp_hits + __popc(bal & ((1u << lane) - 1u));
+            warp_hits += __popc(bal);
+        }
+        // CTA-level compaction: one global atomic per batch
+        if (lane == 0) warp_tot[warp] = warp_hits;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t tot = 0;
+            for (int w = 0; w < CTA_WARPS; w++) {
+                uint32_t v = warp_tot[w];
+                warp_tot[w] = tot;
+                tot += v;
+            }
+            cta_base = tot ? (uint32_t)atomicAdd(&prm.counters[CNT_HITS], (unsigned long long)tot) : 0u;
+        }
+        __syncthreads();
+        const uint32_t wbase = cta_base + warp_tot[warp];
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+            const int x = sx * strip_px + p * 32 + lane;
+            if (strip_ok && x < prm.W && best_id[p] >= 0) prm.hit_list[wbase + my_off[p]] = (uint32_t)((size_t)k * prm.W + x);
+        }
+        __syncthreads();  // warp_tot / cta_base reuse
+    }
+    if (n_exact) atomicAdd(&prm.counters[CNT_EXACT_PRIMARY], n_exact);
+}
+
+// ------------------------------------------------------------------------------------
+// shadow ray directions of one light: castLightRay set-up, kernel.cu:1438-1468.
+// Writes 10 directions to dir[] and returns a = dot(normal, toL) with the toL left
+// after the loop (kernel.cu:1541).  toL is re-normalised in place twice per sample.
+// ------------------------------------------------------------------------------------
+__device__ __noinline__ float light_directions(const LightP L, const v3 start, const v3 normal,
+                                               float* __restrict__ dir /* [10][3] */) {
+    const v3 lpos = mk(L.px, L.py, L.pz);
+    v3 tmp = ref_sub(lpos, start);
+    v3 toL = ref_normalise(tmp);
+    const v3 up = mk(0.f, 1.f, 0.f), fwd = mk(0.f, 0.f, 1.f);
+#pragma unroll 1
+    for (int j = 0; j < 10; j++) {
+        v3 P = ref_cross(toL, up);
+        v3 e = ref_sub(ref_add(lpos, ref_scale(P, L.size)), start);
+        v3 toEdge = ref_normalise(e);
+        float angle = cosf((ref_dot(toL, toEdge)) * 2);
+        float _z = (float)j / 10 * (1.0f - angle) + angle;
+        float sq = sqrtf(1.f - _z * _z);
+        float x = sq * c_cos_phi[j];
+        float y = sq * c_sin_phi[j];
+        v3 n1 = ref_normalise(toL);
+        v3 ax = ref_cross(fwd, n1);
+        v3 axis = ref_normalise(ax);
+        v3 n2 = ref_normalise(toL);
+        float nAngle = acosf(ref_dot(n2, fwd));
+        v3 nd = ref_sub(lpos, ref_rotate_apply(nAngle, axis, mk(x, y, _z)));
+        v3 nn = ref_normalise(nd);
+        dir[j * 3 + 0] = nn.x;
+        dir[j * 3 + 1] = nn.y;
+        dir[j * 3 + 2] = nn.z;
+    }
+    return ref_dot(normal, toL);
+}
+
+// ------------------------------------------------------------------------------------
+// shadow_kernel
+// ------------------------------------------------------------------------------------
+template <int NL>
+__global__ void __launch_bounds__(CTA_THREADS, 2) shadow_kernel(const FrameParams prm) {
+    constexpr int NR = 10 * NL;
+    constexpr uint32_t ALL = (NR == 32) ? 0xffffffffu : ((1u << NR) - 1u);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bars[MAX_STAGES];
+    __shared__ int s_batch;
+
+    const int tid = threadIdx.x;
+    TilePipe tp;
+    pipe_init(tp, prm, prm.sph_shad, reinterpret_cast<float4*>(smem_raw), bars);
+
+    const uint32_t n_items = (uint32_t)prm.counters[CNT_HITS];
+    const bool exhaustive = (prm.flags & 1u) != 0;
+    const v3 O0 = mk(prm.Ox, prm.Oy, prm.Oz);
+    unsigned long long n_exact = 0;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_batch = (int)atomicAdd(&prm.counters[CNT_SHADOW_CURSOR], 1ull);
+        __syncthreads();
+        const uint32_t batch = (uint32_t)s_batch;
+        if ((unsigned long long)batch * CTA_THREADS >= n_items) break;
+        const uint32_t item = batch * CTA_THREADS + tid;
+        const bool valid = item < n_items;
+
+        // ---- shading set-up (kernel.cu:1396-1405, 1643-1655) ----
+        uint32_t o = 0;
+        v3 start = mk(1e9f, 1e9f, 1e9f), normal = mk(0.f, 0.f, 0.f);
+        float tr = 0.f, tg = 0.f, tb = 0.f;
+        if (valid) {
+            o = prm.hit_list[item];
+            const int k = (int)(o / (uint32_t)prm.W), x = (int)(o % (uint32_t)prm.W);
+            const v3 D = primary_dir(prm, prm.dx_tab[x], prm.dy_tab[k]);
+            const float nt = prm.hit_t[o];
+            const float4 sc = __ldg(&prm.sph_exact[prm.hit_id[o]]);
+            const v3 new_org = ref_add(O0, ref_scale(D, nt));
+            normal = ref_sub(new_org, mk(sc.x, sc.y, sc.z));
+            ref_normalise(normal);
+            const float txf = (float)((1 + (double)atan2f(normal.z, normal.x) / 3.1415) * 0.5);
+            const float tyf = (float)((double)acosf(normal.y) / 3.1415);
+            const int maxX = prm.tex_w, maxY = prm.tex_h;
+            start = ref_add(ref_scale(normal, 0.00001f), new_org);
+            int c_index = (int)(tyf * (float)maxY) * maxX + (int)(txf * (float)maxX);
+            c_index = clamp_index(c_index, maxX * maxY);
+            tr = __ldg(&prm.tex_r[c_index]);
+            tg = __ldg(&prm.tex_g[c_index]);
+            tb = __ldg(&prm.tex_b[c_index]);
+        }
+        float fr = 0.f, fg = 0.f, fb = 0.f;
+
+        for (int l0 = 0; l0 < prm.n_lights; l0 += NL) {
+            float dx[NR], dy[NR], dz[NR], a_l[NL];
+            uint32_t blocked = ALL;
+            {
+                float dir[30];
+#pragma unroll
+                for (int l = 0; l < NL; l++) {
+                    const bool lit = valid && (l0 + l) < prm.n_lights;
+                    a_l[l] = 0.f;
+                    if (lit) {
+                        a_l[l] = light_directions(prm.lights[l0 + l], start, normal, dir);
+                        blocked &= ~(0x3ffu << (10 * l));
+                    }
+#pragma unroll
+                    for (int j = 0; j < 10; j++) {
+                        dx[l * 10 + j] = lit ? dir[j * 3 + 0] : 0.f;
+                        dy[l * 10 + j] = lit ? dir[j * 3 + 1] : 0.f;
+                        dz[l * 10 + j] = lit ? dir[j * 3 + 2] : 0.f;
+                    }
+                }
+            }
+
+            // ---- any-hit over all spheres (kernel.cu:1501-1510), filter + exact ----
+            tp.begin_round();
+            bool warp_done = false;
+            for (int c = 0; c < tp.n_chunks; c++) {
+                const float4* tile = tp.acquire(c);
+                const int cnt = tp.count(c);
+                const int base = c * tp.chunk;
+                if (!warp_done) {
+#pragma unroll 1
+                    for (int s = 0; s < cnt; s += 2) {
+                        int trig[2];
+                        float Lxs[2], Lys[2], Lzs[2], svs[2];
+#pragma unroll
+                        for (int u = 0; u < 2; u++) {
+                            const float4 q = tile[s + u];
+                            const float Lx = start.x - q.x, Ly = start.y - q.y, Lz = start.z - q.z;
+                            const float LL = fmaf(Lz, Lz, fmaf(Ly, Ly, Lx * Lx));
+                            const float Cm = fmaf(LL, 1.0f - ORE_KAPPA_SHADOW, -q.w);
+                            float sv = Cm * rsqrt_approx(Cm);
+                            sv = (Cm > 1e-20f) ? sv : -ORE_BIG;
+                            if (exhaustive) sv = -ORE_BIG;
+                            int acc = 0;
+#pragma unroll
+                            for (int j = 0; j < NR; j++) {
+                                const float h = fmaf(dx[j], Lx, fmaf(dy[j], Ly, fmaf(dz[j], Lz, sv)));
+                                acc |= __float_as_int(h);
+                            }
+                            trig[u] = acc;
+                            Lxs[u] = Lx;
+                            Lys[u] = Ly;
+                            Lzs[u] = Lz;
+                            svs[u] = sv;
+                        }
+                        if (((trig[0] | trig[1]) < 0) && blocked != ALL) {
+#pragma unroll 1
+                            for (int u = 0; u < 2; u++) {
+                                const int idx = base + s + u;
+                                if (trig[u] >= 0 || idx >= prm.n_spheres) continue;
+                                const float4 ex = __ldg(&prm.sph_exact[idx]);
+                                const float Lx = Lxs[u], Ly = Lys[u], Lz = Lzs[u], sv = svs[u];
+#pragma unroll
+                                for (int j = 0; j < NR; j++) {
+                                    if (!((blocked >> j) & 1u)) {
+                                        const float h = fmaf(dx[j], Lx, fmaf(dy[j], Ly, fmaf(dz[j], Lz, sv)));
+                                        if (h < 0.f) {
+                                            n_exact++;
+                                            if (ref_intersect_call(start.x, start.y, start.z, dx[j], dy[j], dz[j], ex)) {
+                                                blocked |= (1u << j);
+                                                dx[j] = 0.f;
+                                                dy[j] = 0.f;
+                                                dz[j] = 0.f;
+                                            }
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                        if ((s & 6) == 6) {
+                            if (__all_sync(0xffffffffu, blocked == ALL)) {
+                                warp_done = true;
+                                break;
+                            }
+                        }
+                    }
+                }
+                tp.release(c);
+            }
+
+            // ---- light accumulation (kernel.cu:1537-1543, 1673-1675) ----
+            if (valid) {
+#pragma unroll
+                for (int l = 0; l < NL; l++) {
+                    if (l0 + l < prm.n_lights) {
+                        float b = 0;
+#pragma unroll
+                        for (int j = 0; j < 10; j++)
+                            if (!((blocked >> (l * 10 + j)) & 1u)) b = (float)((double)b + 0.1);
+                        const float a = a_l[l];
+                        b *= a > 0 ? a : 0;
+                        const LightP L = prm.lights[l0 + l];
+                        fr += b * L.r * tr;
+                        fg += b * L.g * tg;
+                        fb += b * L.b * tb;
+                    }
+                }
+            }
+        }
+        if (valid) prm.pixels[o] = ref_rgb_to_int((int)(fr * 254.f), (int)(fg * 254.f), (int)(fb * 254.f));
+    }
+    if (n_exact) atomicAdd(&prm.counters[CNT_EXACT_SHADOW], n_exact);
+}
+
+}  // namespace ore
