@@ -1,0 +1,391 @@
+#!/usr/bin/env python3
+"""bench.py - Mrays/s of the render hot path on N B200s (one process per GPU).
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference's own CPU code on the host cores
+
+A "step" is one frame: one pass of the hot path (frame prep -> primary nearest hit -> shadow +
+shade -> packed framebuffer) over one camera of the orbit.  Default workload = BASELINE.json
+configs[2] (3840x2160, 1024 spheres, 240-frame orbit): the configuration the north_star quotes
+its single-GPU target on.  With N > 1 the SAME frame is split into interleaved row bands
+(strong scaling) that the ranks store straight into the presenting GPU's framebuffer over
+NVLink (peer-mapped), plus one tiny NCCL all-reduce per frame as the completion signal.
+
+Prints ONE JSON line on rank 0 (contract in the task statement): value = whole-job Mrays/s with
+inputs resident in HBM; e2e = the same through the C ABI with HOST output buffers; roofline =
+FP32 accounting of the dominant kernel; cpu_baseline = the CPU checker timed on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (W, H, n_spheres, seed, kind, description)
+    "vga64": (640, 480, 64, 1, "reference", "configs[0]: 640x480, reference-formula scene R(64,1), reference camera"),
+    "1080p64": (1920, 1080, 64, 2, "scaled", "configs[1]: 1920x1080, 64 random spheres S(64,2), orbit"),
+    "4k1024": (3840, 2160, 1024, 3, "scaled", "configs[2]: 3840x2160, 1024 random spheres S(1024,3), 240-frame camera orbit"),
+    "8k1024": (7680, 4320, 1024, 3, "scaled", "configs[3]: 7680x4320, 1024 spheres S(1024,3), row bands"),
+    "4k16384": (3840, 2160, 16384, 5, "scaled", "configs[4]: 3840x2160, 16384 spheres S(16384,5)"),
+}
+FLOP_PER_TEST = 18
+NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
+
+
+def make_workload(pkg, name):
+    W, H, n, seed, kind, desc = WORKLOADS[name]
+    sc = pkg.scene.reference_scene(n, seed) if kind == "reference" else pkg.scene.scaled_scene(n, seed)
+
+    def camera(frame):
+        return pkg.scene.reference_camera() if kind == "reference" else pkg.scene.orbit_camera(sc, frame % 240)
+
+    return W, H, sc, camera, desc
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (profiling recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for i, n in enumerate(names):
+                if f[5 + i].lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    return rank, local, world
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's own CPU code (oracle/_ref) or its C restatement
+# ---------------------------------------------------------------------------------------------
+def cpu_sample_plan(orc, sc, cam, W, H, budget_s):
+    """pick a row stride so that one sample costs about `budget_s` seconds on the host cores"""
+    probe_step = max(1, H // 8)
+    t0 = time.perf_counter()
+    orc.render(sc, cam, W, H, y0=probe_step // 2, y_step=probe_step, want_ids=False, want_t=False)
+    dt = time.perf_counter() - t0
+    rows_probe = (H - probe_step // 2 + probe_step - 1) // probe_step
+    per_row = dt / max(1, rows_probe)
+    rows = int(max(1, min(H, budget_s / max(per_row, 1e-9))))
+    step = max(1, H // rows)
+    return step
+
+
+def run_cpu(args, pkg, what):
+    """times the CPU checker on a bounded sample; returns (mrays, info)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oraclelib  # the one place bench.py executes oracle/ (cpu_baseline + --impl reference)
+
+    orc = oraclelib.load("best")
+    W, H, sc, camera, desc = make_workload(pkg, args.workload)
+    cores = os.cpu_count() or 1
+    n_steps = args.steps if what == "reference" else 1
+    n_warm = args.warmup if what == "reference" else 0
+    budget = min(10.0, 150.0 / max(1, n_steps + n_warm)) if what == "reference" else 12.0
+    step = cpu_sample_plan(orc, sc, camera(0), W, H, budget)
+    y0 = step // 2
+    rows = (H - y0 + step - 1) // step
+    times = []
+    for i in range(n_warm + n_steps):
+        cam = camera(i if what == "reference" else 0)
+        t0 = time.perf_counter()
+        orc.render(sc, cam, W, H, y0=y0, y_step=step, want_ids=False, want_t=False)
+        dt = time.perf_counter() - t0
+        if i >= n_warm:
+            times.append(dt)
+    total = sum(times)
+    mrays = rows * W * len(times) / total / 1e6
+    info = {"value": mrays, "unit": "Mrays/s", "cores": cores, "kind": orc.kind,
+            "sample": f"rows {y0}::{step} of each {W}x{H} frame ({rows} rows, {rows * W} primary rays per step, "
+                      f"{len(times)} step(s), {total:.1f} s), all {cores} host threads (OpenMP)"}
+    return mrays, info, total / len(times)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="4k1024", choices=sorted(WORKLOADS))
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank, local, world = dist_env()
+
+    import rte_b200
+    pkg = rte_b200.pkg
+    W, H, sc, camera, desc = make_workload(pkg, args.workload)
+    config = {"workload": desc, "width": W, "height": H, "n_spheres": sc.n_spheres, "n_lights": int(sc.lights.shape[0]),
+              "rays_per_pixel": 1, "scene": sc.name}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        mrays, info, sec = run_cpu(args, pkg, "reference")
+        line = {"impl": "reference", "metric": "Mrays/s (primary rays)", "value": mrays, "unit": "Mrays/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config, "cpu_baseline": info,
+                "e2e": {"value": mrays, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ---------------- our arm ----------------
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the render path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pkg.build.build_library()
+    r = pkg.Renderer(local)
+    r.set_scene(sc)
+    stream = torch.cuda.Stream(device=local)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")  # > 126 MB L2
+    sync_t = torch.zeros(1, dtype=torch.int32, device=f"cuda:{local}")
+
+    peer = None
+    gatherer = None
+    if world > 1 and args.gather == "nccl":
+        gatherer = pkg.multigpu.BandGatherer(W, H, torch.device("cuda", local))
+    else:
+        peer = pkg.multigpu.PeerFrame(r, W, H, n_buffers=2)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def render_step(f):
+        """device-resident step: this rank's rows of frame f into the presenter's framebuffer"""
+        cam = camera(f)
+        with torch.cuda.stream(stream):
+            if peer is not None:
+                r.render_device(cam, W, H, stream=stream.cuda_stream, **peer.band_args(f % 2))
+                if world > 1:
+                    dist.all_reduce(sync_t)  # completion signal: every rank's rows of frame f have landed
+            else:
+                plan = gatherer.plan
+                r.render_device(cam, W, H, out_ptr=gatherer.band.data_ptr(), stream=stream.cuda_stream,
+                                y0=plan.y0, y1=H, y_step=plan.y_step)
+                gatherer.gather()
+
+    def flush_l2():
+        with torch.cuda.stream(stream):
+            flush.fill_(1)
+
+    # warm-up
+    for f in range(args.warmup):
+        render_step(f)
+    barrier()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    kernel_ms = []
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    barrier()
+    for i in range(args.steps):
+        flush_l2()
+        starts[i].record(stream)
+        render_step(args.warmup + i)
+        ends[i].record(stream)
+        ends[i].synchronize()
+        kernel_ms.append(r.kernel_ms())
+    barrier()
+    clocks = sampler.stop()
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    value = W * H * args.steps / (total_ms * 1e-3) / 1e6
+
+    # ---- e2e: through the C ABI with HOST output, device->host copy inside the timed region ----
+    host = np.empty((H, W), dtype=np.uint32) if rank == 0 else None
+    band_host = None
+
+    def e2e_step(f):
+        cam = camera(f)
+        if world == 1:
+            r.render(cam, W, H, out=host)        # ore_render: kernels + D2H of the frame, synchronous
+        else:
+            render_step(f)
+            stream.synchronize()
+            if rank == 0:
+                if peer is not None:
+                    r.copy_to_host(host, peer.ptrs[f % 2])
+                else:
+                    host[:] = gatherer.frame.cpu().numpy().view(np.uint32)
+
+    for f in range(2):
+        e2e_step(f)
+    barrier()
+    e2e_t = 0.0
+    for i in range(args.steps):
+        flush_l2()
+        barrier()
+        t0 = time.perf_counter()
+        e2e_step(args.warmup + i)
+        if world > 1:
+            dist.barrier()
+        e2e_t += time.perf_counter() - t0
+    e2e_tt = torch.tensor([e2e_t], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(e2e_tt, op=dist.ReduceOp.MAX)
+    e2e_value = W * H * args.steps / float(e2e_tt.item()) / 1e6
+
+    # ---- roofline accounting (untimed): reference-order test counts of the SAME frames ----
+    own = {"primary": 0.0, "shadow": 0.0, "sky": 0.0, "hits": 0.0}
+    count_out = peer.ptrs[0] + 4 * W * rank if peer is not None else gatherer.band.data_ptr()
+    for i in range(args.steps):
+        r.render_device(camera(args.warmup + i), W, H, out_ptr=count_out, y0=rank, y1=H, y_step=world,
+                        out_pitch=(world * W if peer is not None else 0),
+                        flags=pkg.capi.ORE_FLAG_COUNT_REFERENCE_TESTS)
+        c = r.counters()
+        own["primary"] += c["primary_tests"]
+        own["shadow"] += c["shadow_tests_ref"]
+        own["sky"] += c["sky_tests"]
+        own["hits"] += c["hit_pixels"]
+    counts = torch.tensor([own["primary"], own["shadow"], own["sky"], own["hits"]], dtype=torch.float64,
+                          device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(counts)
+    tests_primary, tests_shadow, tests_sky, hits = [float(v) for v in counts.tolist()]
+    peak_tf, nominal_mhz = r.measure_fp32_peak()
+    # dominant kernel = shadow kernel; roofline of rank 0's own launches against rank 0's own tests
+    k_shadow_ms = statistics.mean(m[2] for m in kernel_ms)
+    k_primary_ms = statistics.mean(m[1] for m in kernel_ms)
+    k_prep_ms = statistics.mean(m[0] for m in kernel_ms)
+    own_shadow = own["shadow"]
+    shadow_flop_per_launch = FLOP_PER_TEST * own_shadow / args.steps
+    achieved_tf = shadow_flop_per_launch / (k_shadow_ms * 1e-3) / 1e12
+    step_flop = FLOP_PER_TEST * (tests_primary + tests_shadow + tests_sky) / args.steps
+    step_tf = step_flop / (total_ms / args.steps * 1e-3) / 1e12
+
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.isfile(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(args.workload, {}).get("shadow_kernel_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            _, cpu, _ = run_cpu(args, pkg, "cpu_baseline")
+        line = {
+            "metric": "Mrays/s (primary rays)", "value": value, "unit": "Mrays/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": dict(config, l2="flushed between steps (256 MiB fill, untimed; per-step CUDA events summed)",
+                           parallelism=(f"row-bands x{world} (interleaved rows), presenter = rank 0, gather = {args.gather}"
+                                        if world > 1 else "1 GPU"),
+                           hit_pixel_fraction=hits / (W * H * args.steps),
+                           tests_per_pixel={"primary": tests_primary / (W * H * args.steps),
+                                            "shadow_reference_order": tests_shadow / (W * H * args.steps)}),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 36 + 32,
+                    "d2h_bytes_per_step": W * H * 4,
+                    "note": "ore_render with a host framebuffer (N=1) / peer-written frame + D2H on the presenter (N>1); "
+                            "inputs per step are the 36-byte camera and the 32-byte frame descriptor"},
+            "gpu_launches": 3 * args.steps,
+            "roofline": {
+                "bound": "fp32", "kernel": "shadow_kernel<3> (soft-shadow any-hit + shading)",
+                "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None,
+                "traffic": traffic,
+                "peak_source": "measured: FFMA burn on this GPU in this run (MEASURED_PEAKS.json carries HBM and bf16 only); "
+                               f"nominal 148 SM x 128 lanes x 2 x 1.965 GHz = {NOMINAL_FP32_TFLOPS:.2f}",
+                "flop_per_test": FLOP_PER_TEST,
+                "tests_per_launch": own_shadow / args.steps,
+                "kernel_ms": k_shadow_ms,
+                "definition": "achieved = 18 FLOP x reference-order sphere tests of the launch / CUDA-event kernel time. "
+                              "The kernel shares L=O-c and C across a pixel's 30 shadow rays and filters with 3 FMA/test, "
+                              "so it EXECUTES fewer FLOP than the reference formula counts: frac can exceed 1 and is an "
+                              "algorithmic-work rate, not pipe utilisation (see fma_pipe_utilisation in profiles/).",
+                "whole_step": {"achieved": step_tf, "frac": step_tf / peak_tf if peak_tf else None,
+                               "frac_of_nominal": step_tf / NOMINAL_FP32_TFLOPS},
+                "kernel_ms_all": {"prep": k_prep_ms, "primary": k_primary_ms, "shadow": k_shadow_ms},
+                "dram_write_gbs_framebuffer": W * H * 4 / world / ((k_primary_ms + k_shadow_ms) * 1e-3) / 1e9,
+            },
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if peer is not None:
+        peer.close()
+    r.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

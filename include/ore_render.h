@@ -68,6 +68,9 @@ typedef struct ore_frame {
     int32_t y0, y1, y_step; /* full frame: 0, height, 1 */
     float aspect;           /* the global `aspect`, kernel.cu:1701 */
     uint32_t flags;         /* ore_flags */
+    int32_t out_pitch;      /* output row pitch in pixels; 0 = width (packed).  A rank that
+                               renders rows r, r+P, ... straight into the presenter's frame
+                               passes base = frame + r*width and out_pitch = P*width. */
 } ore_frame;
 
 /* counters of the last ore_render* call */
@@ -126,6 +129,19 @@ int ore_render_device(ore_context* ctx, const ore_camera* cam, const ore_frame* 
                       uint32_t* out_device, void* stream);
 int ore_synchronize(ore_context* ctx);
 
+/* ---- device buffers for multi-GPU presentation --------------------------------------
+ * The reference has one GPU and one managed `pixels` buffer per frame (kernel.cu:1775).
+ * With row bands over several GPUs (one process each) the presenting GPU owns the frame;
+ * it is exported with CUDA IPC so the other ranks' kernels store their rows into it
+ * directly over NVLink (ore_render_device with out_pitch).  Plain cudaMalloc memory. */
+int ore_dev_alloc(ore_context* ctx, size_t bytes, void** dev_ptr);
+int ore_dev_free(ore_context* ctx, void* dev_ptr);
+int ore_ipc_export(ore_context* ctx, void* dev_ptr, unsigned char handle[64]);
+int ore_ipc_import(ore_context* ctx, const unsigned char handle[64], void** dev_ptr);
+int ore_ipc_close(ore_context* ctx, void* dev_ptr);
+/* device -> host copy on the context's stream, synchronous (the setPixelBuff copy) */
+int ore_copy_to_host(ore_context* ctx, void* host_dst, const void* dev_src, size_t bytes);
+
 /* ---- introspection of the LAST render (parity tests, roofline accounting) ---------
  * hit_id: nearest sphere index or -1 (castRay, kernel.cu:1330-1342); hit_t: nearest t,
  * +inf on miss.  Packed like the pixels.  Either pointer may be NULL. */
@@ -134,6 +150,9 @@ int ore_get_counters(ore_context* ctx, ore_counters* out);
 /* average device time (ms) of each kernel of the last render, measured with CUDA events
  * on the launching stream: [0] frame prep, [1] primary, [2] shadow+shade, [3] count */
 int ore_get_kernel_ms(ore_context* ctx, float ms[4]);
+/* Measures the FP32 roofline denominator on this GPU with an FFMA burn (TFLOP/s, best of 5)
+ * and returns the nominal SM clock; used by bench.py only. */
+int ore_measure_fp32_peak(ore_context* ctx, double* tflops, double* sm_clock_mhz_nominal);
 
 #ifdef __cplusplus
 }

@@ -5,5 +5,6 @@ Only what the path needs: `csrc/` (sm_100a kernels + the C ABI of include/ore_re
 `scene.py` (harness-defined synthetic inputs), `capi.py` (ctypes over the C ABI) and
 `multigpu.py` (row-band sharding across the GPUs of one box).
 """
-from . import build, scene  # noqa: F401
-from .capi import OreError, Renderer, load_library  # noqa: F401
+from . import build, multigpu, scene  # noqa: F401
+from . import capi  # noqa: F401,E402
+from .capi import OreError, Renderer, load_library  # noqa: F401,E402

@@ -20,7 +20,8 @@ EXPORTS = [
     "ore_create", "ore_destroy", "ore_abi_version", "ore_last_error",
     "ore_set_spheres", "ore_set_spheres_aos32", "ore_set_lights", "ore_set_texture", "ore_set_sky",
     "ore_render", "ore_render_device", "ore_synchronize",
-    "ore_get_hits", "ore_get_counters", "ore_get_kernel_ms",
+    "ore_get_hits", "ore_get_counters", "ore_get_kernel_ms", "ore_measure_fp32_peak",
+    "ore_dev_alloc", "ore_dev_free", "ore_ipc_export", "ore_ipc_import", "ore_ipc_close", "ore_copy_to_host",
 ]
 
 
@@ -31,7 +32,7 @@ class OreCamera(C.Structure):
 
 class OreFrame(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("y0", C.c_int32), ("y1", C.c_int32),
-                ("y_step", C.c_int32), ("aspect", C.c_float), ("flags", C.c_uint32)]
+                ("y_step", C.c_int32), ("aspect", C.c_float), ("flags", C.c_uint32), ("out_pitch", C.c_int32)]
 
 
 class OreCounters(C.Structure):
@@ -73,6 +74,13 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.ore_get_hits.argtypes = [vp, vp, vp]
     lib.ore_get_counters.argtypes = [vp, C.POINTER(OreCounters)]
     lib.ore_get_kernel_ms.argtypes = [vp, C.POINTER(C.c_float * 4)]
+    lib.ore_measure_fp32_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.ore_dev_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+    lib.ore_dev_free.argtypes = [vp, vp]
+    lib.ore_ipc_export.argtypes = [vp, vp, C.POINTER(C.c_ubyte * 64)]
+    lib.ore_ipc_import.argtypes = [vp, C.POINTER(C.c_ubyte * 64), C.POINTER(vp)]
+    lib.ore_ipc_close.argtypes = [vp, vp]
+    lib.ore_copy_to_host.argtypes = [vp, vp, vp, C.c_size_t]
     for name in EXPORTS:
         if name != "ore_last_error":
             getattr(lib, name).restype = C.c_int
@@ -157,8 +165,9 @@ class Renderer:
         c.yaw, c.pitch = float(camera.yaw), float(camera.pitch)
         return c
 
-    def _frame(self, width, height, y0, y1, y_step, aspect, flags) -> OreFrame:
+    def _frame(self, width, height, y0, y1, y_step, aspect, flags, out_pitch=0) -> OreFrame:
         f = OreFrame()
+        f.out_pitch = int(out_pitch)
         f.width, f.height = int(width), int(height)
         f.y0, f.y1, f.y_step = int(y0), int(height if y1 is None else y1), int(y_step)
         f.aspect = float(self.scene.aspect if aspect is None else aspect)
@@ -175,20 +184,48 @@ class Renderer:
         f = self._frame(width, height, y0, y1, y_step, aspect, flags)
         rows = self.rows(height, y0, y1, y_step)
         if out is None:
-            out = np.empty((rows, width), dtype=np.uint32)
+            out = np.empty((rows, max(0, width)), dtype=np.uint32)
         assert out.dtype == np.uint32 and out.size == rows * width and out.flags["C_CONTIGUOUS"]
         cam = self._cam(camera)
-        self._check(self.lib.ore_render(self.ctx, C.byref(cam), C.byref(f), out.ctypes.data if out.size else None)
-                    if out.size else 0, "ore_render")
+        dummy = C.c_uint32(0)  # an empty band still goes through the ABI's argument checks
+        ptr = out.ctypes.data if out.size else C.addressof(dummy)
+        self._check(self.lib.ore_render(self.ctx, C.byref(cam), C.byref(f), ptr), "ore_render")
         return out
 
     def render_device(self, camera, width, height, out_ptr: int, stream: int = 0, y0=0, y1=None, y_step=1,
-                      aspect=None, flags=0):
+                      aspect=None, flags=0, out_pitch=0):
         """Render into DEVICE memory at `out_ptr` (asynchronous on `stream`)."""
-        f = self._frame(width, height, y0, y1, y_step, aspect, flags)
+        f = self._frame(width, height, y0, y1, y_step, aspect, flags, out_pitch)
         cam = self._cam(camera)
         self._check(self.lib.ore_render_device(self.ctx, C.byref(cam), C.byref(f), C.c_void_p(out_ptr),
                                                C.c_void_p(stream) if stream else None), "ore_render_device")
+
+    # ---- device buffers / IPC (multi-GPU presentation) ----
+    def dev_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self._check(self.lib.ore_dev_alloc(self.ctx, nbytes, C.byref(p)), "ore_dev_alloc")
+        return int(p.value)
+
+    def dev_free(self, ptr: int):
+        self._check(self.lib.ore_dev_free(self.ctx, C.c_void_p(ptr)), "ore_dev_free")
+
+    def ipc_export(self, ptr: int) -> bytes:
+        h = (C.c_ubyte * 64)()
+        self._check(self.lib.ore_ipc_export(self.ctx, C.c_void_p(ptr), C.byref(h)), "ore_ipc_export")
+        return bytes(h)
+
+    def ipc_import(self, handle: bytes) -> int:
+        h = (C.c_ubyte * 64)(*handle)
+        p = C.c_void_p()
+        self._check(self.lib.ore_ipc_import(self.ctx, C.byref(h), C.byref(p)), "ore_ipc_import")
+        return int(p.value)
+
+    def ipc_close(self, ptr: int):
+        self._check(self.lib.ore_ipc_close(self.ctx, C.c_void_p(ptr)), "ore_ipc_close")
+
+    def copy_to_host(self, host: np.ndarray, dev_ptr: int):
+        assert host.flags["C_CONTIGUOUS"]
+        self._check(self.lib.ore_copy_to_host(self.ctx, host.ctypes.data, C.c_void_p(dev_ptr), host.nbytes), "ore_copy_to_host")
 
     def synchronize(self):
         self._check(self.lib.ore_synchronize(self.ctx), "ore_synchronize")
@@ -203,6 +240,12 @@ class Renderer:
         c = OreCounters()
         self._check(self.lib.ore_get_counters(self.ctx, C.byref(c)), "ore_get_counters")
         return {n: int(getattr(c, n)) for n, _ in OreCounters._fields_}
+
+    def measure_fp32_peak(self):
+        """FFMA-burn FP32 peak of this GPU in TFLOP/s and the nominal SM clock in MHz."""
+        tf, mhz = C.c_double(0), C.c_double(0)
+        self._check(self.lib.ore_measure_fp32_peak(self.ctx, C.byref(tf), C.byref(mhz)), "ore_measure_fp32_peak")
+        return tf.value, mhz.value
 
     def kernel_ms(self):
         ms = (C.c_float * 4)()

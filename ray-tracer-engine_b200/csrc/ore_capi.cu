@@ -283,7 +283,8 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
                        cudaStream_t stream) {
     if (!ctx) return ORE_ERR_INVALID;
     if (!cam || !fr) return fail(ctx, ORE_ERR_INVALID, "ore_render: null camera/frame");
-    if (fr->width <= 0 || fr->height <= 0 || fr->y_step <= 0 || fr->y0 < 0 || fr->y1 < fr->y0)
+    if (fr->width <= 0 || fr->height <= 0 || fr->y_step <= 0 || fr->y0 < 0 || fr->y1 < fr->y0 ||
+        (fr->out_pitch != 0 && fr->out_pitch < fr->width))
         return fail(ctx, ORE_ERR_INVALID, "ore_render: bad frame geometry");
     if (!ctx->tex[0] || !ctx->sky[0]) return fail(ctx, ORE_ERR_INVALID, "ore_render: texture and sky must be set first");
     if (!ctx->sph_exact) {
@@ -321,6 +322,7 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
     prm.y0 = fr->y0;
     prm.y_step = fr->y_step;
     prm.n_rows = n_rows;
+    prm.pitch = (out_device && fr->out_pitch > 0) ? fr->out_pitch : W;
     prm.n_spheres = ctx->n_spheres;
     prm.n_spheres_pad = ctx->n_spheres_pad;
     prm.n_lights = ctx->n_lights;
@@ -413,6 +415,13 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
         ctx->last_launches++;
     }
     ORE_CUDA(ctx, cudaEventRecord(ctx->ev[3], stream));
+    if (fr->flags & ORE_FLAG_COUNT_REFERENCE_TESTS) {
+        count_reference_tests_kernel<<<ctx->sm_count * 8, CTA_THREADS, 0, stream>>>(prm);
+        ORE_CUDA(ctx, cudaGetLastError());
+        ctx->last_launches++;
+        ctx->ran_count = true;
+    }
+    ORE_CUDA(ctx, cudaEventRecord(ctx->ev[4], stream));
     ctx->ev_valid = true;
     return ORE_OK;
 }
@@ -443,6 +452,50 @@ extern "C" int ore_synchronize(ore_context* ctx) {
     ORE_CUDA(ctx, cudaSetDevice(ctx->device));
     ORE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ORE_CUDA(ctx, cudaDeviceSynchronize());
+    return ORE_OK;
+}
+
+extern "C" int ore_dev_alloc(ore_context* ctx, size_t bytes, void** dev_ptr) {
+    if (!ctx || !dev_ptr || bytes == 0) return ORE_ERR_INVALID;
+    ORE_CUDA(ctx, cudaSetDevice(ctx->device));
+    ORE_CUDA(ctx, cudaMalloc(dev_ptr, bytes));
+    ORE_CUDA(ctx, cudaMemset(*dev_ptr, 0, bytes));
+    return ORE_OK;
+}
+extern "C" int ore_dev_free(ore_context* ctx, void* dev_ptr) {
+    if (!ctx) return ORE_ERR_INVALID;
+    ORE_CUDA(ctx, cudaSetDevice(ctx->device));
+    ORE_CUDA(ctx, cudaFree(dev_ptr));
+    return ORE_OK;
+}
+extern "C" int ore_ipc_export(ore_context* ctx, void* dev_ptr, unsigned char handle[64]) {
+    if (!ctx || !dev_ptr || !handle) return ORE_ERR_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    ORE_CUDA(ctx, cudaSetDevice(ctx->device));
+    ORE_CUDA(ctx, cudaIpcGetMemHandle(&h, dev_ptr));
+    memcpy(handle, &h, 64);
+    return ORE_OK;
+}
+extern "C" int ore_ipc_import(ore_context* ctx, const unsigned char handle[64], void** dev_ptr) {
+    if (!ctx || !dev_ptr || !handle) return ORE_ERR_INVALID;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    ORE_CUDA(ctx, cudaSetDevice(ctx->device));
+    ORE_CUDA(ctx, cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return ORE_OK;
+}
+extern "C" int ore_ipc_close(ore_context* ctx, void* dev_ptr) {
+    if (!ctx) return ORE_ERR_INVALID;
+    ORE_CUDA(ctx, cudaSetDevice(ctx->device));
+    ORE_CUDA(ctx, cudaIpcCloseMemHandle(dev_ptr));
+    return ORE_OK;
+}
+extern "C" int ore_copy_to_host(ore_context* ctx, void* host_dst, const void* dev_src, size_t bytes) {
+    if (!ctx || !host_dst || !dev_src) return ORE_ERR_INVALID;
+    ORE_CUDA(ctx, cudaSetDevice(ctx->device));
+    ORE_CUDA(ctx, cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ORE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ORE_OK;
 }
 
@@ -481,7 +534,41 @@ extern "C" int ore_get_kernel_ms(ore_context* ctx, float ms[4]) {
     ms[0] = ms[1] = ms[2] = ms[3] = 0.f;
     if (!ctx->ev_valid) return ORE_OK;
     ORE_CUDA(ctx, cudaSetDevice(ctx->device));
-    ORE_CUDA(ctx, cudaEventSynchronize(ctx->ev[3]));
-    for (int i = 0; i < 3; i++) ORE_CUDA(ctx, cudaEventElapsedTime(&ms[i], ctx->ev[i], ctx->ev[i + 1]));
+    ORE_CUDA(ctx, cudaEventSynchronize(ctx->ev[4]));
+    for (int i = 0; i < 4; i++) ORE_CUDA(ctx, cudaEventElapsedTime(&ms[i], ctx->ev[i], ctx->ev[i + 1]));
+    return ORE_OK;
+}
+
+extern "C" int ore_measure_fp32_peak(ore_context* ctx, double* tflops, double* sm_clock_mhz_nominal) {
+    if (!ctx || !tflops) return ORE_ERR_INVALID;
+    ORE_CUDA(ctx, cudaSetDevice(ctx->device));
+    float* d = nullptr;
+    ORE_CUDA(ctx, cudaMalloc((void**)&d, sizeof(float)));
+    const int iters = 4096, grid = ctx->sm_count * 8;
+    cudaEvent_t a, b;
+    ORE_CUDA(ctx, cudaEventCreate(&a));
+    ORE_CUDA(ctx, cudaEventCreate(&b));
+    double best = 0.0;
+    for (int rep = 0; rep < 6; rep++) {
+        ORE_CUDA(ctx, cudaEventRecord(a, ctx->stream));
+        fp32_burn_kernel<<<grid, CTA_THREADS, 0, ctx->stream>>>(d, iters, 1.0000001f, 1e-9f);
+        ORE_CUDA(ctx, cudaGetLastError());
+        ORE_CUDA(ctx, cudaEventRecord(b, ctx->stream));
+        ORE_CUDA(ctx, cudaEventSynchronize(b));
+        float ms = 0.f;
+        ORE_CUDA(ctx, cudaEventElapsedTime(&ms, a, b));
+        const double flop = 2.0 * 16 * 8 * (double)iters * CTA_THREADS * (double)grid;
+        const double tf = flop / (ms * 1e-3) / 1e12;
+        if (rep >= 1 && tf > best) best = tf;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(d);
+    *tflops = best;
+    if (sm_clock_mhz_nominal) {
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device);
+        *sm_clock_mhz_nominal = khz / 1000.0;
+    }
     return ORE_OK;
 }

@@ -45,6 +45,7 @@ struct LightP {
 
 struct FrameParams {
     int W, H, y0, y_step, n_rows;
+    int pitch;  // output row pitch in pixels (pixels[] only; hit records stay packed)
     int n_spheres, n_spheres_pad, n_lights;
     uint32_t flags;
     float aspect, ez, fz;  // ez = -1/aspect (kernel.cu:1629), fz = 0 - ez
@@ -321,7 +322,7 @@ __global__ void __launch_bounds__(CTA_THREADS) primary_kernel(const FrameParams 
                     int ty = (int)(acosf(n.y) / 3.1415f * (float)prm.sky_h);
                     int index = clamp_index(ty * prm.sky_w + tx, prm.sky_w * prm.sky_h);
                     float r = __ldg(&prm.sky_r[index]), g = __ldg(&prm.sky_g[index]), b = __ldg(&prm.sky_b[index]);
-                    prm.pixels[o] = ref_rgb_to_int((int)(r * 254.f), (int)(g * 254.f), (int)(b * 254.f));
+                    prm.pixels[(size_t)k * prm.pitch + x] = ref_rgb_to_int((int)(r * 254.f), (int)(g * 254.f), (int)(b * 254.f));
                 }
             }
             // hit-list order inside a warp: p-major, then lane => 32 neighbouring pixels stay together
@@ -419,11 +420,13 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) shadow_kernel(const FrameParam
 
         // ---- shading set-up (kernel.cu:1396-1405, 1643-1655) ----
         uint32_t o = 0;
+        size_t o_out = 0;
         v3 start = mk(1e9f, 1e9f, 1e9f), normal = mk(0.f, 0.f, 0.f);
         float tr = 0.f, tg = 0.f, tb = 0.f;
         if (valid) {
             o = prm.hit_list[item];
             const int k = (int)(o / (uint32_t)prm.W), x = (int)(o % (uint32_t)prm.W);
+            o_out = (size_t)k * prm.pitch + x;
             const v3 D = primary_dir(prm, prm.dx_tab[x], prm.dy_tab[k]);
             const float nt = prm.hit_t[o];
             const float4 sc = __ldg(&prm.sph_exact[prm.hit_id[o]]);
@@ -551,9 +554,80 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) shadow_kernel(const FrameParam
                 }
             }
         }
-        if (valid) prm.pixels[o] = ref_rgb_to_int((int)(fr * 254.f), (int)(fg * 254.f), (int)(fb * 254.f));
+        if (valid) prm.pixels[o_out] = ref_rgb_to_int((int)(fr * 254.f), (int)(fg * 254.f), (int)(fb * 254.f));
     }
     if (n_exact) atomicAdd(&prm.counters[CNT_EXACT_SHADOW], n_exact);
+}
+
+// ------------------------------------------------------------------------------------
+// count_reference_tests_kernel (ORE_FLAG_COUNT_REFERENCE_TESTS, never on the timed path)
+// The reference's own any-hit loop, literally: one ray at a time, spheres in index order,
+// exact sequence, break at the first hit (kernel.cu:1501-1510).  Sums the number of
+// sphere::intersect calls that loop order makes - the "tests" of the FP32 roofline
+// (SURVEY.md 8d).  One thread per (hit pixel, light).
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CTA_THREADS) count_reference_tests_kernel(const FrameParams prm) {
+    const uint32_t n_items = (uint32_t)prm.counters[CNT_HITS];
+    const unsigned long long total = (unsigned long long)n_items * (unsigned long long)prm.n_lights;
+    const v3 O0 = mk(prm.Ox, prm.Oy, prm.Oz);
+    unsigned long long mine = 0;
+    for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < total;
+         w += (unsigned long long)gridDim.x * blockDim.x) {
+        // consecutive threads = consecutive hit pixels of one light (coherent loops)
+        const uint32_t light = (uint32_t)(w / n_items), item = (uint32_t)(w % n_items);
+        const uint32_t o = prm.hit_list[item];
+        const int k = (int)(o / (uint32_t)prm.W), x = (int)(o % (uint32_t)prm.W);
+        const v3 D = primary_dir(prm, prm.dx_tab[x], prm.dy_tab[k]);
+        const float nt = prm.hit_t[o];
+        const float4 sc = __ldg(&prm.sph_exact[prm.hit_id[o]]);
+        const v3 new_org = ref_add(O0, ref_scale(D, nt));
+        v3 normal = ref_sub(new_org, mk(sc.x, sc.y, sc.z));
+        ref_normalise(normal);
+        const v3 start = ref_add(ref_scale(normal, 0.00001f), new_org);
+        float dir[30];
+        light_directions(prm.lights[light], start, normal, dir);
+#pragma unroll 1
+        for (int j = 0; j < 10; j++) {
+            const v3 d = mk(dir[j * 3 + 0], dir[j * 3 + 1], dir[j * 3 + 2]);
+            int i = 0;
+            bool shadow = false;
+            for (; i < prm.n_spheres; i++) {
+                const float4 s = __ldg(&prm.sph_exact[i]);
+                float t;
+                if (ref_intersect(start, d, s.x, s.y, s.z, s.w, t)) {
+                    shadow = true;
+                    break;
+                }
+            }
+            mine += (unsigned long long)(shadow ? i + 1 : prm.n_spheres);
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, d);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&prm.counters[CNT_SHADOW_TESTS_REF], mine);
+}
+
+// ------------------------------------------------------------------------------------
+// fp32_burn_kernel: dependent-chain-free FFMA burn used to MEASURE the FP32 roofline
+// denominator on the box (MEASURED_PEAKS.json carries HBM and bf16 peaks only).
+// 16 independent accumulators per thread, 2 FLOP per FFMA.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CTA_THREADS) fp32_burn_kernel(float* out, int iters, float a, float b) {
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) acc[i] = (float)(threadIdx.x + i);
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) acc[i] = fmaf(acc[i], a, b);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s += acc[i];
+    if (s == 12345.678f) out[0] = s;  // never true; keeps the chain alive
 }
 
 }  // namespace ore

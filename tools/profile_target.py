@@ -1,0 +1,31 @@
+"""Short program for ncu: a few frames of one workload through the C ABI (no oracle, no CPU work)."""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+import rte_b200  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="4k1024")
+    ap.add_argument("--frames", type=int, default=3)
+    a = ap.parse_args()
+    pkg = rte_b200.pkg
+    W, H, sc, camera, desc = bench.make_workload(pkg, a.workload)
+    r = pkg.Renderer(0)
+    r.set_scene(sc)
+    out = np.empty((H, W), dtype=np.uint32)
+    for f in range(a.frames):
+        r.render(camera(f), W, H, out=out)
+        print(f, [round(v, 3) for v in r.kernel_ms()[:3]], r.counters()["hit_pixels"], flush=True)
+    r.close()
+
+
+if __name__ == "__main__":
+    main()
