@@ -43,7 +43,11 @@ enum ore_flags {
     /* Also count, per frame, the sphere::intersect calls the REFERENCE's loop order
      * would make in castLightRay (first blocker index + 1, or N) - the roofline's
      * "tests" (SURVEY.md 8d).  Costs one extra kernel; off on the timed path. */
-    ORE_FLAG_COUNT_REFERENCE_TESTS = 2
+    ORE_FLAG_COUNT_REFERENCE_TESTS = 2,
+    /* Shadow phase without the per-light cone test: every sample ray is tested against
+     * every sphere (30 filter tests per pixel and sphere).  Same results; this is the
+     * kernel the FP32-pipe roofline figures in profiles/ are quoted on. */
+    ORE_FLAG_PER_RAY_SHADOW = 4
 };
 
 typedef struct ore_context ore_context; /* opaque; owns device buffers, streams, pinned staging */

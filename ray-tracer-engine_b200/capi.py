@@ -15,6 +15,7 @@ from . import build as _build
 
 ORE_FLAG_EXHAUSTIVE = 1
 ORE_FLAG_COUNT_REFERENCE_TESTS = 2
+ORE_FLAG_PER_RAY_SHADOW = 4
 
 EXPORTS = [
     "ore_create", "ore_destroy", "ore_abi_version", "ore_last_error",
@@ -53,7 +54,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    path = path or _build.LIB_PATH
+    path = path or os.environ.get("ORE_LIB") or _build.LIB_PATH
     if not os.path.isfile(path):
         raise OreError(f"{path} not built - run `python -c 'import __graft_entry__ as g; g.build()'`")
     lib = C.CDLL(path)

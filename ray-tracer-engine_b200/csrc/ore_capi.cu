@@ -178,12 +178,18 @@ static int upload_spheres(ore_context* ctx, const float* src, size_t stride_floa
             const float* s = src + (size_t)i * stride_floats + first;
             ex[i] = make_float4(s[0], s[1], s[2], s[3]);
             const float r4 = s[3] * s[3];  // the test squares the stored member, kernel.cu:334
-            float r4p = (float)((double)r4 * (1.0 + (double)ORE_KAPPA_SHADOW));
-            r4p = nextafterf(r4p, INFINITY);
-            sh[i] = make_float4(s[0], s[1], s[2], r4p);
+            // R' = effective radius, rounded up so that R'^2 >= (1+k) r4 in float
+            float rp = (float)sqrt((double)r4 * (1.0 + (double)ORE_KAPPA_SHADOW));
+            rp = nextafterf(rp, INFINITY);
+            while (rp * rp < (float)((double)r4 * (1.0 + (double)ORE_KAPPA_SHADOW))) rp = nextafterf(rp, INFINITY);
+            sh[i] = make_float4(s[0], s[1], s[2], rp);
+        } else if (n > 0) {
+            // padding = copies of the last sphere: any-hit is idempotent and the exact path skips idx >= n
+            ex[i] = ex[n - 1];
+            sh[i] = sh[n - 1];
         } else {
-            ex[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            sh[i] = make_float4(0.f, 0.f, 0.f, -1e30f);  // filter value sqrt(LL+1e30) > |L|: never a candidate
+            ex[i] = make_float4(3e18f, -1e18f, 2e17f, 0.f);
+            sh[i] = make_float4(3e18f, -1e18f, 2e17f, 0.f);
         }
     }
     ORE_CUDA(ctx, cudaMemcpyAsync(ctx->sph_exact, ex, (size_t)n_pad * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
@@ -270,10 +276,10 @@ static constexpr int STREAM_CHUNK = 2048;
 static constexpr int STREAM_STAGES = 3;
 
 template <typename K>
-static int grid_for(ore_context* ctx, K kernel, size_t smem, int* grid) {
+static int grid_for(ore_context* ctx, K kernel, size_t smem, int* grid, int threads = CTA_THREADS) {
     int occ = 0;
     ORE_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ORE_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, CTA_THREADS, smem));
+    ORE_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
     if (occ < 1) return fail(ctx, ORE_ERR_CUDA, "kernel does not fit on an SM");
     *grid = occ * ctx->sm_count;
     return ORE_OK;
@@ -401,16 +407,28 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
     {
         int grid = 0;
         const int nl = ctx->n_lights >= 3 ? 3 : (ctx->n_lights == 2 ? 2 : 1);
-        if (nl == 3) {
-            if ((rc = grid_for(ctx, shadow_kernel<3>, smem, &grid))) return rc;
-            shadow_kernel<3><<<grid, CTA_THREADS, smem, stream>>>(prm);
+        const bool exh = (fr->flags & ORE_FLAG_EXHAUSTIVE) != 0;
+#define ORE_LAUNCH_SHADOW(NL, EXH)                                                        \
+    do {                                                                                  \
+        if ((rc = grid_for(ctx, shadow_kernel<NL, EXH>, smem, &grid, SHADOW_THREADS))) return rc; \
+        shadow_kernel<NL, EXH><<<grid, SHADOW_THREADS, smem, stream>>>(prm);              \
+    } while (0)
+        if (!(fr->flags & ORE_FLAG_PER_RAY_SHADOW)) {
+            if (exh) {
+                if ((rc = grid_for(ctx, shadow_cone_kernel<true>, smem, &grid))) return rc;
+                shadow_cone_kernel<true><<<grid, CTA_THREADS, smem, stream>>>(prm);
+            } else {
+                if ((rc = grid_for(ctx, shadow_cone_kernel<false>, smem, &grid))) return rc;
+                shadow_cone_kernel<false><<<grid, CTA_THREADS, smem, stream>>>(prm);
+            }
+        } else if (nl == 3) {
+            if (exh) ORE_LAUNCH_SHADOW(3, true); else ORE_LAUNCH_SHADOW(3, false);
         } else if (nl == 2) {
-            if ((rc = grid_for(ctx, shadow_kernel<2>, smem, &grid))) return rc;
-            shadow_kernel<2><<<grid, CTA_THREADS, smem, stream>>>(prm);
+            if (exh) ORE_LAUNCH_SHADOW(2, true); else ORE_LAUNCH_SHADOW(2, false);
         } else {
-            if ((rc = grid_for(ctx, shadow_kernel<1>, smem, &grid))) return rc;
-            shadow_kernel<1><<<grid, CTA_THREADS, smem, stream>>>(prm);
+            if (exh) ORE_LAUNCH_SHADOW(1, true); else ORE_LAUNCH_SHADOW(1, false);
         }
+#undef ORE_LAUNCH_SHADOW
         ORE_CUDA(ctx, cudaGetLastError());
         ctx->last_launches++;
     }

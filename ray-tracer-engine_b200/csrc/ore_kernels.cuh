@@ -22,6 +22,17 @@ constexpr int MAX_LIGHTS = 16;
 constexpr int CTA_THREADS = 256;
 constexpr int CTA_WARPS = CTA_THREADS / 32;
 constexpr int MAX_STAGES = 4;
+// shadow kernel launch shape: tunable at build time (see DESIGN.md "Shadow kernel tuning")
+#ifndef ORE_SHADOW_THREADS
+#define ORE_SHADOW_THREADS 256
+#endif
+#ifndef ORE_SHADOW_MIN_CTAS
+#define ORE_SHADOW_MIN_CTAS 2
+#endif
+#ifndef ORE_SHADOW_SG
+#define ORE_SHADOW_SG 4
+#endif
+constexpr int SHADOW_THREADS = ORE_SHADOW_THREADS;
 constexpr int SPHERE_PAD = 16;  // device sphere arrays are padded to a multiple of this
 
 // conservative filter margins (see DESIGN.md "Filter soundness")
@@ -56,7 +67,7 @@ struct FrameParams {
     const float* dy_tab;
     const float4* sph_exact;  // cx,cy,cz,radius member
     float4* sph_prim;         // primary filter coefficients a',b',c',0 (per frame)
-    const float4* sph_shad;   // cx,cy,cz,(1+k)*radius^2 (shadow filter)
+    const float4* sph_shad;   // cx,cy,cz,R' = effective radius rounded up: R'^2 >= (1+k)*radius^2 (shadow filter)
     const float *tex_r, *tex_g, *tex_b;
     int tex_w, tex_h;
     const float *sky_r, *sky_g, *sky_b;
@@ -392,9 +403,10 @@ __device__ __noinline__ float light_directions(const LightP L, const v3 start, c
 // ------------------------------------------------------------------------------------
 // shadow_kernel
 // ------------------------------------------------------------------------------------
-template <int NL>
-__global__ void __launch_bounds__(CTA_THREADS, 2) shadow_kernel(const FrameParams prm) {
+template <int NL, bool EXH>
+__global__ void __launch_bounds__(SHADOW_THREADS, ORE_SHADOW_MIN_CTAS) shadow_kernel(const FrameParams prm) {
     constexpr int NR = 10 * NL;
+    constexpr int SG = ORE_SHADOW_SG;  // spheres per inner step
     constexpr uint32_t ALL = (NR == 32) ? 0xffffffffu : ((1u << NR) - 1u);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bars[MAX_STAGES];
@@ -405,7 +417,6 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) shadow_kernel(const FrameParam
     pipe_init(tp, prm, prm.sph_shad, reinterpret_cast<float4*>(smem_raw), bars);
 
     const uint32_t n_items = (uint32_t)prm.counters[CNT_HITS];
-    const bool exhaustive = (prm.flags & 1u) != 0;
     const v3 O0 = mk(prm.Ox, prm.Oy, prm.Oz);
     unsigned long long n_exact = 0;
 
@@ -414,8 +425,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) shadow_kernel(const FrameParam
         if (tid == 0) s_batch = (int)atomicAdd(&prm.counters[CNT_SHADOW_CURSOR], 1ull);
         __syncthreads();
         const uint32_t batch = (uint32_t)s_batch;
-        if ((unsigned long long)batch * CTA_THREADS >= n_items) break;
-        const uint32_t item = batch * CTA_THREADS + tid;
+        if ((unsigned long long)batch * SHADOW_THREADS >= n_items) break;
+        const uint32_t item = batch * SHADOW_THREADS + tid;
         const bool valid = item < n_items;
 
         // ---- shading set-up (kernel.cu:1396-1405, 1643-1655) ----
@@ -447,23 +458,21 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) shadow_kernel(const FrameParam
 
         for (int l0 = 0; l0 < prm.n_lights; l0 += NL) {
             float dx[NR], dy[NR], dz[NR], a_l[NL];
+            float dirs[NR * 3];  // local-memory copy, indexed dynamically by the rare exact path
             uint32_t blocked = ALL;
-            {
-                float dir[30];
 #pragma unroll
-                for (int l = 0; l < NL; l++) {
-                    const bool lit = valid && (l0 + l) < prm.n_lights;
-                    a_l[l] = 0.f;
-                    if (lit) {
-                        a_l[l] = light_directions(prm.lights[l0 + l], start, normal, dir);
-                        blocked &= ~(0x3ffu << (10 * l));
-                    }
+            for (int l = 0; l < NL; l++) {
+                const bool lit = valid && (l0 + l) < prm.n_lights;
+                a_l[l] = 0.f;
+                if (lit) {
+                    a_l[l] = light_directions(prm.lights[l0 + l], start, normal, dirs + 30 * l);
+                    blocked &= ~(0x3ffu << (10 * l));
+                }
 #pragma unroll
-                    for (int j = 0; j < 10; j++) {
-                        dx[l * 10 + j] = lit ? dir[j * 3 + 0] : 0.f;
-                        dy[l * 10 + j] = lit ? dir[j * 3 + 1] : 0.f;
-                        dz[l * 10 + j] = lit ? dir[j * 3 + 2] : 0.f;
-                    }
+                for (int j = 0; j < 10; j++) {
+                    dx[l * 10 + j] = lit ? dirs[(l * 10 + j) * 3 + 0] : 0.f;
+                    dy[l * 10 + j] = lit ? dirs[(l * 10 + j) * 3 + 1] : 0.f;
+                    dz[l * 10 + j] = lit ? dirs[(l * 10 + j) * 3 + 2] : 0.f;
                 }
             }
 
@@ -476,55 +485,310 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) shadow_kernel(const FrameParam
                 const int base = c * tp.chunk;
                 if (!warp_done) {
 #pragma unroll 1
-                    for (int s = 0; s < cnt; s += 2) {
-                        int trig[2];
-                        float Lxs[2], Lys[2], Lzs[2], svs[2];
+                    for (int s = 0; s < cnt; s += SG) {
+                        // SG spheres at a time: SG independent 3-FMA chains per ray keep the FMA pipe
+                        // busy without waiting on its 4-cycle latency
+                        float Lx[SG], Ly[SG], Lz[SG], sv[SG];
 #pragma unroll
-                        for (int u = 0; u < 2; u++) {
+                        for (int u = 0; u < SG; u++) {
                             const float4 q = tile[s + u];
-                            const float Lx = start.x - q.x, Ly = start.y - q.y, Lz = start.z - q.z;
-                            const float LL = fmaf(Lz, Lz, fmaf(Ly, Ly, Lx * Lx));
-                            const float Cm = fmaf(LL, 1.0f - ORE_KAPPA_SHADOW, -q.w);
-                            float sv = Cm * rsqrt_approx(Cm);
-                            sv = (Cm > 1e-20f) ? sv : -ORE_BIG;
-                            if (exhaustive) sv = -ORE_BIG;
-                            int acc = 0;
-#pragma unroll
-                            for (int j = 0; j < NR; j++) {
-                                const float h = fmaf(dx[j], Lx, fmaf(dy[j], Ly, fmaf(dz[j], Lz, sv)));
-                                acc |= __float_as_int(h);
-                            }
-                            trig[u] = acc;
-                            Lxs[u] = Lx;
-                            Lys[u] = Ly;
-                            Lzs[u] = Lz;
-                            svs[u] = sv;
+                            Lx[u] = start.x - q.x;
+                            Ly[u] = start.y - q.y;
+                            Lz[u] = start.z - q.z;
+                            const float LL = fmaf(Lz[u], Lz[u], fmaf(Ly[u], Ly[u], Lx[u] * Lx[u]));
+                            const float Cm = fmaf(LL, 1.0f - ORE_KAPPA_SHADOW, -(q.w * q.w));
+                            const float sq = Cm * rsqrt_approx(Cm);
+                            sv[u] = EXH ? -ORE_BIG : ((Cm > 1e-20f) ? sq : -ORE_BIG);
                         }
-                        if (((trig[0] | trig[1]) < 0) && blocked != ALL) {
+                        int acc = 0;
+#pragma unroll
+                        for (int j = 0; j < NR; j++) {
+                            float h[SG];
+#pragma unroll
+                            for (int u = 0; u < SG; u++) h[u] = fmaf(dz[j], Lz[u], sv[u]);
+#pragma unroll
+                            for (int u = 0; u < SG; u++) h[u] = fmaf(dy[j], Ly[u], h[u]);
+#pragma unroll
+                            for (int u = 0; u < SG; u++) h[u] = fmaf(dx[j], Lx[u], h[u]);
+#pragma unroll
+                            for (int u = 0; u < SG; u += 2) acc |= __float_as_int(h[u]) | __float_as_int(h[u + 1]);
+                        }
+                        if (acc < 0 && blocked != ALL) {
+                            // rare: some ray of this thread may hit one of the SG spheres -> exact sequence
 #pragma unroll 1
-                            for (int u = 0; u < 2; u++) {
+                            for (int u = 0; u < SG; u++) {
                                 const int idx = base + s + u;
-                                if (trig[u] >= 0 || idx >= prm.n_spheres) continue;
-                                const float4 ex = __ldg(&prm.sph_exact[idx]);
-                                const float Lx = Lxs[u], Ly = Lys[u], Lz = Lzs[u], sv = svs[u];
+                                if (idx >= prm.n_spheres) break;
+                                const float4 q = tile[s + u];
+                                const float lx = start.x - q.x, ly = start.y - q.y, lz = start.z - q.z;
+                                const float LL = fmaf(lz, lz, fmaf(ly, ly, lx * lx));
+                                const float Cm = fmaf(LL, 1.0f - ORE_KAPPA_SHADOW, -(q.w * q.w));
+                                const float sq = Cm * rsqrt_approx(Cm);
+                                const float svu = EXH ? -ORE_BIG : ((Cm > 1e-20f) ? sq : -ORE_BIG);
+                                // candidate rays of this sphere (filter), then the exact sequence in a
+                                // rolled loop that reads the directions from their local-memory copy
+                                uint32_t cand = 0;
 #pragma unroll
                                 for (int j = 0; j < NR; j++) {
-                                    if (!((blocked >> j) & 1u)) {
-                                        const float h = fmaf(dx[j], Lx, fmaf(dy[j], Ly, fmaf(dz[j], Lz, sv)));
-                                        if (h < 0.f) {
-                                            n_exact++;
-                                            if (ref_intersect_call(start.x, start.y, start.z, dx[j], dy[j], dz[j], ex)) {
-                                                blocked |= (1u << j);
-                                                dx[j] = 0.f;
-                                                dy[j] = 0.f;
-                                                dz[j] = 0.f;
-                                            }
+                                    const float h = fmaf(dx[j], lx, fmaf(dy[j], ly, fmaf(dz[j], lz, svu)));
+                                    cand |= (h < 0.f) ? (1u << j) : 0u;
+                                }
+                                cand &= ~blocked;
+                                if (cand) {
+                                    const float4 ex = __ldg(&prm.sph_exact[idx]);
+                                    uint32_t newly = 0;
+                                    while (cand) {
+                                        const int j = __ffs(cand) - 1;
+                                        cand &= cand - 1;
+                                        float t;
+                                        n_exact++;
+                                        if (ref_intersect(start, mk(dirs[j * 3], dirs[j * 3 + 1], dirs[j * 3 + 2]), ex.x, ex.y,
+                                                          ex.z, ex.w, t))
+                                            newly |= 1u << j;
+                                    }
+                                    if (newly) {
+                                        blocked |= newly;
+#pragma unroll
+                                        for (int j = 0; j < NR; j++) {
+                                            const bool nb = (newly >> j) & 1u;
+                                            dx[j] = nb ? 0.f : dx[j];
+                                            dy[j] = nb ? 0.f : dy[j];
+                                            dz[j] = nb ? 0.f : dz[j];
                                         }
                                     }
                                 }
                             }
                         }
-                        if ((s & 6) == 6) {
+                        if ((s & (2 * SG - 1)) == SG) {
+                            if (__all_sync(0xffffffffu, blocked == ALL)) {
+                                warp_done = true;
+                                break;
+                            }
+                        }
+                    }
+                }
+                tp.release(c);
+            }
+
+            // ---- light accumulation (kernel.cu:1537-1543, 1673-1675) ----
+            if (valid) {
+#pragma unroll
+                for (int l = 0; l < NL; l++) {
+                    if (l0 + l < prm.n_lights) {
+                        float b = 0;
+#pragma unroll
+                        for (int j = 0; j < 10; j++)
+                            if (!((blocked >> (l * 10 + j)) & 1u)) b = (float)((double)b + 0.1);
+                        const float a = a_l[l];
+                        b *= a > 0 ? a : 0;
+                        const LightP L = prm.lights[l0 + l];
+                        fr += b * L.r * tr;
+                        fg += b * L.g * tg;
+                        fb += b * L.b * tb;
+                    }
+                }
+            }
+        }
+        if (valid) prm.pixels[o_out] = ref_rgb_to_int((int)(fr * 254.f), (int)(fg * 254.f), (int)(fb * 254.f));
+    }
+    if (n_exact) atomicAdd(&prm.counters[CNT_EXACT_SHADOW], n_exact);
+}
+
+// ------------------------------------------------------------------------------------
+// shadow_cone_kernel (default shadow path)
+//
+// One thread per HIT pixel.  The 10 sample rays of a light leave the same origin inside a
+// narrow cone (new_dir = normalise(l.pos - M*(x,y,_z)), kernel.cu:1468: the jitter vector
+// has length <= ~1.7 against |l.pos| of tens of units).  For every sphere the thread first
+// runs ONE conservative cone-vs-sphere test per light (3 FMA + threshold) and only when a
+// cone can touch the sphere does it test that light's individual rays (filter, then the
+// exact reference sequence).  Every (pixel, sphere) pair is still visited in index order;
+// no spatial structure is built.  Results are identical to the per-ray kernel.
+//
+// Cone test (DESIGN.md "Cone filter"): with L = O - c, s' = sqrt(Cm) the per-ray filter
+// says a ray D can only hit if D.L + s' <= 0, i.e. its angle to the centre direction is at
+// most b' = acos(s'/|L|).  Rays lie within a of the axis A, so a hit needs
+// angle(A, centre) <= a + b'  <=>  A.L + cos(a) s' - sin(a) sqrt(|L|^2 - s'^2) <= 0,
+// and sqrt(|L|^2 - s'^2) <= 1.002 R' + 0.00196 s'.
+// ------------------------------------------------------------------------------------
+template <bool EXH>
+__global__ void __launch_bounds__(CTA_THREADS, 3) shadow_cone_kernel(const FrameParams prm) {
+    constexpr int NL = 3;        // lights per pass
+    constexpr int NR = 10 * NL;
+    constexpr uint32_t ALL = (1u << NR) - 1u;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bars[MAX_STAGES];
+    __shared__ int s_batch;
+
+    const int tid = threadIdx.x;
+    TilePipe tp;
+    pipe_init(tp, prm, prm.sph_shad, reinterpret_cast<float4*>(smem_raw), bars);
+
+    const uint32_t n_items = (uint32_t)prm.counters[CNT_HITS];
+    const v3 O0 = mk(prm.Ox, prm.Oy, prm.Oz);
+    unsigned long long n_exact = 0;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_batch = (int)atomicAdd(&prm.counters[CNT_SHADOW_CURSOR], 1ull);
+        __syncthreads();
+        const uint32_t batch = (uint32_t)s_batch;
+        if ((unsigned long long)batch * CTA_THREADS >= n_items) break;
+        const uint32_t item = batch * CTA_THREADS + tid;
+        const bool valid = item < n_items;
+
+        // ---- shading set-up (kernel.cu:1396-1405, 1643-1655) ----
+        size_t o_out = 0;
+        v3 start = mk(1e9f, 1e9f, 1e9f), normal = mk(0.f, 0.f, 0.f);
+        float tr = 0.f, tg = 0.f, tb = 0.f;
+        if (valid) {
+            const uint32_t o = prm.hit_list[item];
+            const int k = (int)(o / (uint32_t)prm.W), x = (int)(o % (uint32_t)prm.W);
+            o_out = (size_t)k * prm.pitch + x;
+            const v3 D = primary_dir(prm, prm.dx_tab[x], prm.dy_tab[k]);
+            const float nt = prm.hit_t[o];
+            const float4 sc = __ldg(&prm.sph_exact[prm.hit_id[o]]);
+            const v3 new_org = ref_add(O0, ref_scale(D, nt));
+            normal = ref_sub(new_org, mk(sc.x, sc.y, sc.z));
+            ref_normalise(normal);
+            const float txf = (float)((1 + (double)atan2f(normal.z, normal.x) / 3.1415) * 0.5);
+            const float tyf = (float)((double)acosf(normal.y) / 3.1415);
+            const int maxX = prm.tex_w, maxY = prm.tex_h;
+            start = ref_add(ref_scale(normal, 0.00001f), new_org);
+            int c_index = (int)(tyf * (float)maxY) * maxX + (int)(txf * (float)maxX);
+            c_index = clamp_index(c_index, maxX * maxY);
+            tr = __ldg(&prm.tex_r[c_index]);
+            tg = __ldg(&prm.tex_g[c_index]);
+            tb = __ldg(&prm.tex_b[c_index]);
+        }
+        float fr = 0.f, fg = 0.f, fb = 0.f;
+
+        for (int l0 = 0; l0 < prm.n_lights; l0 += NL) {
+            float dirs[NR * 3];  // local memory (L1): only the rare per-ray path reads it
+            float Ax[NL], Ay[NL], Az[NL], ca[NL], sa[NL], a_l[NL];
+            uint32_t blocked = ALL;
+            bool force = false;  // some light cannot use the cone test: every sphere is a candidate
+#pragma unroll
+            for (int l = 0; l < NL; l++) {
+                const bool lit = valid && (l0 + l) < prm.n_lights;
+                a_l[l] = 0.f;
+                Ax[l] = Ay[l] = Az[l] = ca[l] = sa[l] = 0.f;
+                if (lit) {
+                    float* d = dirs + 30 * l;
+                    a_l[l] = light_directions(prm.lights[l0 + l], start, normal, d);
+                    blocked &= ~(0x3ffu << (10 * l));
+                    // cone of the 10 rays: axis = normalised sum, cos(a) = min_j axis.D_j
+                    float sx = 0.f, sy = 0.f, sz = 0.f;
+#pragma unroll 1
+                    for (int j = 0; j < 10; j++) {
+                        sx += d[j * 3];
+                        sy += d[j * 3 + 1];
+                        sz += d[j * 3 + 2];
+                    }
+                    const float inv = rsqrtf(fmaf(sx, sx, fmaf(sy, sy, sz * sz)));
+                    float cmin = 1.f;
+                    bool ok = isfinite(inv);
+                    if (ok) {
+                        sx *= inv;
+                        sy *= inv;
+                        sz *= inv;
+#pragma unroll 1
+                        for (int j = 0; j < 10; j++) {
+                            const float dd = fmaf(d[j * 3], d[j * 3], fmaf(d[j * 3 + 1], d[j * 3 + 1], d[j * 3 + 2] * d[j * 3 + 2]));
+                            ok = ok && fabsf(dd - 1.f) < 1e-4f;  // the filters assume |D| = 1 (normalised by the reference)
+                            cmin = fminf(cmin, fmaf(sx, d[j * 3], fmaf(sy, d[j * 3 + 1], sz * d[j * 3 + 2])));
+                        }
+                    }
+                    if (ok && cmin > 0.5f && !EXH) {
+                        const float cosa = cmin - 4e-6f;
+                        const float sina = sqrtf(fmaxf(0.f, fmaf(-cosa, cosa, 1.f))) * 1.0001f + 1e-6f;
+                        Ax[l] = sx;
+                        Ay[l] = sy;
+                        Az[l] = sz;
+                        ca[l] = cosa - 0.00196f * sina;
+                        sa[l] = 1.002f * sina;
+                    } else {
+                        // degenerate bundle (zero direction, very wide cone) or exhaustive mode
+                        force = true;
+                    }
+                }
+            }
+
+            tp.begin_round();
+            bool warp_done = false;
+            for (int c = 0; c < tp.n_chunks; c++) {
+                const float4* tile = tp.acquire(c);
+                const int cnt = tp.count(c);
+                const int base = c * tp.chunk;
+                if (!warp_done) {
+                    const float4* __restrict__ tp_ptr = tile;
+#pragma unroll 1
+                    for (int s = 0; s < cnt; s += 2, tp_ptr += 2) {
+                        float m[2];
+#pragma unroll
+                        for (int u = 0; u < 2; u++) {
+                            const float4 q = tp_ptr[u];
+                            const float Lx = start.x - q.x, Ly = start.y - q.y, Lz = start.z - q.z;
+                            const float LL = fmaf(Lz, Lz, fmaf(Ly, Ly, Lx * Lx));
+                            const float Cm = fmaf(LL, 1.0f - ORE_KAPPA_SHADOW, -(q.w * q.w));
+                            const float sq = Cm * rsqrt_approx(Cm);
+                            const float sv = (Cm > 1e-20f) ? sq : -ORE_BIG;
+                            float mm = INFINITY;
+#pragma unroll
+                            for (int l = 0; l < NL; l++) {
+                                const float T = fmaf(ca[l], sv, -(sa[l] * q.w));
+                                mm = fminf(mm, fmaf(Ax[l], Lx, fmaf(Ay[l], Ly, fmaf(Az[l], Lz, T))));
+                            }
+                            m[u] = mm;
+                        }
+                        if ((force || fminf(m[0], m[1]) < 0.f) && blocked != ALL) {
+#pragma unroll 1
+                            for (int u = 0; u < 2; u++) {
+                                const int idx = base + s + u;
+                                if (idx >= prm.n_spheres) break;
+                                // (rare) recompute this sphere's filter terms, then test the live rays
+                                const float4 q = tp_ptr[u];
+                                const float lx = start.x - q.x, ly = start.y - q.y, lz = start.z - q.z;
+                                const float LL = fmaf(lz, lz, fmaf(ly, ly, lx * lx));
+                                const float Cm = fmaf(LL, 1.0f - ORE_KAPPA_SHADOW, -(q.w * q.w));
+                                const float sq = Cm * rsqrt_approx(Cm);
+                                const float svu = (EXH || !(Cm > 1e-20f)) ? -ORE_BIG : sq;
+                                uint32_t live = ~blocked & ALL;
+                                if (!force) {
+                                    // only the lights whose cone touches this sphere
+                                    uint32_t lm = 0;
+#pragma unroll
+                                    for (int l = 0; l < NL; l++) {
+                                        const float T = fmaf(ca[l], svu, -(sa[l] * q.w));
+                                        if (fmaf(Ax[l], lx, fmaf(Ay[l], ly, fmaf(Az[l], lz, T))) < 0.f) lm |= 0x3ffu << (10 * l);
+                                    }
+                                    live &= lm;
+                                }
+                                if (!live) continue;
+                                const float4 ex = __ldg(&prm.sph_exact[idx]);
+                                while (live) {
+                                    const int j = __ffs(live) - 1;
+                                    live &= live - 1;
+                                    const v3 D = mk(dirs[j * 3], dirs[j * 3 + 1], dirs[j * 3 + 2]);
+                                    const float h = fmaf(D.x, lx, fmaf(D.y, ly, fmaf(D.z, lz, svu)));
+                                    if (h < 0.f) {
+                                        float t;
+                                        n_exact++;
+                                        if (ref_intersect(start, D, ex.x, ex.y, ex.z, ex.w, t)) blocked |= 1u << j;
+                                    }
+                                }
+                            }
+                            // a light whose 10 rays are all blocked drops out of the cone test
+#pragma unroll
+                            for (int l = 0; l < NL; l++) {
+                                if (((blocked >> (10 * l)) & 0x3ffu) == 0x3ffu) {
+                                    Ax[l] = Ay[l] = Az[l] = 0.f;
+                                    ca[l] = 0.f;
+                                    sa[l] = 0.f;
+                                }
+                            }
+                        }
+                        if ((s & 14) == 14) {
                             if (__all_sync(0xffffffffu, blocked == ALL)) {
                                 warp_done = true;
                                 break;

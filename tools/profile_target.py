@@ -15,6 +15,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="4k1024")
     ap.add_argument("--frames", type=int, default=3)
+    ap.add_argument("--flags", type=int, default=0)
     a = ap.parse_args()
     pkg = rte_b200.pkg
     W, H, sc, camera, desc = bench.make_workload(pkg, a.workload)
@@ -22,7 +23,7 @@ def main():
     r.set_scene(sc)
     out = np.empty((H, W), dtype=np.uint32)
     for f in range(a.frames):
-        r.render(camera(f), W, H, out=out)
+        r.render(camera(f), W, H, out=out, flags=a.flags)
         print(f, [round(v, 3) for v in r.kernel_ms()[:3]], r.counters()["hit_pixels"], flush=True)
     r.close()
 
