@@ -47,7 +47,11 @@ enum ore_flags {
     /* Shadow phase without the per-light cone test: every sample ray is tested against
      * every sphere (30 filter tests per pixel and sphere).  Same results; this is the
      * kernel the FP32-pipe roofline figures in profiles/ are quoted on. */
-    ORE_FLAG_PER_RAY_SHADOW = 4
+    ORE_FLAG_PER_RAY_SHADOW = 4,
+    /* No warp-cooperative culling: the primary kernel applies the per-pixel filter to every
+     * sphere and the shadow kernel the per-pixel cone test to every sphere (the previous
+     * generation of both kernels).  Same results. */
+    ORE_FLAG_NO_WARP_CULL = 8
 };
 
 typedef struct ore_context ore_context; /* opaque; owns device buffers, streams, pinned staging */

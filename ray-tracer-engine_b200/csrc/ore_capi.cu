@@ -36,6 +36,7 @@ struct ore_context {
     int n_spheres = 0, n_spheres_pad = 0;
     float4* sph_exact = nullptr;
     float4* sph_prim = nullptr;
+    float4* sph_cone = nullptr;
     float4* sph_shad = nullptr;
     size_t sph_cap = 0;
     int n_lights = 0;
@@ -145,7 +146,7 @@ extern "C" int ore_destroy(ore_context* ctx) {
     if (!ctx) return ORE_ERR_INVALID;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    void* dev[] = {ctx->sph_exact, ctx->sph_prim, ctx->sph_shad, ctx->tex[0], ctx->tex[1], ctx->tex[2],
+    void* dev[] = {ctx->sph_exact, ctx->sph_prim, ctx->sph_cone, ctx->sph_shad, ctx->tex[0], ctx->tex[1], ctx->tex[2],
                    ctx->sky[0],    ctx->sky[1],   ctx->sky[2],   ctx->dx_tab, ctx->dy_tab, ctx->hit_id,
                    ctx->hit_t,     ctx->hit_list, ctx->pixels,   ctx->counters};
     for (void* p : dev)
@@ -164,10 +165,11 @@ static int upload_spheres(ore_context* ctx, const float* src, size_t stride_floa
     if (!ctx || n < 0 || (n > 0 && !src)) return fail(ctx, ORE_ERR_INVALID, "ore_set_spheres: bad arguments");
     ORE_CUDA(ctx, cudaSetDevice(ctx->device));
     const int n_pad = ((n + SPHERE_PAD - 1) / SPHERE_PAD) * SPHERE_PAD + SPHERE_PAD;  // >= 1 pad block
-    size_t cap_e = ctx->sph_cap, cap_p = ctx->sph_cap, cap_s = ctx->sph_cap;
+    size_t cap_e = ctx->sph_cap, cap_p = ctx->sph_cap, cap_s = ctx->sph_cap, cap_c = ctx->sph_cap;
     int rc;
     if ((rc = ensure_dev(ctx, &ctx->sph_exact, &cap_e, (size_t)n_pad))) return rc;
     if ((rc = ensure_dev(ctx, &ctx->sph_prim, &cap_p, (size_t)n_pad))) return rc;
+    if ((rc = ensure_dev(ctx, &ctx->sph_cone, &cap_c, (size_t)n_pad))) return rc;
     if ((rc = ensure_dev(ctx, &ctx->sph_shad, &cap_s, (size_t)n_pad))) return rc;
     ctx->sph_cap = cap_e < cap_p ? (cap_e < cap_s ? cap_e : cap_s) : (cap_p < cap_s ? cap_p : cap_s);
     if ((rc = ensure_pinned(ctx, 2 * (size_t)n_pad * sizeof(float4)))) return rc;
@@ -348,6 +350,22 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
         prm.cy = cosf(yawRad);
         prm.sy = sinf(yawRad);
     }
+    {
+        // largest half-angle of a 32 x PRIMARY_P pixel tile seen from the eye (tile cone of the primary
+        // kernel): |v_pixel - v_centre| <= halfdiag on the image plane and |v| >= fz, so sin(a) <= halfdiag/fz
+        const double delta = 2.0 * (double)fr->aspect / (double)W;
+        const double hx = 16.0 * delta, hy = (0.5 * (PRIMARY_P - 1) * fr->y_step + 0.5) * delta;
+        const double xr = sqrt(hx * hx + hy * hy) / fabs((double)prm.fz);
+        prm.px_delta = (float)delta;
+        if (!(xr < 0.9)) {
+            prm.tile_ca = -1e20f;  // tiles too wide for a cone: every sphere is a candidate
+            prm.tile_sa = 0.f;
+        } else {
+            const double a = asin(xr) * 1.001 + 1e-6;
+            prm.tile_ca = (float)(cos(a) * (1.0 - 1e-6) - 1e-6);
+            prm.tile_sa = (float)(sin(a) * (1.0 + 1e-6) + 1e-6);
+        }
+    }
     if ((size_t)ctx->n_spheres_pad * sizeof(float4) <= RESIDENT_BYTES) {
         prm.resident = 1;
         prm.chunk = ctx->n_spheres_pad;
@@ -364,6 +382,7 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
     prm.dy_tab = ctx->dy_tab;
     prm.sph_exact = ctx->sph_exact;
     prm.sph_prim = ctx->sph_prim;
+    prm.sph_cone = ctx->sph_cone;
     prm.sph_shad = ctx->sph_shad;
     prm.tex_r = ctx->tex[0];
     prm.tex_g = ctx->tex[1];
@@ -393,13 +412,29 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
         ctx->last_launches++;
     }
     ORE_CUDA(ctx, cudaEventRecord(ctx->ev[1], stream));
+    const bool exh = (fr->flags & ORE_FLAG_EXHAUSTIVE) != 0;
+    const bool warp_cull = !(fr->flags & (ORE_FLAG_NO_WARP_CULL | ORE_FLAG_PER_RAY_SHADOW));
     {
         int grid = 0;
-        if ((rc = grid_for(ctx, primary_kernel<PRIMARY_P>, smem, &grid))) return rc;
-        const int strips_per_row = (W + 32 * PRIMARY_P - 1) / (32 * PRIMARY_P);
-        const long long n_batches = ((long long)n_rows * strips_per_row + CTA_WARPS - 1) / CTA_WARPS;
-        if (grid > n_batches) grid = (int)n_batches;
-        primary_kernel<PRIMARY_P><<<grid, CTA_THREADS, smem, stream>>>(prm);
+        if (warp_cull) {
+            const long long tiles = (long long)((W + 31) / 32) * ((n_rows + PRIMARY_P - 1) / PRIMARY_P);
+            const long long n_batches = (tiles + CTA_WARPS - 1) / CTA_WARPS;
+            if (exh) {
+                if ((rc = grid_for(ctx, primary_tile_kernel<PRIMARY_P, true>, smem, &grid))) return rc;
+                if (grid > n_batches) grid = (int)n_batches;
+                primary_tile_kernel<PRIMARY_P, true><<<grid, CTA_THREADS, smem, stream>>>(prm);
+            } else {
+                if ((rc = grid_for(ctx, primary_tile_kernel<PRIMARY_P, false>, smem, &grid))) return rc;
+                if (grid > n_batches) grid = (int)n_batches;
+                primary_tile_kernel<PRIMARY_P, false><<<grid, CTA_THREADS, smem, stream>>>(prm);
+            }
+        } else {
+            if ((rc = grid_for(ctx, primary_kernel<PRIMARY_P>, smem, &grid))) return rc;
+            const int strips_per_row = (W + 32 * PRIMARY_P - 1) / (32 * PRIMARY_P);
+            const long long n_batches = ((long long)n_rows * strips_per_row + CTA_WARPS - 1) / CTA_WARPS;
+            if (grid > n_batches) grid = (int)n_batches;
+            primary_kernel<PRIMARY_P><<<grid, CTA_THREADS, smem, stream>>>(prm);
+        }
         ORE_CUDA(ctx, cudaGetLastError());
         ctx->last_launches++;
     }
@@ -407,13 +442,22 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
     {
         int grid = 0;
         const int nl = ctx->n_lights >= 3 ? 3 : (ctx->n_lights == 2 ? 2 : 1);
-        const bool exh = (fr->flags & ORE_FLAG_EXHAUSTIVE) != 0;
 #define ORE_LAUNCH_SHADOW(NL, EXH)                                                        \
     do {                                                                                  \
         if ((rc = grid_for(ctx, shadow_kernel<NL, EXH>, smem, &grid, SHADOW_THREADS))) return rc; \
         shadow_kernel<NL, EXH><<<grid, SHADOW_THREADS, smem, stream>>>(prm);              \
     } while (0)
-        if (!(fr->flags & ORE_FLAG_PER_RAY_SHADOW)) {
+        if (warp_cull) {
+            // the beam kernel stages the whole record array (resident) or reads it through L1/L2: no ring
+            const size_t bsmem = prm.resident ? (size_t)ctx->n_spheres_pad * sizeof(float4) : 0;
+            if (exh) {
+                if ((rc = grid_for(ctx, shadow_beam_kernel<true>, bsmem, &grid))) return rc;
+                shadow_beam_kernel<true><<<grid, CTA_THREADS, bsmem, stream>>>(prm);
+            } else {
+                if ((rc = grid_for(ctx, shadow_beam_kernel<false>, bsmem, &grid))) return rc;
+                shadow_beam_kernel<false><<<grid, CTA_THREADS, bsmem, stream>>>(prm);
+            }
+        } else if (!(fr->flags & ORE_FLAG_PER_RAY_SHADOW)) {
             if (exh) {
                 if ((rc = grid_for(ctx, shadow_cone_kernel<true>, smem, &grid))) return rc;
                 shadow_cone_kernel<true><<<grid, CTA_THREADS, smem, stream>>>(prm);

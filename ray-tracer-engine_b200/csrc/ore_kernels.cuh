@@ -67,6 +67,9 @@ struct FrameParams {
     const float* dy_tab;
     const float4* sph_exact;  // cx,cy,cz,radius member
     float4* sph_prim;         // primary filter coefficients a',b',c',0 (per frame)
+    float4* sph_cone;         // primary tile-cone record Mx,My,Mz,W in the camera frame (per frame)
+    float tile_ca, tile_sa;   // cos/sin of the largest pixel-tile half-angle (+ margins), host-computed
+    float px_delta;           // image-plane pixel pitch 2*aspect/width
     const float4* sph_shad;   // cx,cy,cz,R' = effective radius rounded up: R'^2 >= (1+k)*radius^2 (shadow filter)
     const float *tex_r, *tex_g, *tex_b;
     int tex_w, tex_h;
@@ -122,6 +125,7 @@ __global__ void prep_frame_kernel(const FrameParams prm) {
     }
     if (i < prm.n_spheres_pad) {
         float4 out = make_float4(0.f, 0.f, ORE_BIG, 0.f);  // padding: never a candidate
+        float4 cone = make_float4(0.f, 0.f, 0.f, ORE_BIG);
         if (i < prm.n_spheres) {
             const float4 s = prm.sph_exact[i];
             // L exactly as the reference forms it (float), then the filter works in double
@@ -131,6 +135,7 @@ __global__ void prep_frame_kernel(const FrameParams prm) {
             const double Cm = LL * (1.0 - ORE_KAPPA_PRIMARY) - r4 * (1.0 + ORE_KAPPA_PRIMARY);
             if (!(Cm > 1e-9 * LL) || !(Cm > 1e-30)) {
                 out = make_float4(0.f, 0.f, -ORE_BIG, 0.f);  // origin in/near the sphere: always exact
+                cone = make_float4(0.f, 0.f, 0.f, -ORE_BIG);
             } else {
                 const double sv = sqrt(Cm);
                 const double cp = prm.cp, sp = prm.sp, cy = prm.cy, sy = prm.sy;
@@ -138,9 +143,15 @@ __global__ void prep_frame_kernel(const FrameParams prm) {
                 const double My = sp * sy * Lx + cp * Ly + sp * cy * Lz;
                 const double Mz = cp * sy * Lx - sp * Ly + cp * cy * Lz;
                 out = make_float4((float)(Mx / sv), (float)(My / sv), (float)((double)prm.fz * Mz / sv), 0.f);
+                // tile cone (camera frame): a pixel tile whose directions lie within `a` of its axis A can
+                // only contain a hit if  A.M + cos(a) sv - sin(a) sqrt(LL - sv^2) <= 0   (DESIGN.md "Cone filter")
+                const double Rpp = sqrt(LL - Cm);
+                const double Wd = (double)prm.tile_ca * sv - (double)prm.tile_sa * Rpp;
+                cone = make_float4((float)Mx, (float)My, (float)Mz, (float)(Wd - 4e-6 * sqrt(LL) - 1e-30));
             }
         }
         prm.sph_prim[i] = out;
+        prm.sph_cone[i] = cone;
     }
 }
 
@@ -366,6 +377,164 @@ __global__ void __launch_bounds__(CTA_THREADS) primary_kernel(const FrameParams 
 }
 
 // ------------------------------------------------------------------------------------
+// primary_tile_kernel (default primary path)
+//
+// One warp = one tile of 32 x P pixels.  The 32 lanes first test 32 DIFFERENT spheres
+// against the tile's bounding cone (one 3-FMA test per lane, shared-memory records staged
+// by TMA), ballot, and only the surviving spheres get the per-pixel filter + exact
+// sequence.  Every (tile, sphere) pair is visited in index order; candidates keep
+// ascending order, so the strict '<' tie rule (kernel.cu:1335) is preserved.
+// ------------------------------------------------------------------------------------
+template <int P, bool EXH>
+__global__ void __launch_bounds__(CTA_THREADS, 2) primary_tile_kernel(const FrameParams prm) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bars[MAX_STAGES];
+    __shared__ uint32_t warp_tot[CTA_WARPS];
+    __shared__ uint32_t cta_base;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    TilePipe tp;
+    pipe_init(tp, prm, prm.sph_cone, reinterpret_cast<float4*>(smem_raw), bars);
+
+    const int tiles_x = (prm.W + 31) / 32;
+    const int tiles_y = (prm.n_rows + P - 1) / P;
+    const int total_tiles = tiles_x * tiles_y;
+    const int n_batches = (total_tiles + CTA_WARPS - 1) / CTA_WARPS;
+    const v3 O = mk(prm.Ox, prm.Oy, prm.Oz);
+    unsigned long long n_exact = 0;
+
+    for (int batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
+        const int tile_id = batch * CTA_WARPS + warp;
+        const bool tile_ok = tile_id < total_tiles;
+        const int ty = tile_ok ? tile_id / tiles_x : 0;
+        const int tx = tile_ok ? tile_id % tiles_x : 0;
+        const int x = tx * 32 + lane;
+        const bool x_ok = tile_ok && x < prm.W;
+        const float dx = x_ok ? prm.dx_tab[x] : 0.f;
+
+        float dyp[P], negn[P], best_t[P];
+        int best_id[P];
+        v3 D[P];
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+            const int k = ty * P + p;
+            const bool ok = x_ok && k < prm.n_rows;
+            dyp[p] = prm.dy_tab[k < prm.n_rows ? k : prm.n_rows - 1];
+            D[p] = primary_dir(prm, dx, dyp[p]);
+            const float nv = sqrtf(fmaf(dx, dx, fmaf(dyp[p], dyp[p], prm.fz * prm.fz)));
+            negn[p] = ok ? (EXH ? INFINITY : -nv * 0.99999905f) : -INFINITY;
+            best_t[p] = INFINITY;
+            best_id[p] = -1;
+        }
+        // tile axis in the camera frame: nominal tile centre on the image plane (warp-uniform)
+        float ax, ay, az;
+        {
+            const int k0 = ty * P;
+            const float cx = prm.dx_tab[min(tx * 32, prm.W - 1)] + 15.5f * prm.px_delta;
+            const float cy = prm.dy_tab[min(k0, prm.n_rows - 1)] + 0.5f * (float)(P - 1) * (float)prm.y_step * prm.px_delta;
+            const float inv = rsqrtf(fmaf(cx, cx, fmaf(cy, cy, prm.fz * prm.fz)));
+            ax = cx * inv;
+            ay = cy * inv;
+            az = prm.fz * inv;
+        }
+
+        tp.begin_round();
+        for (int c = 0; c < tp.n_chunks; c++) {
+            const float4* tile = tp.acquire(c);
+            const int cnt = tp.count(c);
+            const int base = c * tp.chunk;
+#pragma unroll 1
+            for (int s = 0; s < cnt; s += 32) {
+                // n_spheres_pad is a multiple of 16, chunks are multiples of 32 except possibly the last
+                const bool in = s + lane < cnt;
+                const float4 rec = in ? tile[s + lane] : make_float4(0.f, 0.f, 0.f, ORE_BIG);
+                const float hA = fmaf(ax, rec.x, fmaf(ay, rec.y, fmaf(az, rec.z, rec.w)));
+                const bool cand = in && (base + s + lane) < prm.n_spheres && (EXH || hA <= 0.f);
+                uint32_t mask = __ballot_sync(0xffffffffu, cand && tile_ok);
+                while (mask) {
+                    const int i = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const int idx = base + s + i;
+                    const float4 q = __ldg(&prm.sph_prim[idx]);
+                    const float e = fmaf(dx, q.x, q.z);
+                    bool any = false;
+#pragma unroll
+                    for (int p = 0; p < P; p++) any |= (fmaf(dyp[p], q.y, e) <= negn[p]);
+                    if (any) {
+                        const float4 ex = __ldg(&prm.sph_exact[idx]);
+#pragma unroll
+                        for (int p = 0; p < P; p++) {
+                            if (fmaf(dyp[p], q.y, e) <= negn[p]) {
+                                float t;
+                                n_exact++;
+                                if (ref_intersect(O, D[p], ex.x, ex.y, ex.z, ex.w, t)) {
+                                    if (t < best_t[p]) {
+                                        best_t[p] = t;
+                                        best_id[p] = idx;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            tp.release(c);
+        }
+
+        // ---- epilogue: records, sky for misses, hit-list compaction (row-major inside the tile) ----
+        uint32_t warp_hits = 0;
+        uint32_t my_off[P];
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+            const int k = ty * P + p;
+            const bool ok = x_ok && k < prm.n_rows;
+            const bool hit = ok && best_id[p] >= 0;
+            if (ok) {
+                const size_t o = (size_t)k * prm.W + x;
+                prm.hit_id[o] = best_id[p];
+                prm.hit_t[o] = best_t[p];
+                if (!hit) {
+                    // skybox::getFColor, kernel.cu:1146-1166
+                    float t;
+                    ref_intersect(O, D[p], 0.f, 0.f, 0.f, prm.sky_radius, t);
+                    v3 hp = ref_add(O, ref_scale(D[p], t));
+                    v3 n = ref_sub(hp, mk(0.f, 0.f, 0.f));
+                    ref_normalise(n);
+                    int sx = (int)((1.f + atan2f(n.z, n.x) / 3.1415f) * 0.5f * (float)prm.sky_w);
+                    int sy = (int)(acosf(n.y) / 3.1415f * (float)prm.sky_h);
+                    int index = clamp_index(sy * prm.sky_w + sx, prm.sky_w * prm.sky_h);
+                    float r = __ldg(&prm.sky_r[index]), g = __ldg(&prm.sky_g[index]), b = __ldg(&prm.sky_b[index]);
+                    prm.pixels[(size_t)k * prm.pitch + x] = ref_rgb_to_int((int)(r * 254.f), (int)(g * 254.f), (int)(b * 254.f));
+                }
+            }
+            const uint32_t bal = __ballot_sync(0xffffffffu, hit);
+            my_off[p] = warp_hits + __popc(bal & ((1u << lane) - 1u));
+            warp_hits += __popc(bal);
+        }
+        if (lane == 0) warp_tot[warp] = warp_hits;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t tot = 0;
+            for (int w = 0; w < CTA_WARPS; w++) {
+                uint32_t v = warp_tot[w];
+                warp_tot[w] = tot;
+                tot += v;
+            }
+            cta_base = tot ? (uint32_t)atomicAdd(&prm.counters[CNT_HITS], (unsigned long long)tot) : 0u;
+        }
+        __syncthreads();
+        const uint32_t wbase = cta_base + warp_tot[warp];
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+            const int k = ty * P + p;
+            if (x_ok && k < prm.n_rows && best_id[p] >= 0) prm.hit_list[wbase + my_off[p]] = (uint32_t)((size_t)k * prm.W + x);
+        }
+        __syncthreads();  // warp_tot / cta_base reuse
+    }
+    if (n_exact) atomicAdd(&prm.counters[CNT_EXACT_PRIMARY], n_exact);
+}
+
+// ------------------------------------------------------------------------------------
 // shadow ray directions of one light: castLightRay set-up, kernel.cu:1438-1468.
 // Writes 10 directions to dir[] and returns a = dot(normal, toL) with the toL left
 // after the loop (kernel.cu:1541).  toL is re-normalised in place twice per sample.
@@ -398,6 +567,72 @@ __device__ __noinline__ float light_directions(const LightP L, const v3 start, c
         dir[j * 3 + 2] = nn.z;
     }
     return ref_dot(normal, toL);
+}
+
+// ------------------------------------------------------------------------------------
+// light_directions_n: the same set-up for up to NL lights in lockstep (independent chains
+// overlap), with exact reuse: every per-sample quantity except _z/x/y is a pure function of
+// the toL seen at the top of the iteration, and that toL stops changing once the in-place
+// re-normalisation reaches a fixed point (usually after one or two samples).  While toL
+// repeats bit for bit, angle and the rotate() matrix are reused instead of recomputed.
+// ------------------------------------------------------------------------------------
+template <int NL>
+__device__ __forceinline__ void light_directions_n(const FrameParams& prm, int l0, int n_act, const v3 start,
+                                                   const v3 normal, float* __restrict__ dirs /* [NL][10][3] */,
+                                                   float (&a_out)[NL]) {
+    const v3 up = mk(0.f, 1.f, 0.f), fwd = mk(0.f, 0.f, 1.f);
+    v3 lpos[NL], toL[NL], prev[NL];
+    float lsize[NL], angle[NL];
+    RotM M[NL];
+#pragma unroll
+    for (int l = 0; l < NL; l++) {
+        if (l < n_act) {
+            const LightP L = prm.lights[l0 + l];
+            lpos[l] = mk(L.px, L.py, L.pz);
+            lsize[l] = L.size;
+            v3 tmp = ref_sub(lpos[l], start);
+            toL[l] = ref_normalise(tmp);
+        } else {
+            lpos[l] = toL[l] = mk(0.f, 0.f, 0.f);
+            lsize[l] = 0.f;
+        }
+        prev[l] = mk(__int_as_float(0x7fc00001), 0.f, 0.f);  // matches nothing
+        angle[l] = 0.f;
+        M[l] = RotM{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    }
+#pragma unroll 1
+    for (int j = 0; j < 10; j++) {
+#pragma unroll
+        for (int l = 0; l < NL; l++) {
+            if (l < n_act) {
+                if (!same_bits(toL[l], prev[l])) {
+                    prev[l] = toL[l];
+                    v3 P = ref_cross(toL[l], up);
+                    v3 e = ref_sub(ref_add(lpos[l], ref_scale(P, lsize[l])), start);
+                    v3 toEdge = ref_normalise(e);
+                    angle[l] = cosf((ref_dot(toL[l], toEdge)) * 2);
+                    v3 n1 = ref_normalise(toL[l]);
+                    v3 ax = ref_cross(fwd, n1);
+                    v3 axis = ref_normalise(ax);
+                    v3 n2 = ref_normalise(toL[l]);
+                    float nAngle = acosf(ref_dot(n2, fwd));
+                    M[l] = ref_rotate_matrix(nAngle, axis);
+                }
+                const float _z = (float)j / 10 * (1.0f - angle[l]) + angle[l];
+                const float sq = sqrtf(1.f - _z * _z);
+                const float x = sq * c_cos_phi[j];
+                const float y = sq * c_sin_phi[j];
+                v3 nd = ref_sub(lpos[l], ref_matrix_apply(M[l], mk(x, y, _z)));
+                v3 nn = ref_normalise(nd);
+                float* d = dirs + (l * 10 + j) * 3;
+                d[0] = nn.x;
+                d[1] = nn.y;
+                d[2] = nn.z;
+            }
+        }
+    }
+#pragma unroll
+    for (int l = 0; l < NL; l++) a_out[l] = (l < n_act) ? ref_dot(normal, toL[l]) : 0.f;
 }
 
 // ------------------------------------------------------------------------------------
@@ -668,14 +903,16 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) shadow_cone_kernel(const Frame
             float Ax[NL], Ay[NL], Az[NL], ca[NL], sa[NL], a_l[NL];
             uint32_t blocked = ALL;
             bool force = false;  // some light cannot use the cone test: every sphere is a candidate
+            {
+                const int n_act = valid ? min(NL, prm.n_lights - l0) : 0;
+                light_directions_n<NL>(prm, l0, n_act, start, normal, dirs, a_l);
+            }
 #pragma unroll
             for (int l = 0; l < NL; l++) {
                 const bool lit = valid && (l0 + l) < prm.n_lights;
-                a_l[l] = 0.f;
                 Ax[l] = Ay[l] = Az[l] = ca[l] = sa[l] = 0.f;
                 if (lit) {
                     float* d = dirs + 30 * l;
-                    a_l[l] = light_directions(prm.lights[l0 + l], start, normal, d);
                     blocked &= ~(0x3ffu << (10 * l));
                     // cone of the 10 rays: axis = normalised sum, cos(a) = min_j axis.D_j
                     float sx = 0.f, sy = 0.f, sz = 0.f;
@@ -797,6 +1034,308 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) shadow_cone_kernel(const Frame
                     }
                 }
                 tp.release(c);
+            }
+
+            // ---- light accumulation (kernel.cu:1537-1543, 1673-1675) ----
+            if (valid) {
+#pragma unroll
+                for (int l = 0; l < NL; l++) {
+                    if (l0 + l < prm.n_lights) {
+                        float b = 0;
+#pragma unroll
+                        for (int j = 0; j < 10; j++)
+                            if (!((blocked >> (l * 10 + j)) & 1u)) b = (float)((double)b + 0.1);
+                        const float a = a_l[l];
+                        b *= a > 0 ? a : 0;
+                        const LightP L = prm.lights[l0 + l];
+                        fr += b * L.r * tr;
+                        fg += b * L.g * tg;
+                        fb += b * L.b * tb;
+                    }
+                }
+            }
+        }
+        if (valid) prm.pixels[o_out] = ref_rgb_to_int((int)(fr * 254.f), (int)(fg * 254.f), (int)(fb * 254.f));
+    }
+    if (n_exact) atomicAdd(&prm.counters[CNT_EXACT_SHADOW], n_exact);
+}
+
+// ------------------------------------------------------------------------------------
+// shadow_beam_kernel (default shadow path)
+//
+// shadow_cone_kernel with one more level in front: a warp's 32 hit pixels are neighbours
+// (hit-list order = row-major inside a 32 x P tile), so their ray origins fit in a small
+// region and their per-light cones in one slightly wider cone around a common axis line.
+// Level 1: lane i tests sphere s0+i against the three warp beams (axial / lateral distance
+// to the axis line through the origins' centroid) and the warp ballots.  Level 2: each lane
+// runs its own per-pixel cone test, then the per-ray filter and the exact sequence, on the
+// survivors.  A hit at X = S_i + tD (t >= 0) has axial coordinate <= centre + R and lateral
+// offset <= rho_perp + t sin(a), which is exactly what level 1 bounds.
+// ------------------------------------------------------------------------------------
+template <bool EXH>
+__global__ void __launch_bounds__(CTA_THREADS, 2) shadow_beam_kernel(const FrameParams prm) {
+    constexpr int NL = 3;        // lights per pass
+    constexpr int NR = 10 * NL;
+    constexpr uint32_t ALL = (1u << NR) - 1u;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bars[MAX_STAGES];
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    // Sphere records (cx,cy,cz,R'): the whole array is staged once per CTA into shared memory by one
+    // TMA bulk copy when it fits; larger scenes are read through L1/L2 (256 KiB for 16384 spheres).
+    // Either way warps run independently: each fetches 32 consecutive hit pixels at a time.
+    const float4* __restrict__ spheres = prm.sph_shad;
+    if (prm.resident) {
+        float4* slot = reinterpret_cast<float4*>(smem_raw);
+        if (tid == 0) {
+            mbar_init(&bars[0], 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t bytes = (uint32_t)prm.n_spheres_pad * 16u;
+            mbar_expect_tx(&bars[0], bytes);
+            tma_bulk_g2s(slot, prm.sph_shad, bytes, &bars[0]);
+        }
+        mbar_wait(&bars[0], 0);
+        spheres = slot;
+    }
+    const int n_sph = prm.n_spheres;
+
+    const uint32_t n_items = (uint32_t)prm.counters[CNT_HITS];
+    const v3 O0 = mk(prm.Ox, prm.Oy, prm.Oz);
+    unsigned long long n_exact = 0;
+
+    for (;;) {
+        uint32_t wb = 0;
+        if (lane == 0) wb = (uint32_t)atomicAdd(&prm.counters[CNT_SHADOW_CURSOR], 1ull);
+        wb = __shfl_sync(0xffffffffu, wb, 0);
+        if ((unsigned long long)wb * 32ull >= n_items) break;
+        const uint32_t item = wb * 32u + lane;
+        const bool valid = item < n_items;
+
+        // ---- shading set-up (kernel.cu:1396-1405, 1643-1655) ----
+        size_t o_out = 0;
+        v3 start = mk(1e9f, 1e9f, 1e9f), normal = mk(0.f, 0.f, 0.f);
+        float tr = 0.f, tg = 0.f, tb = 0.f;
+        if (valid) {
+            const uint32_t o = prm.hit_list[item];
+            const int k = (int)(o / (uint32_t)prm.W), x = (int)(o % (uint32_t)prm.W);
+            o_out = (size_t)k * prm.pitch + x;
+            const v3 D = primary_dir(prm, prm.dx_tab[x], prm.dy_tab[k]);
+            const float nt = prm.hit_t[o];
+            const float4 sc = __ldg(&prm.sph_exact[prm.hit_id[o]]);
+            const v3 new_org = ref_add(O0, ref_scale(D, nt));
+            normal = ref_sub(new_org, mk(sc.x, sc.y, sc.z));
+            ref_normalise(normal);
+            const float txf = (float)((1 + (double)atan2f(normal.z, normal.x) / 3.1415) * 0.5);
+            const float tyf = (float)((double)acosf(normal.y) / 3.1415);
+            const int maxX = prm.tex_w, maxY = prm.tex_h;
+            start = ref_add(ref_scale(normal, 0.00001f), new_org);
+            int c_index = (int)(tyf * (float)maxY) * maxX + (int)(txf * (float)maxX);
+            c_index = clamp_index(c_index, maxX * maxY);
+            tr = __ldg(&prm.tex_r[c_index]);
+            tg = __ldg(&prm.tex_g[c_index]);
+            tb = __ldg(&prm.tex_b[c_index]);
+        }
+        float fr = 0.f, fg = 0.f, fb = 0.f;
+
+        for (int l0 = 0; l0 < prm.n_lights; l0 += NL) {
+            float dirs[NR * 3];  // local memory (L1): only the rare per-ray path reads it
+            float Ax[NL], Ay[NL], Az[NL], ca[NL], sa[NL], a_l[NL];
+            uint32_t blocked = ALL;
+            bool force = false;  // some light cannot use the cone test: every sphere is a candidate
+            {
+                const int n_act = valid ? min(NL, prm.n_lights - l0) : 0;
+                light_directions_n<NL>(prm, l0, n_act, start, normal, dirs, a_l);
+            }
+#pragma unroll
+            for (int l = 0; l < NL; l++) {
+                const bool lit = valid && (l0 + l) < prm.n_lights;
+                Ax[l] = Ay[l] = Az[l] = ca[l] = sa[l] = 0.f;
+                if (lit) {
+                    float* d = dirs + 30 * l;
+                    blocked &= ~(0x3ffu << (10 * l));
+                    // cone of the 10 rays: axis = normalised sum, cos(a) = min_j axis.D_j
+                    float sx = 0.f, sy = 0.f, sz = 0.f;
+#pragma unroll 1
+                    for (int j = 0; j < 10; j++) {
+                        sx += d[j * 3];
+                        sy += d[j * 3 + 1];
+                        sz += d[j * 3 + 2];
+                    }
+                    const float inv = rsqrtf(fmaf(sx, sx, fmaf(sy, sy, sz * sz)));
+                    float cmin = 1.f;
+                    bool ok = isfinite(inv);
+                    if (ok) {
+                        sx *= inv;
+                        sy *= inv;
+                        sz *= inv;
+#pragma unroll 1
+                        for (int j = 0; j < 10; j++) {
+                            const float dd = fmaf(d[j * 3], d[j * 3], fmaf(d[j * 3 + 1], d[j * 3 + 1], d[j * 3 + 2] * d[j * 3 + 2]));
+                            ok = ok && fabsf(dd - 1.f) < 1e-4f;  // the filters assume |D| = 1 (normalised by the reference)
+                            cmin = fminf(cmin, fmaf(sx, d[j * 3], fmaf(sy, d[j * 3 + 1], sz * d[j * 3 + 2])));
+                        }
+                    }
+                    if (ok && cmin > 0.5f && !EXH) {
+                        const float cosa = cmin - 4e-6f;
+                        const float sina = sqrtf(fmaxf(0.f, fmaf(-cosa, cosa, 1.f))) * 1.0001f + 1e-6f;
+                        Ax[l] = sx;
+                        Ay[l] = sy;
+                        Az[l] = sz;
+                        ca[l] = cosa - 0.00196f * sina;
+                        sa[l] = 1.002f * sina;
+                    } else {
+                        // degenerate bundle (zero direction, very wide cone) or exhaustive mode
+                        force = true;
+                    }
+                }
+            }
+
+            // ---- warp beams: per light one axis line through the origins' centroid; the warp's rays of
+            //      that light stay within rho_perp + (axial distance) * tan(a) of it (DESIGN.md "Beam test")
+            const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+            const float nvalid = (float)__popc(vmask);
+            float bx = valid ? start.x : 0.f, by = valid ? start.y : 0.f, bz = valid ? start.z : 0.f;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                bx += __shfl_xor_sync(0xffffffffu, bx, d);
+                by += __shfl_xor_sync(0xffffffffu, by, d);
+                bz += __shfl_xor_sync(0xffffffffu, bz, d);
+            }
+            const float inv_n = 1.f / fmaxf(nvalid, 1.f);
+            bx *= inv_n;
+            by *= inv_n;
+            bz *= inv_n;
+            const float ex = valid ? start.x - bx : 0.f, ey = valid ? start.y - by : 0.f, ez = valid ? start.z - bz : 0.f;
+            const float escale = 1e-5f * (fabsf(bx) + fabsf(by) + fabsf(bz) + 1.f);  // rounding slack on offsets
+            bool wforce = __any_sync(0xffffffffu, valid && force);
+            float wAx[NL], wAy[NL], wAz[NL], wtan[NL], wk1[NL], wk2[NL];  // k1 = -a_min, k2 = rho_perp
+#pragma unroll
+            for (int l = 0; l < NL; l++) {
+                const bool part = valid && ca[l] > 0.f;  // lanes whose light l takes part (lit, not degenerate)
+                float sx = part ? Ax[l] : 0.f, sy = part ? Ay[l] : 0.f, sz = part ? Az[l] : 0.f;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {
+                    sx += __shfl_xor_sync(0xffffffffu, sx, d);
+                    sy += __shfl_xor_sync(0xffffffffu, sy, d);
+                    sz += __shfl_xor_sync(0xffffffffu, sz, d);
+                }
+                const float n2 = fmaf(sx, sx, fmaf(sy, sy, sz * sz));
+                const float inv = rsqrtf(fmaxf(n2, 1e-30f));
+                sx *= inv;
+                sy *= inv;
+                sz *= inv;
+                // widest angle between the warp axis and any participating ray: theta_lane + a_lane
+                float cw = 1.f, amin = 3e38f, rp = 0.f;
+                if (part) {
+                    const float sina = sa[l] * (1.f / 1.002f);
+                    const float cosa = ca[l] + 0.00196f * sina;
+                    const float c1 = fminf(1.f, fmaf(sx, Ax[l], fmaf(sy, Ay[l], sz * Az[l])));
+                    const float s1 = sqrtf(fmaxf(0.f, fmaf(-c1, c1, 1.f))) + 1e-6f;
+                    cw = fmaf(c1, cosa, -(s1 * sina)) - 2e-6f;
+                    const float ai = fmaf(ex, sx, fmaf(ey, sy, ez * sz));  // axial offset of this origin
+                    const float px = ex - ai * sx, py = ey - ai * sy, pz = ez - ai * sz;
+                    amin = ai;
+                    rp = sqrtf(fmaf(px, px, fmaf(py, py, pz * pz)));
+                }
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {
+                    cw = fminf(cw, __shfl_xor_sync(0xffffffffu, cw, d));
+                    amin = fminf(amin, __shfl_xor_sync(0xffffffffu, amin, d));
+                    rp = fmaxf(rp, __shfl_xor_sync(0xffffffffu, rp, d));
+                }
+                const bool any_part = __any_sync(0xffffffffu, part);
+                wAx[l] = wAy[l] = wAz[l] = 0.f;
+                wtan[l] = 0.f;
+                wk1[l] = -3e38f;  // u = sc + R' + k1 < 0: never a candidate
+                wk2[l] = 0.f;
+                if (any_part) {
+                    if (!(n2 > 1e-12f) || !(cw > 0.3f)) {
+                        wforce = true;  // bundle axes disagree wildly: no warp-level culling
+                    } else {
+                        const float sinw = sqrtf(fmaxf(0.f, fmaf(-cw, cw, 1.f))) * 1.0001f + 1e-6f;
+                        wAx[l] = sx;
+                        wAy[l] = sy;
+                        wAz[l] = sz;
+                        wtan[l] = sinw / cw * 1.0001f;
+                        wk1[l] = -(amin - escale);
+                        wk2[l] = rp * 1.0001f + escale;
+                    }
+                }
+            }
+            if (EXH) wforce = true;
+
+            bool warp_done = false;
+#pragma unroll 1
+            for (int s0 = 0; s0 < n_sph && !warp_done; s0 += 32) {
+                // ---- level 1: lane i tests sphere s0+i against the warp's beams ----
+                const bool in = s0 + lane < n_sph;
+                bool wc = false;
+                if (in) {
+                    const float4 q = spheres[s0 + lane];
+                    const float Lx = bx - q.x, Ly = by - q.y, Lz = bz - q.z;
+                    const float LL = fmaf(Lz, Lz, fmaf(Ly, Ly, Lx * Lx));
+                    const float Rq = fmaf(q.w, 1.0001f, fmaf(LL, 1e-12f, 1e-6f));  // radius + rounding slack
+                    const float slack = LL * 2e-6f;                                 // cancellation in LL - sc^2
+#pragma unroll
+                    for (int l = 0; l < NL; l++) {
+                        const float sc = -fmaf(wAx[l], Lx, fmaf(wAy[l], Ly, wAz[l] * Lz));  // centre's axial coordinate
+                        const float u = sc + Rq + wk1[l];                                     // >= 0 unless wholly behind
+                        const float thr = fmaf(u, wtan[l], Rq + wk2[l]);
+                        const float d2 = fmaf(-sc, sc, LL);
+                        wc = wc || (u >= 0.f && d2 <= fmaf(thr, thr, slack));
+                    }
+                    wc = wc || wforce;
+                }
+                uint32_t wmask = __ballot_sync(0xffffffffu, wc);
+                // ---- level 2: every lane runs its own cone test on the surviving spheres ----
+                while (wmask) {
+                    const int i = __ffs(wmask) - 1;
+                    wmask &= wmask - 1;
+                    const int s = s0 + i;
+                    const float4 q = spheres[s];
+                    const float lx = start.x - q.x, ly = start.y - q.y, lz = start.z - q.z;
+                    const float LL = fmaf(lz, lz, fmaf(ly, ly, lx * lx));
+                    const float Cm = fmaf(LL, 1.0f - ORE_KAPPA_SHADOW, -(q.w * q.w));
+                    const float sq = Cm * rsqrt_approx(Cm);
+                    const float svu = (EXH || !(Cm > 1e-20f)) ? -ORE_BIG : sq;
+                    uint32_t live = ~blocked & ALL;
+                    if (!force) {
+                        uint32_t lm = 0;
+#pragma unroll
+                        for (int l = 0; l < NL; l++) {
+                            const float T = fmaf(ca[l], svu, -(sa[l] * q.w));
+                            if (fmaf(Ax[l], lx, fmaf(Ay[l], ly, fmaf(Az[l], lz, T))) < 0.f) lm |= 0x3ffu << (10 * l);
+                        }
+                        live &= lm;
+                    }
+                    if (live) {
+                        const float4 ex4 = __ldg(&prm.sph_exact[s]);
+                        while (live) {
+                            const int j = __ffs(live) - 1;
+                            live &= live - 1;
+                            const v3 D = mk(dirs[j * 3], dirs[j * 3 + 1], dirs[j * 3 + 2]);
+                            const float h = fmaf(D.x, lx, fmaf(D.y, ly, fmaf(D.z, lz, svu)));
+                            if (h < 0.f) {
+                                float t;
+                                n_exact++;
+                                if (ref_intersect(start, D, ex4.x, ex4.y, ex4.z, ex4.w, t)) blocked |= 1u << j;
+                            }
+                        }
+#pragma unroll
+                        for (int l = 0; l < NL; l++) {
+                            if (((blocked >> (10 * l)) & 0x3ffu) == 0x3ffu) {
+                                Ax[l] = Ay[l] = Az[l] = 0.f;
+                                ca[l] = 0.f;
+                                sa[l] = 0.f;
+                            }
+                        }
+                    }
+                }
+                if (__all_sync(0xffffffffu, blocked == ALL)) warp_done = true;
             }
 
             // ---- light accumulation (kernel.cu:1537-1543, 1673-1675) ----
