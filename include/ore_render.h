@@ -91,6 +91,8 @@ typedef struct ore_counters {
     uint64_t exact_primary;   /* exact re-adjudications executed, primary phase           */
     uint64_t exact_shadow;    /* exact re-adjudications executed, shadow phase            */
     uint64_t kernel_launches; /* kernels launched by the call                             */
+    uint64_t beam_l1;         /* spheres passing the warp-level beam test (sum over warps) */
+    uint64_t beam_l2;         /* (pixel, sphere) pairs passing the per-pixel cone test     */
 } ore_counters;
 
 /* ---- lifetime ---------------------------------------------------------------------

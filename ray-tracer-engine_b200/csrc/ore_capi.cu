@@ -139,6 +139,16 @@ extern "C" int ore_create(ore_context** out, int device) {
     }
     ORE_CUDA(ctx, cudaMemcpyToSymbol(c_cos_phi, cphi, sizeof cphi));
     ORE_CUDA(ctx, cudaMemcpyToSymbol(c_sin_phi, sphi, sizeof sphi));
+    float bk[11];
+    {
+        float b = 0;
+        bk[0] = b;
+        for (int k = 1; k <= 10; k++) {
+            b += 0.1;  // float += double, kernel.cu:1538
+            bk[k] = b;
+        }
+    }
+    ORE_CUDA(ctx, cudaMemcpyToSymbol(c_b_of_k, bk, sizeof bk));
     return ORE_OK;
 }
 
@@ -588,6 +598,8 @@ extern "C" int ore_get_counters(ore_context* ctx, ore_counters* out) {
     out->exact_primary = c[CNT_EXACT_PRIMARY];
     out->exact_shadow = c[CNT_EXACT_SHADOW];
     out->kernel_launches = ctx->last_launches;
+    out->beam_l1 = c[CNT_BEAM_L1];
+    out->beam_l2 = c[CNT_BEAM_L2];
     return ORE_OK;
 }
 

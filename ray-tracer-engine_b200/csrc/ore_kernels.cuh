@@ -47,6 +47,8 @@ enum CounterSlot {
     CNT_EXACT_SHADOW = 3,
     CNT_SHADOW_TESTS_REF = 4,
     CNT_COUNT_CURSOR = 5,
+    CNT_BEAM_L1 = 6,   // spheres passing the warp-level beam test (summed over warps and light passes)
+    CNT_BEAM_L2 = 7,   // (pixel, sphere) pairs passing the per-pixel cone test
     CNT_SLOTS = 8
 };
 
@@ -88,6 +90,9 @@ struct FrameParams {
 // values, evaluated once on the host (same libm as the oracle) at context creation
 __constant__ float c_cos_phi[10];
 __constant__ float c_sin_phi[10];
+// b after k unshadowed samples: `b += 0.1` is float += double (kernel.cu:1537-1539), so b depends only on
+// how many of the 10 samples were unshadowed; the 11 values are produced on the host with that arithmetic
+__constant__ float c_b_of_k[11];
 
 // ------------------------------------------------------------------------------------
 // primary ray of pixel (x, row k): kernel.cu:1624-1631 with dx/dy from the tables
@@ -810,10 +815,7 @@ __global__ void __launch_bounds__(SHADOW_THREADS, ORE_SHADOW_MIN_CTAS) shadow_ke
 #pragma unroll
                 for (int l = 0; l < NL; l++) {
                     if (l0 + l < prm.n_lights) {
-                        float b = 0;
-#pragma unroll
-                        for (int j = 0; j < 10; j++)
-                            if (!((blocked >> (l * 10 + j)) & 1u)) b = (float)((double)b + 0.1);
+                        float b = c_b_of_k[10 - __popc((blocked >> (l * 10)) & 0x3ffu)];
                         const float a = a_l[l];
                         b *= a > 0 ? a : 0;
                         const LightP L = prm.lights[l0 + l];
@@ -1041,10 +1043,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) shadow_cone_kernel(const Frame
 #pragma unroll
                 for (int l = 0; l < NL; l++) {
                     if (l0 + l < prm.n_lights) {
-                        float b = 0;
-#pragma unroll
-                        for (int j = 0; j < 10; j++)
-                            if (!((blocked >> (l * 10 + j)) & 1u)) b = (float)((double)b + 0.1);
+                        float b = c_b_of_k[10 - __popc((blocked >> (l * 10)) & 0x3ffu)];
                         const float a = a_l[l];
                         b *= a > 0 ? a : 0;
                         const LightP L = prm.lights[l0 + l];
@@ -1106,6 +1105,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) shadow_beam_kernel(const Frame
     const uint32_t n_items = (uint32_t)prm.counters[CNT_HITS];
     const v3 O0 = mk(prm.Ox, prm.Oy, prm.Oz);
     unsigned long long n_exact = 0;
+    unsigned int n_l1 = 0, n_l2 = 0;
 
     for (;;) {
         uint32_t wb = 0;
@@ -1291,6 +1291,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) shadow_beam_kernel(const Frame
                     wc = wc || wforce;
                 }
                 uint32_t wmask = __ballot_sync(0xffffffffu, wc);
+                n_l1 += __popc(wmask);
                 // ---- level 2: every lane runs its own cone test on the surviving spheres ----
                 while (wmask) {
                     const int i = __ffs(wmask) - 1;
@@ -1313,6 +1314,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) shadow_beam_kernel(const Frame
                         live &= lm;
                     }
                     if (live) {
+                        n_l2++;
                         const float4 ex4 = __ldg(&prm.sph_exact[s]);
                         while (live) {
                             const int j = __ffs(live) - 1;
@@ -1343,10 +1345,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) shadow_beam_kernel(const Frame
 #pragma unroll
                 for (int l = 0; l < NL; l++) {
                     if (l0 + l < prm.n_lights) {
-                        float b = 0;
-#pragma unroll
-                        for (int j = 0; j < 10; j++)
-                            if (!((blocked >> (l * 10 + j)) & 1u)) b = (float)((double)b + 0.1);
+                        float b = c_b_of_k[10 - __popc((blocked >> (l * 10)) & 0x3ffu)];
                         const float a = a_l[l];
                         b *= a > 0 ? a : 0;
                         const LightP L = prm.lights[l0 + l];
@@ -1360,6 +1359,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) shadow_beam_kernel(const Frame
         if (valid) prm.pixels[o_out] = ref_rgb_to_int((int)(fr * 254.f), (int)(fg * 254.f), (int)(fb * 254.f));
     }
     if (n_exact) atomicAdd(&prm.counters[CNT_EXACT_SHADOW], n_exact);
+    if (lane == 0 && n_l1) atomicAdd(&prm.counters[CNT_BEAM_L1], (unsigned long long)n_l1);
+    if (n_l2) atomicAdd(&prm.counters[CNT_BEAM_L2], (unsigned long long)n_l2);
 }
 
 // ------------------------------------------------------------------------------------

@@ -24,7 +24,8 @@ def main():
     out = np.empty((H, W), dtype=np.uint32)
     for f in range(a.frames):
         r.render(camera(f), W, H, out=out, flags=a.flags)
-        print(f, [round(v, 3) for v in r.kernel_ms()[:3]], r.counters()["hit_pixels"], flush=True)
+        c = r.counters()
+        print(f, [round(v, 3) for v in r.kernel_ms()[:3]], c["hit_pixels"], "L1/warp", round(c["beam_l1"] / max(1, c["hit_pixels"] / 32), 1), "L2/px", round(c["beam_l2"] / max(1, c["hit_pixels"]), 2), "exactS/px", round(c["exact_shadow"] / max(1, c["hit_pixels"]), 1), "exactP/px", round(c["exact_primary"] / c["pixels"], 2), flush=True)
     r.close()
 
 
