@@ -1,0 +1,108 @@
+// kernel_shim.cpp - replaces the HOST half of the reference's kernel.cu for the sphere render path:
+// the global scene, onStart() (kernel.cu:1704-1714) and update() (kernel.cu:1762-1792), on top of the
+// C ABI in include/ore_render.h.  window.cpp links against this exactly as it links against kernel.cu.
+//
+// What changes relative to the reference's update(): no per-frame cudaMallocManaged/cudaMalloc/cudaFree
+// (kernel.cu:1775-1790) - the context owns persistent device buffers - and the frame lands in a pinned
+// host buffer by one async copy instead of managed-memory page migration; setPixelBuff still receives a
+// host-readable pointer and copies from it (window.cpp:130-132).
+#include "ore_host.h"
+
+#include <cmath>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "../../include/ore_render.h"
+#include "ore_memmanager.h"
+#include "ore_sprite.h"
+#include "ore_window_callbacks.h"
+
+#define checkOre(expr) check_ore((expr), #expr, g_ctx ? ore_last_error(g_ctx) : "", __FILE__, __LINE__)
+
+namespace {
+ore_context* g_ctx = nullptr;
+// kernel.cu:1692-1702 - the reference's globals
+int light_size = 3;
+ore_camera cam = {{4, 3, 10}, {0, 0, 1}, 0.f, 180.f, -20.f};          // camera cam({4,3,10},{0,0,1},0) + :261
+float aspect = (float)tan((90 * 0.5 * 3.1415) / 180);                  // kernel.cu:1701
+int g_sphere_count = 64;                                               // the reference ships 0 (kernel.cu:1231)
+unsigned g_seed = 1;                                                   // unseeded rand()
+std::string g_texture = "proc:smooth:512:512:102";
+std::string g_sky = "proc:smooth:1024:512:203";
+sprite* texture = nullptr;
+sprite* skyTex = nullptr;
+unsigned int* g_pixels = nullptr;  // pinned host frame handed to setPixelBuff
+size_t g_pixels_cap = 0;
+
+unsigned msvc_rand(unsigned& s) {
+    s = s * 214013u + 2531011u;
+    return (s >> 16) & 0x7fff;
+}
+}  // namespace
+
+void oreConfigureScene(int sphere_count, unsigned seed, const char* tex, const char* sky) {
+    g_sphere_count = sphere_count;
+    g_seed = seed;
+    if (tex) g_texture = tex;
+    if (sky) g_sky = sky;
+}
+
+void oreSetCamera(float x, float y, float z, float yaw_deg, float pitch_deg) {
+    cam.org[0] = x;
+    cam.org[1] = y;
+    cam.org[2] = z;
+    cam.yaw = yaw_deg;
+    cam.pitch = pitch_deg;
+}
+
+void onStart() {
+    checkOre(ore_create(&g_ctx, 0));
+    // object::loadMesh sphere generator, kernel.cu:1189-1191: centre = (rand()%100)/10, r = (rand()%100)/100;
+    // the sphere ctor stores r*r (kernel.cu:287)
+    std::vector<float> s((size_t)g_sphere_count * 4);
+    unsigned st = g_seed;
+    for (int i = 0; i < g_sphere_count; i++) {
+        s[4 * i + 0] = (float)(msvc_rand(st) % 100) / 10;
+        s[4 * i + 1] = (float)(msvc_rand(st) % 100) / 10;
+        s[4 * i + 2] = (float)(msvc_rand(st) % 100) / 10;
+        const float r = (float)(msvc_rand(st) % 100) / 100;
+        s[4 * i + 3] = r * r;
+    }
+    checkOre(ore_set_spheres(g_ctx, s.data(), g_sphere_count));
+    texture = new sprite(g_texture);   // objs->texture = new sprite(tex), kernel.cu:1201
+    skyTex = new sprite(g_sky);        // new skybox(img, 10000), kernel.cu:1700
+    checkOre(ore_set_texture(g_ctx, texture->rBuff->data, texture->gBuff->data, texture->bBuff->data, texture->width,
+                             texture->height));
+    checkOre(ore_set_sky(g_ctx, skyTex->rBuff->data, skyTex->gBuff->data, skyTex->bBuff->data, skyTex->width,
+                         skyTex->height, 10000.f));
+    // kernel.cu:1708-1712
+    const float lights[3][7] = {{20, 20, 20, 20, 1, 0, 0}, {0, 20, -20, 20, 0, 0, 1}, {0, 20, 0, 20, 0, 1, 0}};
+    checkOre(ore_set_lights(g_ctx, &lights[0][0], light_size));
+}
+
+void update() {
+    // checkKey() (kernel.cu:1716-1759) is Win32 key polling; headless callers use oreSetCamera()
+    const int width = getScreenWidth(), height = getScreenHeight();
+    const size_t n = (size_t)width * height;
+    cam.aspect = (float)height / width;  // kernel.cu:1773 (never read by the kernel)
+    if (n > g_pixels_cap) {
+        if (g_pixels) checkCudaErrors(cudaFreeHost(g_pixels));
+        checkCudaErrors(cudaMallocHost((void**)&g_pixels, n * sizeof(unsigned int)));
+        g_pixels_cap = n;
+    }
+    ore_frame fr = {width, height, 0, height, 1, aspect, ORE_FLAG_NONE, 0};
+    checkOre(ore_render(g_ctx, &cam, &fr, g_pixels));  // launch + sync + device->host, like :1783-1788
+    setPixelBuff(g_pixels);
+}
+
+void oreShutdown() {
+    if (g_ctx) ore_destroy(g_ctx);
+    g_ctx = nullptr;
+    delete texture;
+    delete skyTex;
+    texture = skyTex = nullptr;
+    if (g_pixels) cudaFreeHost(g_pixels);
+    g_pixels = nullptr;
+    g_pixels_cap = 0;
+}
