@@ -348,6 +348,25 @@ def main():
         except Exception:
             traffic = None
 
+    ref_gpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # the reference's OWN CUDA kernel built for sm_100 (oracle/_ref/libref_sm100*.so), same scene, 3 frames:
+        # reported alongside, never on our path
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oraclelib
+            ref_gpu = {}
+            cams = [camera(args.warmup + i) for i in range(3)]
+            for fast in (False, True):
+                if oraclelib.have_ref_gpu(fast):
+                    _, ms_up, ms_k = oraclelib.RefGpu(fast=fast).render(sc, cams, W, H)
+                    ref_gpu["use_fast_math" if fast else "default_flags"] = {
+                        "ms_per_update": ms_up, "ms_per_kernel": ms_k,
+                        "mrays_per_s_update": W * H / ms_up / 1e3, "mrays_per_s_kernel": W * H / ms_k / 1e3}
+            ref_gpu["what"] = ("the reference's rayTrace kernel / update() compiled unmodified in arithmetic for sm_100 "
+                               "(oracle/ref_build/make_ref_gpu.py), run headless on this GPU in this run")
+        except Exception as e:  # measurement extra only
+            ref_gpu = {"unavailable": str(e)[:200]}
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -390,6 +409,7 @@ def main():
                 "dram_write_gbs_framebuffer": W * H * 4 / world / ((k_primary_ms + k_shadow_ms) * 1e-3) / 1e9,
             },
             "cpu_baseline": cpu,
+            "reference_kernel_on_b200": ref_gpu,
         }
         print(json.dumps(line))
     if peer is not None:

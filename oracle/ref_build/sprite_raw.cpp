@@ -11,6 +11,7 @@
 // behaviour there.  The harness DEFINES it: every plane gets width+1 trailing floats
 // equal to its last texel, i.e. the out-of-range read behaves like an index clamp.
 // The CUDA path clamps the index, so both read identical values.
+#include <cstring>
 #include <map>
 #include <string>
 #include <vector>

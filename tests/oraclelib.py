@@ -105,6 +105,49 @@ class Oracle:
         return int(self.lib.oracle_rgb_to_int(int(r), int(g), int(b)))
 
 
+REF_GPU_SO = os.path.join(ORACLE_DIR, "_ref", "libref_sm100.so")
+REF_GPU_FAST_SO = os.path.join(ORACLE_DIR, "_ref", "libref_sm100_fast.so")
+
+
+class RefGpu:
+    """The reference's OWN rayTrace kernel + update() built for sm_100 (oracle/ref_build/make_ref_gpu.py).
+    Measurement infrastructure: "reference kernel on B200"."""
+
+    def __init__(self, fast: bool = False):
+        path = REF_GPU_FAST_SO if fast else REF_GPU_SO
+        if not os.path.isfile(path):
+            raise FileNotFoundError(path)
+        self.lib = C.CDLL(path)
+        self.lib.refgpu_render.restype = C.c_int
+        self.lib.refgpu_render.argtypes = [C.POINTER(OracleFrame), _fp, C.c_int, C.c_void_p, _fp, _fp]
+        self.fast = fast
+
+    def render(self, scene, cameras, width, height):
+        """cameras: list of Camera; returns (last frame u32[H,W], ms per update(), ms per bare kernel)"""
+        f = OracleFrame()
+        f.width, f.height, f.y0, f.y1, f.y_step = width, height, 0, height, 1
+        f.aspect = float(scene.aspect)
+        sph = np.ascontiguousarray(scene.spheres, dtype=np.float32)
+        lig = np.ascontiguousarray(scene.lights, dtype=np.float32)
+        f.n_spheres, f.spheres = sph.shape[0], _ptr(sph.reshape(-1))
+        f.n_lights, f.lights = lig.shape[0], _ptr(lig.reshape(-1))
+        t, s = scene.texture, scene.sky
+        f.tex_w, f.tex_h, f.tex_r, f.tex_g, f.tex_b = t.width, t.height, _ptr(t.r), _ptr(t.g), _ptr(t.b)
+        f.sky_w, f.sky_h, f.sky_r, f.sky_g, f.sky_b = s.width, s.height, _ptr(s.r), _ptr(s.g), _ptr(s.b)
+        f.sky_size = float(scene.sky_size)
+        cams = np.array([[*c.org, c.yaw, c.pitch] for c in cameras], dtype=np.float32)
+        px = np.zeros((height, width), dtype=np.uint32)
+        a, b = C.c_float(0), C.c_float(0)
+        rc = self.lib.refgpu_render(C.byref(f), _ptr(cams.reshape(-1)), len(cameras), px.ctypes.data, C.byref(a), C.byref(b))
+        if rc != 0:
+            raise RuntimeError(f"refgpu_render rc={rc}")
+        return px, float(a.value), float(b.value)
+
+
+def have_ref_gpu(fast: bool = False) -> bool:
+    return os.path.isfile(REF_GPU_FAST_SO if fast else REF_GPU_SO)
+
+
 def load(which: str = "port") -> Oracle:
     if which == "port":
         return Oracle(build_port())
