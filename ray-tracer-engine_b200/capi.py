@@ -23,6 +23,7 @@ EXPORTS = [
     "ore_set_spheres", "ore_set_spheres_aos32", "ore_set_lights", "ore_set_texture", "ore_set_sky",
     "ore_render", "ore_render_device", "ore_synchronize",
     "ore_get_hits", "ore_get_counters", "ore_get_kernel_ms", "ore_measure_fp32_peak",
+    "ore_render_async", "ore_wait", "ore_host_alloc", "ore_host_free",
     "ore_dev_alloc", "ore_dev_free", "ore_ipc_export", "ore_ipc_import", "ore_ipc_close", "ore_copy_to_host",
 ]
 
@@ -73,6 +74,10 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.ore_render.argtypes = [vp, C.POINTER(OreCamera), C.POINTER(OreFrame), vp]
     lib.ore_render_device.argtypes = [vp, C.POINTER(OreCamera), C.POINTER(OreFrame), vp, vp]
     lib.ore_synchronize.argtypes = [vp]
+    lib.ore_render_async.argtypes = [vp, C.POINTER(OreCamera), C.POINTER(OreFrame), vp]
+    lib.ore_wait.argtypes = [vp]
+    lib.ore_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+    lib.ore_host_free.argtypes = [vp, vp]
     lib.ore_get_hits.argtypes = [vp, vp, vp]
     lib.ore_get_counters.argtypes = [vp, C.POINTER(OreCounters)]
     lib.ore_get_kernel_ms.argtypes = [vp, C.POINTER(C.c_float * 4)]
@@ -228,6 +233,31 @@ class Renderer:
     def copy_to_host(self, host: np.ndarray, dev_ptr: int):
         assert host.flags["C_CONTIGUOUS"]
         self._check(self.lib.ore_copy_to_host(self.ctx, host.ctypes.data, C.c_void_p(dev_ptr), host.nbytes), "ore_copy_to_host")
+
+    # ---- pipelined presentation ----
+    def host_alloc(self, shape, dtype=np.uint32) -> np.ndarray:
+        """numpy view of pinned host memory allocated through the ABI (freed with host_free)."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        self._check(self.lib.ore_host_alloc(self.ctx, n, C.byref(p)), "ore_host_alloc")
+        buf = (C.c_ubyte * n).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+        self._pinned = getattr(self, "_pinned", {})
+        self._pinned[arr.ctypes.data] = p.value
+        return arr
+
+    def host_free(self, arr: np.ndarray):
+        p = getattr(self, "_pinned", {}).pop(arr.ctypes.data, None)
+        if p is not None:
+            self._check(self.lib.ore_host_free(self.ctx, C.c_void_p(p)), "ore_host_free")
+
+    def render_async(self, camera, width, height, out: np.ndarray, y0=0, y1=None, y_step=1, aspect=None, flags=0):
+        f = self._frame(width, height, y0, y1, y_step, aspect, flags)
+        cam = self._cam(camera)
+        self._check(self.lib.ore_render_async(self.ctx, C.byref(cam), C.byref(f), out.ctypes.data), "ore_render_async")
+
+    def wait(self):
+        self._check(self.lib.ore_wait(self.ctx), "ore_wait")
 
     def synchronize(self):
         self._check(self.lib.ore_synchronize(self.ctx), "ore_synchronize")

@@ -23,6 +23,11 @@ struct ore_context {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_rendered[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    uint32_t* pixels_b = nullptr;  // second device framebuffer (pipelined presentation)
+    size_t pixels_b_cap = 0;
+    unsigned long long async_frames = 0;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     bool ev_valid = false;
     bool ran_count = false;
@@ -127,6 +132,11 @@ extern "C" int ore_create(ore_context** out, int device) {
     }
     ctx->sm_count = prop.multiProcessorCount;
     ORE_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ORE_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        ORE_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_rendered[i], cudaEventDisableTiming));
+        ORE_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
+    }
     for (int i = 0; i < 5; i++) ORE_CUDA(ctx, cudaEventCreate(&ctx->ev[i]));
     ORE_CUDA(ctx, cudaMalloc((void**)&ctx->counters, CNT_SLOTS * sizeof(unsigned long long)));
     ORE_CUDA(ctx, cudaMemset(ctx->counters, 0, CNT_SLOTS * sizeof(unsigned long long)));
@@ -156,6 +166,13 @@ extern "C" int ore_destroy(ore_context* ctx) {
     if (!ctx) return ORE_ERR_INVALID;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->ev_rendered[i]) cudaEventDestroy(ctx->ev_rendered[i]);
+        if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
+    }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->pixels_b) cudaFree(ctx->pixels_b);
     void* dev[] = {ctx->sph_exact, ctx->sph_prim, ctx->sph_cone, ctx->sph_shad, ctx->tex[0], ctx->tex[1], ctx->tex[2],
                    ctx->sky[0],    ctx->sky[1],   ctx->sky[2],   ctx->dx_tab, ctx->dy_tab, ctx->hit_id,
                    ctx->hit_t,     ctx->hit_list, ctx->pixels,   ctx->counters};
@@ -516,6 +533,62 @@ extern "C" int ore_render(ore_context* ctx, const ore_camera* cam, const ore_fra
                                       ctx->stream));
     }
     ORE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ORE_OK;
+}
+
+extern "C" int ore_render_async(ore_context* ctx, const ore_camera* cam, const ore_frame* frame, uint32_t* out_host) {
+    if (!ctx) return ORE_ERR_INVALID;
+    if (!out_host || !frame) return fail(ctx, ORE_ERR_INVALID, "ore_render_async: null output/frame");
+    ORE_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int n_rows = frame->y_step > 0 ? (frame->y1 - frame->y0 + frame->y_step - 1) / frame->y_step : 0;
+    const size_t n_px = (size_t)(n_rows > 0 ? n_rows : 0) * (size_t)(frame->width > 0 ? frame->width : 0);
+    const int buf = (int)(ctx->async_frames & 1ull);
+    int rc;
+    // two device framebuffers: the context's own and a second one
+    if (n_px > ctx->pixels_b_cap) {
+        ORE_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+        if ((rc = ensure_dev(ctx, &ctx->pixels_b, &ctx->pixels_b_cap, n_px))) return rc;
+    }
+    if (n_px > ctx->px_cap || !ctx->pixels) {
+        // let render_impl size the per-frame buffers first (synchronously, once)
+        ORE_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+        ore_frame probe = *frame;
+        if ((rc = render_impl(ctx, cam, &probe, nullptr, ctx->stream))) return rc;
+        ORE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    uint32_t* target = buf ? ctx->pixels_b : ctx->pixels;
+    // do not overwrite a framebuffer whose previous copy is still in flight
+    ORE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[buf], 0));
+    ore_frame fr = *frame;
+    fr.out_pitch = 0;
+    if ((rc = render_impl(ctx, cam, &fr, target, ctx->stream))) return rc;
+    ORE_CUDA(ctx, cudaEventRecord(ctx->ev_rendered[buf], ctx->stream));
+    ORE_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rendered[buf], 0));
+    if (ctx->last_px)
+        ORE_CUDA(ctx, cudaMemcpyAsync(out_host, target, ctx->last_px * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                      ctx->copy_stream));
+    ORE_CUDA(ctx, cudaEventRecord(ctx->ev_copied[buf], ctx->copy_stream));
+    ctx->async_frames++;
+    return ORE_OK;
+}
+
+extern "C" int ore_wait(ore_context* ctx) {
+    if (!ctx) return ORE_ERR_INVALID;
+    ORE_CUDA(ctx, cudaSetDevice(ctx->device));
+    ORE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ORE_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    return ORE_OK;
+}
+
+extern "C" int ore_host_alloc(ore_context* ctx, size_t bytes, void** host_ptr) {
+    if (!ctx || !host_ptr || bytes == 0) return ORE_ERR_INVALID;
+    ORE_CUDA(ctx, cudaSetDevice(ctx->device));
+    ORE_CUDA(ctx, cudaMallocHost(host_ptr, bytes));
+    return ORE_OK;
+}
+extern "C" int ore_host_free(ore_context* ctx, void* host_ptr) {
+    if (!ctx) return ORE_ERR_INVALID;
+    ORE_CUDA(ctx, cudaFreeHost(host_ptr));
     return ORE_OK;
 }
 
