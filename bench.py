@@ -8,8 +8,9 @@
 
 A "step" is one frame: one pass of the hot path (frame prep -> primary nearest hit -> shadow +
 shade -> packed framebuffer) over one camera of the orbit.  Default workload = BASELINE.json
-configs[2] (3840x2160, 1024 spheres, 240-frame orbit): the configuration the north_star quotes
-its single-GPU target on.  With N > 1 the SAME frame is split into interleaved row bands
+configs[3] (7680x4320, 1024 spheres): the configuration the 1/2/4/8-GPU metric is quoted on; it fits
+one GPU, so the SAME workload runs at every N (at N = 1 the line also carries the 4K / 1024-sphere
+figures of configs[2], the scene of the single-GPU roofline target).  With N > 1 the frame is split into interleaved row bands
 (strong scaling) that the ranks store straight into the presenting GPU's framebuffer over
 NVLink (peer-mapped), plus one tiny NCCL all-reduce per frame as the completion signal.
 
@@ -167,7 +168,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="4k1024", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="8k1024", choices=sorted(WORKLOADS))
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -201,6 +202,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device - the render path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on stdout; rank 0's stdout is ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pkg.build.build_library()
     r = pkg.Renderer(local)
@@ -368,6 +371,26 @@ def main():
         except Exception:
             traffic = None
 
+    also_4k = None
+    if world == 1 and args.workload == "8k1024":
+        # configs[2] (4K / 1024 spheres, the single-GPU roofline scene): same scene, quarter of the pixels
+        W4, H4 = 3840, 2160
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ms4, kms4 = [], []
+        for i in range(args.warmup + 10):
+            flush_l2()
+            ev0.record(stream)
+            with torch.cuda.stream(stream):
+                r.render_device(camera(i), W4, H4, out_ptr=count_out, stream=stream.cuda_stream)
+            ev1.record(stream)
+            ev1.synchronize()
+            if i >= args.warmup:
+                ms4.append(ev0.elapsed_time(ev1))
+                kms4.append(r.kernel_ms())
+        also_4k = {"workload": WORKLOADS["4k1024"][5], "value": W4 * H4 / statistics.mean(ms4) / 1e3, "unit": "Mrays/s",
+                   "ms_per_step": statistics.mean(ms4), "steps": 10,
+                   "kernel_ms": {"prep": statistics.mean(m[0] for m in kms4), "primary": statistics.mean(m[1] for m in kms4),
+                                 "shadow": statistics.mean(m[2] for m in kms4)}}
     ref_gpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # the reference's OWN CUDA kernel built for sm_100 (oracle/_ref/libref_sm100*.so), same scene, 3 frames:
@@ -433,6 +456,7 @@ def main():
             },
             "cpu_baseline": cpu,
             "reference_kernel_on_b200": ref_gpu,
+            "also_configs2_4k1024": also_4k,
         }
         print(json.dumps(line))
     if host:

@@ -512,9 +512,34 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) primary_tile_kernel(const Fram
                     prm.pixels[(size_t)k * prm.pitch + x] = ref_rgb_to_int((int)(r * 254.f), (int)(g * 254.f), (int)(b * 254.f));
                 }
             }
-            const uint32_t bal = __ballot_sync(0xffffffffu, hit);
-            my_off[p] = warp_hits + __popc(bal & ((1u << lane) - 1u));
-            warp_hits += __popc(bal);
+        }
+        // hit-list order inside the tile: grouped by hit sphere (ascending id), row-major inside a group, so the
+        // 32 consecutive entries a shadow warp takes mostly lie on ONE sphere (tight beams)
+        {
+            uint32_t rem = 0;
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+                const int k = ty * P + p;
+                my_off[p] = 0;
+                if (x_ok && k < prm.n_rows && best_id[p] >= 0) rem |= 1u << p;
+            }
+            while (__any_sync(0xffffffffu, rem != 0)) {
+                int cur = 0x7fffffff;
+#pragma unroll
+                for (int p = 0; p < P; p++)
+                    if ((rem >> p) & 1u) cur = min(cur, best_id[p]);
+                cur = __reduce_min_sync(0xffffffffu, cur);
+#pragma unroll
+                for (int p = 0; p < P; p++) {
+                    const bool m = ((rem >> p) & 1u) && best_id[p] == cur;
+                    const uint32_t bal = __ballot_sync(0xffffffffu, m);
+                    if (m) {
+                        my_off[p] = warp_hits + __popc(bal & ((1u << lane) - 1u));
+                        rem &= ~(1u << p);
+                    }
+                    warp_hits += __popc(bal);
+                }
+            }
         }
         if (lane == 0) warp_tot[warp] = warp_hits;
         __syncthreads();
@@ -1117,6 +1142,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) shadow_beam_kernel(const Frame
 
         // ---- shading set-up (kernel.cu:1396-1405, 1643-1655) ----
         size_t o_out = 0;
+        int my_id = -1;
         v3 start = mk(1e9f, 1e9f, 1e9f), normal = mk(0.f, 0.f, 0.f);
         float tr = 0.f, tg = 0.f, tb = 0.f;
         if (valid) {
@@ -1125,7 +1151,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) shadow_beam_kernel(const Frame
             o_out = (size_t)k * prm.pitch + x;
             const v3 D = primary_dir(prm, prm.dx_tab[x], prm.dy_tab[k]);
             const float nt = prm.hit_t[o];
-            const float4 sc = __ldg(&prm.sph_exact[prm.hit_id[o]]);
+            my_id = prm.hit_id[o];
+            const float4 sc = __ldg(&prm.sph_exact[my_id]);
             const v3 new_org = ref_add(O0, ref_scale(D, nt));
             normal = ref_sub(new_org, mk(sc.x, sc.y, sc.z));
             ref_normalise(normal);
@@ -1194,150 +1221,162 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) shadow_beam_kernel(const Frame
                 }
             }
 
-            // ---- warp beams: per light one axis line through the origins' centroid; the warp's rays of
-            //      that light stay within rho_perp + (axial distance) * tan(a) of it (DESIGN.md "Beam test")
-            const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
-            const float nvalid = (float)__popc(vmask);
-            float bx = valid ? start.x : 0.f, by = valid ? start.y : 0.f, bz = valid ? start.z : 0.f;
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {
-                bx += __shfl_xor_sync(0xffffffffu, bx, d);
-                by += __shfl_xor_sync(0xffffffffu, by, d);
-                bz += __shfl_xor_sync(0xffffffffu, bz, d);
-            }
-            const float inv_n = 1.f / fmaxf(nvalid, 1.f);
-            bx *= inv_n;
-            by *= inv_n;
-            bz *= inv_n;
-            const float ex = valid ? start.x - bx : 0.f, ey = valid ? start.y - by : 0.f, ez = valid ? start.z - bz : 0.f;
-            const float escale = 1e-5f * (fabsf(bx) + fabsf(by) + fabsf(bz) + 1.f);  // rounding slack on offsets
-            bool wforce = __any_sync(0xffffffffu, valid && force);
-            float wAx[NL], wAy[NL], wAz[NL], wtan[NL], wk1[NL], wk2[NL];  // k1 = -a_min, k2 = rho_perp
-#pragma unroll
-            for (int l = 0; l < NL; l++) {
-                const bool part = valid && ca[l] > 0.f;  // lanes whose light l takes part (lit, not degenerate)
-                float sx = part ? Ax[l] : 0.f, sy = part ? Ay[l] : 0.f, sz = part ? Az[l] : 0.f;
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) {
-                    sx += __shfl_xor_sync(0xffffffffu, sx, d);
-                    sy += __shfl_xor_sync(0xffffffffu, sy, d);
-                    sz += __shfl_xor_sync(0xffffffffu, sz, d);
-                }
-                const float n2 = fmaf(sx, sx, fmaf(sy, sy, sz * sz));
-                const float inv = rsqrtf(fmaxf(n2, 1e-30f));
-                sx *= inv;
-                sy *= inv;
-                sz *= inv;
-                // widest angle between the warp axis and any participating ray: theta_lane + a_lane
-                float cw = 1.f, amin = 3e38f, rp = 0.f;
-                if (part) {
-                    const float sina = sa[l] * (1.f / 1.002f);
-                    const float cosa = ca[l] + 0.00196f * sina;
-                    const float c1 = fminf(1.f, fmaf(sx, Ax[l], fmaf(sy, Ay[l], sz * Az[l])));
-                    const float s1 = sqrtf(fmaxf(0.f, fmaf(-c1, c1, 1.f))) + 1e-6f;
-                    cw = fmaf(c1, cosa, -(s1 * sina)) - 2e-6f;
-                    const float ai = fmaf(ex, sx, fmaf(ey, sy, ez * sz));  // axial offset of this origin
-                    const float px = ex - ai * sx, py = ey - ai * sy, pz = ez - ai * sz;
-                    amin = ai;
-                    rp = sqrtf(fmaf(px, px, fmaf(py, py, pz * pz)));
-                }
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) {
-                    cw = fminf(cw, __shfl_xor_sync(0xffffffffu, cw, d));
-                    amin = fminf(amin, __shfl_xor_sync(0xffffffffu, amin, d));
-                    rp = fmaxf(rp, __shfl_xor_sync(0xffffffffu, rp, d));
-                }
-                const bool any_part = __any_sync(0xffffffffu, part);
-                wAx[l] = wAy[l] = wAz[l] = 0.f;
-                wtan[l] = 0.f;
-                wk1[l] = -3e38f;  // u = sc + R' + k1 < 0: never a candidate
-                wk2[l] = 0.f;
-                if (any_part) {
-                    if (!(n2 > 1e-12f) || !(cw > 0.3f)) {
-                        wforce = true;  // bundle axes disagree wildly: no warp-level culling
-                    } else {
-                        const float sinw = sqrtf(fmaxf(0.f, fmaf(-cw, cw, 1.f))) * 1.0001f + 1e-6f;
-                        wAx[l] = sx;
-                        wAy[l] = sy;
-                        wAz[l] = sz;
-                        wtan[l] = sinw / cw * 1.0001f;
-                        wk1[l] = -(amin - escale);
-                        wk2[l] = rp * 1.0001f + escale;
-                    }
-                }
-            }
-            if (EXH) wforce = true;
-
-            bool warp_done = false;
+            // Lanes are processed in groups that hit the SAME sphere (the hit list is grouped that way, so a warp
+            // normally is one group; a warp straddling a silhouette is two or three): origins on one sphere give
+            // a narrow beam.  At most 4 passes; the last pass takes every lane that is left.
+            uint32_t pending = __ballot_sync(0xffffffffu, valid);
 #pragma unroll 1
-            for (int s0 = 0; s0 < n_sph && !warp_done; s0 += 32) {
-                // ---- level 1: lane i tests sphere s0+i against the warp's beams ----
-                const bool in = s0 + lane < n_sph;
-                bool wc = false;
-                if (in) {
-                    const float4 q = spheres[s0 + lane];
-                    const float Lx = bx - q.x, Ly = by - q.y, Lz = bz - q.z;
-                    const float LL = fmaf(Lz, Lz, fmaf(Ly, Ly, Lx * Lx));
-                    const float Rq = fmaf(q.w, 1.0001f, fmaf(LL, 1e-12f, 1e-6f));  // radius + rounding slack
-                    const float slack = LL * 2e-6f;                                 // cancellation in LL - sc^2
-#pragma unroll
-                    for (int l = 0; l < NL; l++) {
-                        const float sc = -fmaf(wAx[l], Lx, fmaf(wAy[l], Ly, wAz[l] * Lz));  // centre's axial coordinate
-                        const float u = sc + Rq + wk1[l];                                     // >= 0 unless wholly behind
-                        const float thr = fmaf(u, wtan[l], Rq + wk2[l]);
-                        const float d2 = fmaf(-sc, sc, LL);
-                        wc = wc || (u >= 0.f && d2 <= fmaf(thr, thr, slack));
-                    }
-                    wc = wc || wforce;
+            for (int pass = 0; pending; pass++) {
+                const int leader = __ffs(pending) - 1;
+                const int gid = __shfl_sync(0xffffffffu, my_id, leader);
+                const bool ing = valid && ((pending >> (tid & 31)) & 1u) && (pass >= 3 || my_id == gid);
+                const uint32_t gmask = __ballot_sync(0xffffffffu, ing);
+                pending &= ~gmask;
+                // ---- warp beams: per light one axis line through the origins' centroid; the warp's rays of
+                //      that light stay within rho_perp + (axial distance) * tan(a) of it (DESIGN.md "Beam test")
+                const float nvalid = (float)__popc(gmask);
+                float bx = ing ? start.x : 0.f, by = ing ? start.y : 0.f, bz = ing ? start.z : 0.f;
+    #pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {
+                    bx += __shfl_xor_sync(0xffffffffu, bx, d);
+                    by += __shfl_xor_sync(0xffffffffu, by, d);
+                    bz += __shfl_xor_sync(0xffffffffu, bz, d);
                 }
-                uint32_t wmask = __ballot_sync(0xffffffffu, wc);
-                n_l1 += __popc(wmask);
-                // ---- level 2: every lane runs its own cone test on the surviving spheres ----
-                while (wmask) {
-                    const int i = __ffs(wmask) - 1;
-                    wmask &= wmask - 1;
-                    const int s = s0 + i;
-                    const float4 q = spheres[s];
-                    const float lx = start.x - q.x, ly = start.y - q.y, lz = start.z - q.z;
-                    const float LL = fmaf(lz, lz, fmaf(ly, ly, lx * lx));
-                    const float Cm = fmaf(LL, 1.0f - ORE_KAPPA_SHADOW, -(q.w * q.w));
-                    const float sq = Cm * rsqrt_approx(Cm);
-                    const float svu = (EXH || !(Cm > 1e-20f)) ? -ORE_BIG : sq;
-                    uint32_t live = ~blocked & ALL;
-                    if (!force) {
-                        uint32_t lm = 0;
-#pragma unroll
-                        for (int l = 0; l < NL; l++) {
-                            const float T = fmaf(ca[l], svu, -(sa[l] * q.w));
-                            if (fmaf(Ax[l], lx, fmaf(Ay[l], ly, fmaf(Az[l], lz, T))) < 0.f) lm |= 0x3ffu << (10 * l);
-                        }
-                        live &= lm;
+                const float inv_n = 1.f / fmaxf(nvalid, 1.f);
+                bx *= inv_n;
+                by *= inv_n;
+                bz *= inv_n;
+                const float ex = ing ? start.x - bx : 0.f, ey = ing ? start.y - by : 0.f, ez = ing ? start.z - bz : 0.f;
+                const float escale = 1e-5f * (fabsf(bx) + fabsf(by) + fabsf(bz) + 1.f);  // rounding slack on offsets
+                bool wforce = __any_sync(0xffffffffu, ing && force);
+                float wAx[NL], wAy[NL], wAz[NL], wtan[NL], wk1[NL], wk2[NL];  // k1 = -a_min, k2 = rho_perp
+    #pragma unroll
+                for (int l = 0; l < NL; l++) {
+                    const bool part = ing && ca[l] > 0.f;  // lanes of the group whose light l takes part (lit, not degenerate)
+                    float sx = part ? Ax[l] : 0.f, sy = part ? Ay[l] : 0.f, sz = part ? Az[l] : 0.f;
+    #pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) {
+                        sx += __shfl_xor_sync(0xffffffffu, sx, d);
+                        sy += __shfl_xor_sync(0xffffffffu, sy, d);
+                        sz += __shfl_xor_sync(0xffffffffu, sz, d);
                     }
-                    if (live) {
-                        n_l2++;
-                        const float4 ex4 = __ldg(&prm.sph_exact[s]);
-                        while (live) {
-                            const int j = __ffs(live) - 1;
-                            live &= live - 1;
-                            const v3 D = mk(dirs[j * 3], dirs[j * 3 + 1], dirs[j * 3 + 2]);
-                            const float h = fmaf(D.x, lx, fmaf(D.y, ly, fmaf(D.z, lz, svu)));
-                            if (h < 0.f) {
-                                float t;
-                                n_exact++;
-                                if (ref_intersect(start, D, ex4.x, ex4.y, ex4.z, ex4.w, t)) blocked |= 1u << j;
+                    const float n2 = fmaf(sx, sx, fmaf(sy, sy, sz * sz));
+                    const float inv = rsqrtf(fmaxf(n2, 1e-30f));
+                    sx *= inv;
+                    sy *= inv;
+                    sz *= inv;
+                    // widest angle between the warp axis and any participating ray: theta_lane + a_lane
+                    float cw = 1.f, amin = 3e38f, rp = 0.f;
+                    if (part) {
+                        const float sina = sa[l] * (1.f / 1.002f);
+                        const float cosa = ca[l] + 0.00196f * sina;
+                        const float c1 = fminf(1.f, fmaf(sx, Ax[l], fmaf(sy, Ay[l], sz * Az[l])));
+                        const float s1 = sqrtf(fmaxf(0.f, fmaf(-c1, c1, 1.f))) + 1e-6f;
+                        cw = fmaf(c1, cosa, -(s1 * sina)) - 2e-6f;
+                        const float ai = fmaf(ex, sx, fmaf(ey, sy, ez * sz));  // axial offset of this origin
+                        const float px = ex - ai * sx, py = ey - ai * sy, pz = ez - ai * sz;
+                        amin = ai;
+                        rp = sqrtf(fmaf(px, px, fmaf(py, py, pz * pz)));
+                    }
+    #pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) {
+                        cw = fminf(cw, __shfl_xor_sync(0xffffffffu, cw, d));
+                        amin = fminf(amin, __shfl_xor_sync(0xffffffffu, amin, d));
+                        rp = fmaxf(rp, __shfl_xor_sync(0xffffffffu, rp, d));
+                    }
+                    const bool any_part = __any_sync(0xffffffffu, part);
+                    wAx[l] = wAy[l] = wAz[l] = 0.f;
+                    wtan[l] = 0.f;
+                    wk1[l] = -3e38f;  // u = sc + R' + k1 < 0: never a candidate
+                    wk2[l] = 0.f;
+                    if (any_part) {
+                        if (!(n2 > 1e-12f) || !(cw > 0.3f)) {
+                            wforce = true;  // bundle axes disagree wildly: no warp-level culling
+                        } else {
+                            const float sinw = sqrtf(fmaxf(0.f, fmaf(-cw, cw, 1.f))) * 1.0001f + 1e-6f;
+                            wAx[l] = sx;
+                            wAy[l] = sy;
+                            wAz[l] = sz;
+                            wtan[l] = sinw / cw * 1.0001f;
+                            wk1[l] = -(amin - escale);
+                            wk2[l] = rp * 1.0001f + escale;
+                        }
+                    }
+                }
+                if (EXH) wforce = true;
+
+                bool warp_done = false;
+    #pragma unroll 1
+                for (int s0 = 0; s0 < n_sph && !warp_done; s0 += 32) {
+                    // ---- level 1: lane i tests sphere s0+i against the warp's beams ----
+                    const bool in = s0 + lane < n_sph;
+                    bool wc = false;
+                    if (in) {
+                        const float4 q = spheres[s0 + lane];
+                        const float Lx = bx - q.x, Ly = by - q.y, Lz = bz - q.z;
+                        const float LL = fmaf(Lz, Lz, fmaf(Ly, Ly, Lx * Lx));
+                        const float Rq = fmaf(q.w, 1.0001f, fmaf(LL, 1e-12f, 1e-6f));  // radius + rounding slack
+                        const float slack = LL * 2e-6f;                                 // cancellation in LL - sc^2
+    #pragma unroll
+                        for (int l = 0; l < NL; l++) {
+                            const float sc = -fmaf(wAx[l], Lx, fmaf(wAy[l], Ly, wAz[l] * Lz));  // centre's axial coordinate
+                            const float u = sc + Rq + wk1[l];                                     // >= 0 unless wholly behind
+                            const float thr = fmaf(u, wtan[l], Rq + wk2[l]);
+                            const float d2 = fmaf(-sc, sc, LL);
+                            wc = wc || (u >= 0.f && d2 <= fmaf(thr, thr, slack));
+                        }
+                        wc = wc || wforce;
+                    }
+                    uint32_t wmask = __ballot_sync(0xffffffffu, wc);
+                    n_l1 += __popc(wmask);
+                    // ---- level 2: every lane runs its own cone test on the surviving spheres ----
+                    while (wmask) {
+                        const int i = __ffs(wmask) - 1;
+                        wmask &= wmask - 1;
+                        const int s = s0 + i;
+                        const float4 q = spheres[s];
+                        const float lx = start.x - q.x, ly = start.y - q.y, lz = start.z - q.z;
+                        const float LL = fmaf(lz, lz, fmaf(ly, ly, lx * lx));
+                        const float Cm = fmaf(LL, 1.0f - ORE_KAPPA_SHADOW, -(q.w * q.w));
+                        const float sq = Cm * rsqrt_approx(Cm);
+                        const float svu = (EXH || !(Cm > 1e-20f)) ? -ORE_BIG : sq;
+                        uint32_t live = ing ? (~blocked & ALL) : 0u;
+                        if (!force) {
+                            uint32_t lm = 0;
+    #pragma unroll
+                            for (int l = 0; l < NL; l++) {
+                                const float T = fmaf(ca[l], svu, -(sa[l] * q.w));
+                                if (fmaf(Ax[l], lx, fmaf(Ay[l], ly, fmaf(Az[l], lz, T))) < 0.f) lm |= 0x3ffu << (10 * l);
+                            }
+                            live &= lm;
+                        }
+                        if (live) {
+                            n_l2++;
+                            const float4 ex4 = __ldg(&prm.sph_exact[s]);
+                            while (live) {
+                                const int j = __ffs(live) - 1;
+                                live &= live - 1;
+                                const v3 D = mk(dirs[j * 3], dirs[j * 3 + 1], dirs[j * 3 + 2]);
+                                const float h = fmaf(D.x, lx, fmaf(D.y, ly, fmaf(D.z, lz, svu)));
+                                if (h < 0.f) {
+                                    float t;
+                                    n_exact++;
+                                    if (ref_intersect(start, D, ex4.x, ex4.y, ex4.z, ex4.w, t)) blocked |= 1u << j;
+                                }
+                            }
+    #pragma unroll
+                            for (int l = 0; l < NL; l++) {
+                                if (((blocked >> (10 * l)) & 0x3ffu) == 0x3ffu) {
+                                    Ax[l] = Ay[l] = Az[l] = 0.f;
+                                    ca[l] = 0.f;
+                                    sa[l] = 0.f;
+                                }
                             }
                         }
-#pragma unroll
-                        for (int l = 0; l < NL; l++) {
-                            if (((blocked >> (10 * l)) & 0x3ffu) == 0x3ffu) {
-                                Ax[l] = Ay[l] = Az[l] = 0.f;
-                                ca[l] = 0.f;
-                                sa[l] = 0.f;
-                            }
-                        }
                     }
+                    if (__all_sync(0xffffffffu, !ing || blocked == ALL)) warp_done = true;
                 }
-                if (__all_sync(0xffffffffu, blocked == ALL)) warp_done = true;
+
             }
 
             // ---- light accumulation (kernel.cu:1537-1543, 1673-1675) ----
