@@ -666,6 +666,47 @@ __device__ __forceinline__ void light_directions_n(const FrameParams& prm, int l
 }
 
 // ------------------------------------------------------------------------------------
+// light_directions_reuse: one light, one copy of the code (instruction-cache friendly), same exact reuse
+// of angle / rotate() matrix while toL repeats bit for bit.  Returns a = dot(normal, toL_final).
+// ------------------------------------------------------------------------------------
+__device__ __noinline__ float light_directions_reuse(const LightP L, const v3 start, const v3 normal,
+                                                     float* __restrict__ dir /* [10][3] */) {
+    const v3 up = mk(0.f, 1.f, 0.f), fwd = mk(0.f, 0.f, 1.f);
+    const v3 lpos = mk(L.px, L.py, L.pz);
+    v3 tmp = ref_sub(lpos, start);
+    v3 toL = ref_normalise(tmp);
+    v3 prev = mk(__int_as_float(0x7fc00001), 0.f, 0.f);
+    float angle = 0.f;
+    RotM M = RotM{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int j = 0; j < 10; j++) {
+        if (!same_bits(toL, prev)) {
+            prev = toL;
+            v3 P = ref_cross(toL, up);
+            v3 e = ref_sub(ref_add(lpos, ref_scale(P, L.size)), start);
+            v3 toEdge = ref_normalise(e);
+            angle = cosf((ref_dot(toL, toEdge)) * 2);
+            v3 n1 = ref_normalise(toL);
+            v3 ax = ref_cross(fwd, n1);
+            v3 axis = ref_normalise(ax);
+            v3 n2 = ref_normalise(toL);
+            float nAngle = acosf(ref_dot(n2, fwd));
+            M = ref_rotate_matrix(nAngle, axis);
+        }
+        const float _z = (float)j / 10 * (1.0f - angle) + angle;
+        const float sq = sqrtf(1.f - _z * _z);
+        const float x = sq * c_cos_phi[j];
+        const float y = sq * c_sin_phi[j];
+        v3 nd = ref_sub(lpos, ref_matrix_apply(M, mk(x, y, _z)));
+        v3 nn = ref_normalise(nd);
+        dir[j * 3 + 0] = nn.x;
+        dir[j * 3 + 1] = nn.y;
+        dir[j * 3 + 2] = nn.z;
+    }
+    return ref_dot(normal, toL);
+}
+
+// ------------------------------------------------------------------------------------
 // shadow_kernel
 // ------------------------------------------------------------------------------------
 template <int NL, bool EXH>
@@ -1097,7 +1138,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) shadow_cone_kernel(const Frame
 // offset <= rho_perp + t sin(a), which is exactly what level 1 bounds.
 // ------------------------------------------------------------------------------------
 template <bool EXH>
-__global__ void __launch_bounds__(CTA_THREADS, 2) shadow_beam_kernel(const FrameParams prm) {
+__global__ void __launch_bounds__(CTA_THREADS, 3) shadow_beam_kernel(const FrameParams prm) {
     constexpr int NL = 3;        // lights per pass
     constexpr int NR = 10 * NL;
     constexpr uint32_t ALL = (1u << NR) - 1u;
@@ -1173,9 +1214,21 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) shadow_beam_kernel(const Frame
             float Ax[NL], Ay[NL], Az[NL], ca[NL], sa[NL], a_l[NL];
             uint32_t blocked = ALL;
             bool force = false;  // some light cannot use the cone test: every sphere is a candidate
-            {
-                const int n_act = valid ? min(NL, prm.n_lights - l0) : 0;
-                light_directions_n<NL>(prm, l0, n_act, start, normal, dirs, a_l);
+#pragma unroll 1
+            for (int l = 0; l < NL; l++) {
+                float a = 0.f;
+                if (valid && (l0 + l) < prm.n_lights) {
+                    LightP L;
+                    const LightP* __restrict__ src = &prm.lights[0];
+                    // copy out of the parameter bank without taking its address into local memory
+                    const int li = l0 + l;
+                    L.px = src[li].px; L.py = src[li].py; L.pz = src[li].pz; L.size = src[li].size;
+                    L.r = src[li].r; L.g = src[li].g; L.b = src[li].b;
+                    a = light_directions_reuse(L, start, normal, dirs + 30 * l);
+                }
+                if (l == 0) a_l[0] = a;
+                if (l == 1) a_l[1] = a;
+                if (l == 2) a_l[2] = a;
             }
 #pragma unroll
             for (int l = 0; l < NL; l++) {
