@@ -13,7 +13,7 @@ import rte_b200  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="4k1024")
+    ap.add_argument("--workload", default="8k1024")
     ap.add_argument("--frames", type=int, default=3)
     ap.add_argument("--flags", type=int, default=0)
     a = ap.parse_args()
