@@ -67,7 +67,7 @@ typedef struct ore_camera {
     float pitch; /* degrees */
 } ore_camera;
 
-/* One frame (or one row band of it).  Rows rendered: y0, y0+y_step, ... < y1, in
+/* One frame (or one row band of it).  Rows rendered: y0, y0+y_step, ... < y1 (see y_block), in
  * GLOBAL image coordinates (dy depends on the global row, kernel.cu:1625); output
  * row k is image row y0 + k*y_step, `width` pixels each, 0x00RRGGBB (rgbToInt,
  * kernel.cu:546-556), row 0 = bottom scanline on screen (window.cpp:43). */
@@ -76,9 +76,16 @@ typedef struct ore_frame {
     int32_t y0, y1, y_step; /* full frame: 0, height, 1 */
     float aspect;           /* the global `aspect`, kernel.cu:1701 */
     uint32_t flags;         /* ore_flags */
-    int32_t out_pitch;      /* output row pitch in pixels; 0 = width (packed).  A rank that
-                               renders rows r, r+P, ... straight into the presenter's frame
-                               passes base = frame + r*width and out_pitch = P*width. */
+    int32_t out_pitch;      /* ore_render_device only.  0: rendered rows are stored packed (row k of the
+                               output = k-th rendered row).  > 0: pitch in pixels of ONE IMAGE ROW of the
+                               destination; rendered rows are stored at their image position relative to
+                               y0 (row y goes to out + (y - y0)*out_pitch).  A rank that renders its rows
+                               straight into the presenter's frame passes out = frame + y0*width and
+                               out_pitch = width. */
+    int32_t y_block;        /* 0 or 1: single rows y0, y0+y_step, ...; B > 1: blocks of B consecutive rows
+                               starting at y0, y0+y_step, ... (B <= y_step).  Block-interleaving keeps the
+                               8-row pixel tiles of the primary kernel compact when rows are dealt to P GPUs:
+                               rank r uses y0 = 8r, y_step = 8P, y_block = 8. */
 } ore_frame;
 
 /* counters of the last ore_render* call */

@@ -35,7 +35,7 @@ class OreCamera(C.Structure):
 
 class OreFrame(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("y0", C.c_int32), ("y1", C.c_int32),
-                ("y_step", C.c_int32), ("aspect", C.c_float), ("flags", C.c_uint32), ("out_pitch", C.c_int32)]
+                ("y_step", C.c_int32), ("aspect", C.c_float), ("flags", C.c_uint32), ("out_pitch", C.c_int32), ("y_block", C.c_int32)]
 
 
 class OreCounters(C.Structure):
@@ -172,9 +172,10 @@ class Renderer:
         c.yaw, c.pitch = float(camera.yaw), float(camera.pitch)
         return c
 
-    def _frame(self, width, height, y0, y1, y_step, aspect, flags, out_pitch=0) -> OreFrame:
+    def _frame(self, width, height, y0, y1, y_step, aspect, flags, out_pitch=0, y_block=1) -> OreFrame:
         f = OreFrame()
         f.out_pitch = int(out_pitch)
+        f.y_block = int(y_block)
         f.width, f.height = int(width), int(height)
         f.y0, f.y1, f.y_step = int(y0), int(height if y1 is None else y1), int(y_step)
         f.aspect = float(self.scene.aspect if aspect is None else aspect)
@@ -182,14 +183,19 @@ class Renderer:
         return f
 
     @staticmethod
-    def rows(height, y0=0, y1=None, y_step=1) -> int:
+    def rows(height, y0=0, y1=None, y_step=1, y_block=1) -> int:
         y1 = height if y1 is None else y1
-        return max(0, (y1 - y0 + y_step - 1) // y_step)
+        span = y1 - y0
+        if span <= 0:
+            return 0
+        if y_block >= y_step:
+            return span
+        return (span // y_step) * y_block + min(span % y_step, y_block)
 
-    def render(self, camera, width, height, y0=0, y1=None, y_step=1, aspect=None, flags=0, out=None) -> np.ndarray:
+    def render(self, camera, width, height, y0=0, y1=None, y_step=1, aspect=None, flags=0, out=None, y_block=1) -> np.ndarray:
         """Render into HOST memory (device->host copy inside the call). Returns uint32 [rows, W]."""
-        f = self._frame(width, height, y0, y1, y_step, aspect, flags)
-        rows = self.rows(height, y0, y1, y_step)
+        f = self._frame(width, height, y0, y1, y_step, aspect, flags, 0, y_block)
+        rows = self.rows(height, y0, y1, y_step, y_block)
         if out is None:
             out = np.empty((rows, max(0, width)), dtype=np.uint32)
         assert out.dtype == np.uint32 and out.size == rows * width and out.flags["C_CONTIGUOUS"]
@@ -200,9 +206,9 @@ class Renderer:
         return out
 
     def render_device(self, camera, width, height, out_ptr: int, stream: int = 0, y0=0, y1=None, y_step=1,
-                      aspect=None, flags=0, out_pitch=0):
+                      aspect=None, flags=0, out_pitch=0, y_block=1):
         """Render into DEVICE memory at `out_ptr` (asynchronous on `stream`)."""
-        f = self._frame(width, height, y0, y1, y_step, aspect, flags, out_pitch)
+        f = self._frame(width, height, y0, y1, y_step, aspect, flags, out_pitch, y_block)
         cam = self._cam(camera)
         self._check(self.lib.ore_render_device(self.ctx, C.byref(cam), C.byref(f), C.c_void_p(out_ptr),
                                                C.c_void_p(stream) if stream else None), "ore_render_device")

@@ -314,6 +314,16 @@ static int grid_for(ore_context* ctx, K kernel, size_t smem, int* grid, int thre
     return ORE_OK;
 }
 
+// rows y0 + m*y_step + j (j < y_block) below y1
+static int frame_rows(const ore_frame* fr) {
+    const int yb = fr->y_block > 0 ? fr->y_block : 1;
+    const int span = fr->y1 - fr->y0;
+    if (span <= 0 || fr->y_step <= 0) return 0;
+    if (yb >= fr->y_step) return span;  // contiguous
+    const int full = span / fr->y_step, rem = span % fr->y_step;
+    return full * yb + (rem < yb ? rem : yb);
+}
+
 static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame* fr, uint32_t* out_device,
                        cudaStream_t stream) {
     if (!ctx) return ORE_ERR_INVALID;
@@ -328,7 +338,9 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
     }
     ORE_CUDA(ctx, cudaSetDevice(ctx->device));
     const int W = fr->width;
-    const int n_rows = (fr->y1 - fr->y0 + fr->y_step - 1) / fr->y_step;
+    const int yb = fr->y_block > 0 ? fr->y_block : 1;
+    if (yb > fr->y_step && fr->y_step != 1) return fail(ctx, ORE_ERR_INVALID, "ore_render: y_block must not exceed y_step");
+    const int n_rows = frame_rows(fr);
     const size_t n_px = (size_t)n_rows * W;
     if (n_px >= (size_t)1 << 31) return fail(ctx, ORE_ERR_INVALID, "ore_render: band too large");
     ctx->last_px = n_px;
@@ -355,9 +367,11 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
     prm.W = W;
     prm.H = fr->height;
     prm.y0 = fr->y0;
-    prm.y_step = fr->y_step;
+    prm.y_step = (yb >= fr->y_step) ? 1 : fr->y_step;
     prm.n_rows = n_rows;
-    prm.pitch = (out_device && fr->out_pitch > 0) ? fr->out_pitch : W;
+    prm.y_block = (yb >= fr->y_step) ? 1 : yb;
+    prm.out_global = (out_device && fr->out_pitch > 0) ? 1 : 0;
+    prm.pitch = prm.out_global ? fr->out_pitch : W;
     prm.n_spheres = ctx->n_spheres;
     prm.n_spheres_pad = ctx->n_spheres_pad;
     prm.n_lights = ctx->n_lights;
@@ -381,7 +395,17 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
         // largest half-angle of a 32 x PRIMARY_P pixel tile seen from the eye (tile cone of the primary
         // kernel): |v_pixel - v_centre| <= halfdiag on the image plane and |v| >= fz, so sin(a) <= halfdiag/fz
         const double delta = 2.0 * (double)fr->aspect / (double)W;
-        const double hx = 16.0 * delta, hy = (0.5 * (PRIMARY_P - 1) * fr->y_step + 0.5) * delta;
+        // tallest image-row span of PRIMARY_P consecutive RENDERED rows (rows come in blocks of y_block)
+        int max_span = 0;
+        {
+            const int B = prm.y_block, S = prm.y_step;
+            for (int k0 = 0; k0 < B * PRIMARY_P; k0 += PRIMARY_P) {
+                const int k1 = k0 + PRIMARY_P - 1;
+                const int sp = ((k1 / B) * S + k1 % B) - ((k0 / B) * S + k0 % B);
+                if (sp > max_span) max_span = sp;
+            }
+        }
+        const double hx = 16.0 * delta, hy = (0.5 * max_span + 0.5) * delta;
         const double xr = sqrt(hx * hx + hy * hy) / fabs((double)prm.fz);
         prm.px_delta = (float)delta;
         if (!(xr < 0.9)) {
@@ -540,7 +564,7 @@ extern "C" int ore_render_async(ore_context* ctx, const ore_camera* cam, const o
     if (!ctx) return ORE_ERR_INVALID;
     if (!out_host || !frame) return fail(ctx, ORE_ERR_INVALID, "ore_render_async: null output/frame");
     ORE_CUDA(ctx, cudaSetDevice(ctx->device));
-    const int n_rows = frame->y_step > 0 ? (frame->y1 - frame->y0 + frame->y_step - 1) / frame->y_step : 0;
+    const int n_rows = frame_rows(frame);
     const size_t n_px = (size_t)(n_rows > 0 ? n_rows : 0) * (size_t)(frame->width > 0 ? frame->width : 0);
     const int buf = (int)(ctx->async_frames & 1ull);
     int rc;

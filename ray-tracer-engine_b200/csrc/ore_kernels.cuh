@@ -58,7 +58,9 @@ struct LightP {
 
 struct FrameParams {
     int W, H, y0, y_step, n_rows;
-    int pitch;  // output row pitch in pixels (pixels[] only; hit records stay packed)
+    int y_block;     // rows come in blocks of y_block consecutive image rows, block starts y_step apart
+    int pitch;       // output row pitch in pixels (pixels[] only; hit records stay packed)
+    int out_global;  // 1: pixel rows are stored at their image position relative to y0, 0: packed
     int n_spheres, n_spheres_pad, n_lights;
     uint32_t flags;
     float aspect, ez, fz;  // ez = -1/aspect (kernel.cu:1629), fz = 0 - ez
@@ -109,6 +111,14 @@ __device__ __forceinline__ v3 primary_dir(const FrameParams& prm, float dx, floa
 }
 
 __device__ __forceinline__ int clamp_index(int idx, int n) { return idx < 0 ? 0 : (idx >= n ? n - 1 : idx); }
+
+// image row (relative to y0) of rendered row k, and where its pixels go
+__device__ __forceinline__ int image_row_rel(const FrameParams& prm, int k) {
+    return (k / prm.y_block) * prm.y_step + (k % prm.y_block);
+}
+__device__ __forceinline__ size_t out_index(const FrameParams& prm, int k, int x) {
+    return (size_t)(prm.out_global ? image_row_rel(prm, k) : k) * prm.pitch + x;
+}
 
 // ---- out-of-line helpers: ONE copy of each cold or bulky sequence keeps the kernels' code small enough
 // ---- for the instruction caches (measured: -27 % shadow-kernel time when the light set-up stopped being
@@ -166,7 +176,7 @@ __global__ void prep_frame_kernel(const FrameParams prm) {
     }
     if (i < prm.n_rows) {
         // kernel.cu:1625  float dy = aspect * (2 * (y + 0.5) / (float)height)*((float)height/width) - 1;
-        const int y = prm.y0 + i * prm.y_step;
+        const int y = prm.y0 + image_row_rel(prm, i);
         float hw = (float)prm.H / (float)prm.W;
         double v = (double)prm.aspect * (2 * (y + 0.5) / (double)(float)prm.H) * (double)hw - 1;
         const_cast<float*>(prm.dy_tab)[i] = (float)v;
@@ -392,7 +402,7 @@ __global__ void __launch_bounds__(CTA_THREADS) primary_kernel(const FrameParams 
                     int ty = (int)(acosf(n.y) / 3.1415f * (float)prm.sky_h);
                     int index = clamp_index(ty * prm.sky_w + tx, prm.sky_w * prm.sky_h);
                     float r = __ldg(&prm.sky_r[index]), g = __ldg(&prm.sky_g[index]), b = __ldg(&prm.sky_b[index]);
-                    prm.pixels[(size_t)k * prm.pitch + x] = ref_rgb_to_int((int)(r * 254.f), (int)(g * 254.f), (int)(b * 254.f));
+                    prm.pixels[out_index(prm, k, x)] = ref_rgb_to_int((int)(r * 254.f), (int)(g * 254.f), (int)(b * 254.f));
                 }
             }
             // hit-list order inside a warp: p-major, then lane => 32 neighbouring pixels stay together
@@ -481,7 +491,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) primary_tile_kernel(const Fram
         {
             const int k0 = ty * P;
             const float cx = prm.dx_tab[min(tx * 32, prm.W - 1)] + 15.5f * prm.px_delta;
-            const float cy = prm.dy_tab[min(k0, prm.n_rows - 1)] + 0.5f * (float)(P - 1) * (float)prm.y_step * prm.px_delta;
+            const float cy = 0.5f * (prm.dy_tab[min(k0, prm.n_rows - 1)] + prm.dy_tab[min(k0 + P - 1, prm.n_rows - 1)]);
             const float inv = rsqrtf(fmaf(cx, cx, fmaf(cy, cy, prm.fz * prm.fz)));
             ax = cx * inv;
             ay = cy * inv;
@@ -544,7 +554,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) primary_tile_kernel(const Fram
                 prm.hit_id[o] = best_id[p];
                 prm.hit_t[o] = best_t[p];
                 if (!hit) {
-                    prm.pixels[(size_t)k * prm.pitch + x] = sky_pixel(sk, O.x, O.y, O.z, D[p].x, D[p].y, D[p].z);
+                    prm.pixels[out_index(prm, k, x)] = sky_pixel(sk, O.x, O.y, O.z, D[p].x, D[p].y, D[p].z);
                 }
             }
         }
@@ -878,7 +888,7 @@ __global__ void __launch_bounds__(SHADOW_THREADS, ORE_SHADOW_MIN_CTAS) shadow_ke
         if (valid) {
             o = prm.hit_list[item];
             const int k = (int)(o / (uint32_t)prm.W), x = (int)(o % (uint32_t)prm.W);
-            o_out = (size_t)k * prm.pitch + x;
+            o_out = out_index(prm, k, x);
             const v3 D = primary_dir(prm, prm.dx_tab[x], prm.dy_tab[k]);
             const float nt = prm.hit_t[o];
             const float4 sc = __ldg(&prm.sph_exact[prm.hit_id[o]]);
@@ -1082,7 +1092,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) shadow_cone_kernel(const Frame
         if (valid) {
             const uint32_t o = prm.hit_list[item];
             const int k = (int)(o / (uint32_t)prm.W), x = (int)(o % (uint32_t)prm.W);
-            o_out = (size_t)k * prm.pitch + x;
+            o_out = out_index(prm, k, x);
             const v3 D = primary_dir(prm, prm.dx_tab[x], prm.dy_tab[k]);
             const float nt = prm.hit_t[o];
             const float4 sc = __ldg(&prm.sph_exact[prm.hit_id[o]]);
@@ -1324,7 +1334,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) shadow_beam_kernel(const Frame
         if (valid) {
             const uint32_t o = prm.hit_list[item];
             const int k = (int)(o / (uint32_t)prm.W), x = (int)(o % (uint32_t)prm.W);
-            o_out = (size_t)k * prm.pitch + x;
+            o_out = out_index(prm, k, x);
             const v3 D = primary_dir(prm, prm.dx_tab[x], prm.dy_tab[k]);
             const float nt = prm.hit_t[o];
             my_id = prm.hit_id[o];

@@ -91,7 +91,7 @@ void update() {
         checkCudaErrors(cudaMallocHost((void**)&g_pixels, n * sizeof(unsigned int)));
         g_pixels_cap = n;
     }
-    ore_frame fr = {width, height, 0, height, 1, aspect, ORE_FLAG_NONE, 0};
+    ore_frame fr = {width, height, 0, height, 1, aspect, ORE_FLAG_NONE, 0, 0};
     checkOre(ore_render(g_ctx, &cam, &fr, g_pixels));  // launch + sync + device->host, like :1783-1788
     setPixelBuff(g_pixels);
 }

@@ -142,10 +142,15 @@ class PeerFrame:
                 self._opened.append(p)
                 self.ptrs.append(p)
 
+    ROW_BLOCK = 8  # rows are dealt to the ranks in blocks of 8 (= the primary kernel's tile height)
+
     def band_args(self, buf: int) -> dict:
-        """kwargs for Renderer.render_device: this rank's interleaved rows of buffer `buf`."""
-        return dict(out_ptr=self.ptrs[buf] + 4 * self.width * self.rank, y0=self.rank, y1=self.height,
-                    y_step=self.world, out_pitch=self.world * self.width)
+        """kwargs for Renderer.render_device: this rank's block-interleaved rows of buffer `buf`, stored at
+        their image position in the presenter's frame."""
+        b = self.ROW_BLOCK if self.world > 1 else 1
+        y0 = b * self.rank
+        return dict(out_ptr=self.ptrs[buf] + 4 * self.width * y0, y0=y0, y1=self.height,
+                    y_step=b * self.world, y_block=b, out_pitch=self.width)
 
     def close(self):
         for p in self._opened:
