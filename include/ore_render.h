@@ -180,6 +180,9 @@ int ore_get_kernel_ms(ore_context* ctx, float ms[4]);
 /* Measures the FP32 roofline denominator on this GPU with an FFMA burn (TFLOP/s, best of 5)
  * and returns the nominal SM clock; used by bench.py only. */
 int ore_measure_fp32_peak(ore_context* ctx, double* tflops, double* sm_clock_mhz_nominal);
+/* Tests only: evaluates the device libm the path uses on n host inputs.
+ * op 0 cosf(a), 1 sinf(a), 2 acosf(a), 3 atan2f(a, b).  The path's versions return glibc's bits (ore_libm.cuh). */
+int ore_debug_libm(ore_context* ctx, int op, int n, const float* a_host, const float* b_host, float* out_host);
 
 #ifdef __cplusplus
 }

@@ -22,7 +22,7 @@ EXPORTS = [
     "ore_create", "ore_destroy", "ore_abi_version", "ore_last_error",
     "ore_set_spheres", "ore_set_spheres_aos32", "ore_set_lights", "ore_set_texture", "ore_set_sky",
     "ore_render", "ore_render_device", "ore_synchronize",
-    "ore_get_hits", "ore_get_counters", "ore_get_kernel_ms", "ore_measure_fp32_peak",
+    "ore_get_hits", "ore_get_counters", "ore_get_kernel_ms", "ore_measure_fp32_peak", "ore_debug_libm",
     "ore_render_async", "ore_wait", "ore_host_alloc", "ore_host_free",
     "ore_dev_alloc", "ore_dev_free", "ore_ipc_export", "ore_ipc_import", "ore_ipc_close", "ore_copy_to_host",
 ]
@@ -82,6 +82,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.ore_get_counters.argtypes = [vp, C.POINTER(OreCounters)]
     lib.ore_get_kernel_ms.argtypes = [vp, C.POINTER(C.c_float * 4)]
     lib.ore_measure_fp32_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.ore_debug_libm.argtypes = [vp, C.c_int, C.c_int, fp, fp, fp]
     lib.ore_dev_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
     lib.ore_dev_free.argtypes = [vp, vp]
     lib.ore_ipc_export.argtypes = [vp, vp, C.POINTER(C.c_ubyte * 64)]
@@ -284,6 +285,15 @@ class Renderer:
         tf, mhz = C.c_double(0), C.c_double(0)
         self._check(self.lib.ore_measure_fp32_peak(self.ctx, C.byref(tf), C.byref(mhz)), "ore_measure_fp32_peak")
         return tf.value, mhz.value
+
+    def debug_libm(self, op: str, a: np.ndarray, b: np.ndarray | None = None) -> np.ndarray:
+        """device libm of the path on host inputs (tests): op in cosf, sinf, acosf, atan2f(a=y, b=x)"""
+        code = {"cosf": 0, "sinf": 1, "acosf": 2, "atan2f": 3}[op]
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        b = np.ascontiguousarray(a if b is None else b, dtype=np.float32)
+        out = np.empty_like(a)
+        self._check(self.lib.ore_debug_libm(self.ctx, code, a.size, _fptr(a), _fptr(b), _fptr(out)), "ore_debug_libm")
+        return out
 
     def kernel_ms(self):
         ms = (C.c_float * 4)()

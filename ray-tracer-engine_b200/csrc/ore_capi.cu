@@ -710,6 +710,26 @@ extern "C" int ore_get_kernel_ms(ore_context* ctx, float ms[4]) {
     return ORE_OK;
 }
 
+extern "C" int ore_debug_libm(ore_context* ctx, int op, int n, const float* a_host, const float* b_host, float* out_host) {
+    if (!ctx || n <= 0 || !a_host || !out_host || op < 0 || op > 3) return ORE_ERR_INVALID;
+    ORE_CUDA(ctx, cudaSetDevice(ctx->device));
+    float *a = nullptr, *b = nullptr, *o = nullptr;
+    const size_t bytes = (size_t)n * sizeof(float);
+    ORE_CUDA(ctx, cudaMalloc((void**)&a, bytes));
+    ORE_CUDA(ctx, cudaMalloc((void**)&b, bytes));
+    ORE_CUDA(ctx, cudaMalloc((void**)&o, bytes));
+    ORE_CUDA(ctx, cudaMemcpy(a, a_host, bytes, cudaMemcpyHostToDevice));
+    ORE_CUDA(ctx, cudaMemcpy(b, b_host ? b_host : a_host, bytes, cudaMemcpyHostToDevice));
+    libm_probe_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(op, n, a, b, o);
+    ORE_CUDA(ctx, cudaGetLastError());
+    ORE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ORE_CUDA(ctx, cudaMemcpy(out_host, o, bytes, cudaMemcpyDeviceToHost));
+    cudaFree(a);
+    cudaFree(b);
+    cudaFree(o);
+    return ORE_OK;
+}
+
 extern "C" int ore_measure_fp32_peak(ore_context* ctx, double* tflops, double* sm_clock_mhz_nominal) {
     if (!ctx || !tflops) return ORE_ERR_INVALID;
     ORE_CUDA(ctx, cudaSetDevice(ctx->device));
