@@ -421,6 +421,23 @@ def main():
                    "ms_per_step": statistics.mean(ms4), "steps": 10,
                    "kernel_ms": {"prep": statistics.mean(m[0] for m in kms4), "primary": statistics.mean(m[1] for m in kms4),
                                  "shadow": statistics.mean(m[2] for m in kms4)}}
+    fast_libm = None
+    if world == 1:
+        # the same frames with ORE_FLAG_FAST_LIBM (CUDA's libm: within 1 LSB instead of bit-identical)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for i in range(3):
+            r.render_device(camera(i), W, H, out_ptr=count_out, stream=stream.cuda_stream, flags=pkg.capi.ORE_FLAG_FAST_LIBM)
+        stream.synchronize()
+        ev0.record(stream)
+        for i in range(10):
+            r.render_device(camera(args.warmup + i), W, H, out_ptr=count_out, stream=stream.cuda_stream,
+                            flags=pkg.capi.ORE_FLAG_FAST_LIBM)
+        ev1.record(stream)
+        ev1.synchronize()
+        fl_ms = ev0.elapsed_time(ev1) / 10
+        fast_libm = {"flag": "ORE_FLAG_FAST_LIBM", "value": W * H / fl_ms / 1e3, "unit": "Mrays/s", "ms_per_step": fl_ms, "steps": 10,
+                     "note": "CUDA's cosf/sinf/acosf/atan2f instead of the glibc-bit-compatible device functions; ids/t unchanged, "
+                             "pixels within 1 LSB on >= 99.9 % instead of bit-identical"}
     ref_gpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # the reference's OWN CUDA kernel built for sm_100 (oracle/_ref/libref_sm100*.so), same scene, 3 frames:
@@ -489,6 +506,7 @@ def main():
             "cpu_baseline": cpu,
             "reference_kernel_on_b200": ref_gpu,
             "also_configs2_4k1024": also_4k,
+            "fast_libm": fast_libm,
         }
         print(json.dumps(line))
     if host:

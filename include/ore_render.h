@@ -51,7 +51,11 @@ enum ore_flags {
     /* No warp-cooperative culling: the primary kernel applies the per-pixel filter to every
      * sphere and the shadow kernel the per-pixel cone test to every sphere (the previous
      * generation of both kernels).  Same results. */
-    ORE_FLAG_NO_WARP_CULL = 8
+    ORE_FLAG_NO_WARP_CULL = 8,
+    /* Use CUDA's own cosf/sinf/acosf/atan2f instead of the glibc-bit-compatible device functions of the default
+     * path (csrc/ore_libm.cuh).  ~20 % faster; ids and t unchanged; pixels within 1 LSB of the default on
+     * >= 99.9 % (measured 99.999 %) instead of bit-identical to the host-compiled reference. */
+    ORE_FLAG_FAST_LIBM = 16
 };
 
 typedef struct ore_context ore_context; /* opaque; owns device buffers, streams, pinned staging */

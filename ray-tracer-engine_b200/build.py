@@ -12,8 +12,8 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libore_b200.so")
-SOURCES = ["ore_capi.cu"]
-HEADERS = ["ore_kernels.cuh", "ore_device.cuh", os.path.join("..", "..", "include", "ore_render.h")]
+SOURCES = ["ore_capi.cu", "ore_fast.cu"]
+HEADERS = ["ore_kernels.cuh", "ore_device.cuh", "ore_libm.cuh", os.path.join("..", "..", "include", "ore_render.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

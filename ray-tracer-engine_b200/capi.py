@@ -17,6 +17,7 @@ ORE_FLAG_EXHAUSTIVE = 1
 ORE_FLAG_COUNT_REFERENCE_TESTS = 2
 ORE_FLAG_PER_RAY_SHADOW = 4
 ORE_FLAG_NO_WARP_CULL = 8
+ORE_FLAG_FAST_LIBM = 16
 
 EXPORTS = [
     "ore_create", "ore_destroy", "ore_abi_version", "ore_last_error",

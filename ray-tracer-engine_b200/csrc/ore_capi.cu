@@ -19,6 +19,12 @@
 
 using namespace ore;
 
+// second instantiation of the default-path kernels with CUDA's libm (ore_fast.cu)
+extern "C" int ore_fast_set_tables(const float* cphi, const float* sphi, const float* bk);
+extern "C" int ore_fast_primary_tile(const void* prm, int sm_count, size_t smem, long long n_batches, int exh,
+                                     cudaStream_t stream);
+extern "C" int ore_fast_shadow_beam(const void* prm, int sm_count, size_t smem, int exh, cudaStream_t stream);
+
 struct ore_context {
     int device = 0;
     int sm_count = 0;
@@ -159,6 +165,7 @@ extern "C" int ore_create(ore_context** out, int device) {
         }
     }
     ORE_CUDA(ctx, cudaMemcpyToSymbol(c_b_of_k, bk, sizeof bk));
+    if (ore_fast_set_tables(cphi, sphi, bk)) return fail(ctx, ORE_ERR_CUDA, "constant tables of the fast-libm kernels");
     return ORE_OK;
 }
 
@@ -465,9 +472,14 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
     ORE_CUDA(ctx, cudaEventRecord(ctx->ev[1], stream));
     const bool exh = (fr->flags & ORE_FLAG_EXHAUSTIVE) != 0;
     const bool warp_cull = !(fr->flags & (ORE_FLAG_NO_WARP_CULL | ORE_FLAG_PER_RAY_SHADOW));
+    const bool fast_libm = (fr->flags & ORE_FLAG_FAST_LIBM) != 0;  // default-path kernels only
     {
         int grid = 0;
-        if (warp_cull) {
+        if (warp_cull && fast_libm) {
+            const long long tiles = (long long)((W + 31) / 32) * ((n_rows + PRIMARY_P - 1) / PRIMARY_P);
+            const long long n_batches = (tiles + CTA_WARPS - 1) / CTA_WARPS;
+            ORE_CUDA(ctx, (cudaError_t)ore_fast_primary_tile(&prm, ctx->sm_count, smem, n_batches, exh ? 1 : 0, stream));
+        } else if (warp_cull) {
             const long long tiles = (long long)((W + 31) / 32) * ((n_rows + PRIMARY_P - 1) / PRIMARY_P);
             const long long n_batches = (tiles + CTA_WARPS - 1) / CTA_WARPS;
             if (exh) {
@@ -501,7 +513,9 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
         if (warp_cull) {
             // the beam kernel stages the whole record array (resident) or reads it through L1/L2: no ring
             const size_t bsmem = prm.resident ? (size_t)ctx->n_spheres_pad * sizeof(float4) : 0;
-            if (exh) {
+            if (fast_libm) {
+                ORE_CUDA(ctx, (cudaError_t)ore_fast_shadow_beam(&prm, ctx->sm_count, bsmem, exh ? 1 : 0, stream));
+            } else if (exh) {
                 if ((rc = grid_for(ctx, shadow_beam_kernel<true>, bsmem, &grid))) return rc;
                 shadow_beam_kernel<true><<<grid, CTA_THREADS, bsmem, stream>>>(prm);
             } else {
