@@ -125,6 +125,15 @@ int ore_set_spheres(ore_context* ctx, const float* xyz_radius, int32_t n);
 /* Same, from the reference's own 32-byte AoS records (vptr@0, orgin@8, reflective@20,
  * radius@24; `sizeof(float)*8` per sphere, kernel.cu:1218-1220). */
 int ore_set_spheres_aos32(ore_context* ctx, const void* records, int32_t n);
+/* "Next" primitives of castRay / castLightRay.  The reference ships both counts at 0
+ * (kernel.cu:1231).  Hit ids continue after the spheres: cube i -> n_spheres + i, plane i -> n_spheres +
+ * n_cubes + i.  Exact tests, no filters: meant for the handful of objects the reference would hold.
+ * Replaces object::cubeAllocMem (kernel.cu:1224-1228): n x {c1.xyz, c2.xyz} = the `cube(c1, c2)` ctor
+ * arguments (kernel.cu:391-396; orgin = (c1+c2)/2 is derived here as the ctor does). */
+int ore_set_cubes(ore_context* ctx, const float* c1_c2, int32_t n);
+/* Replaces object::planeAllocMem (kernel.cu:1213-1217, which copies ONE plane; any count is accepted here):
+ * n x {pos.xyz, normal.xyz} = the `plane(pos, normal)` ctor arguments (kernel.cu:364-367). */
+int ore_set_planes(ore_context* ctx, const float* pos_normal, int32_t n);
 /* Replaces cudaMalloc+cudaMemcpy of `lights` in update() (kernel.cu:1776-1778):
  * n x {pos.xyz, size, r, g, b} (kernel.cu:1246-1261). */
 int ore_set_lights(ore_context* ctx, const float* lights7, int32_t n);
@@ -174,7 +183,7 @@ int ore_ipc_close(ore_context* ctx, void* dev_ptr);
 int ore_copy_to_host(ore_context* ctx, void* host_dst, const void* dev_src, size_t bytes);
 
 /* ---- introspection of the LAST render (parity tests, roofline accounting) ---------
- * hit_id: nearest sphere index or -1 (castRay, kernel.cu:1330-1342); hit_t: nearest t,
+ * hit_id: nearest primitive or -1 (castRay, kernel.cu:1330-1372; spheres, then cubes, then planes); hit_t: nearest t,
  * +inf on miss.  Packed like the pixels.  Either pointer may be NULL. */
 int ore_get_hits(ore_context* ctx, int32_t* hit_id_host, float* hit_t_host);
 int ore_get_counters(ore_context* ctx, ore_counters* out);

@@ -65,6 +65,57 @@ static inline int sphere_intersect(v3 O, v3 D, v3 c, float radius, float* t_out)
     return 0;
 }
 
+/* ---- plane::intersect, kernel.cu:369-380 -------------------------------------------- */
+static inline int plane_intersect(v3 O, v3 D, v3 pos, v3 normal, float* t_out) {
+    float denom = v_dot(normal, D);
+    if (denom < 0) {
+        v3 pl0 = v_sub(pos, O);
+        float t = v_dot(pl0, normal) / denom;
+        *t_out = t;
+        return t >= 0;
+    }
+    return 0;
+}
+
+/* ---- cube::intersect, kernel.cu:399-484 (live part :460-483); max/min are the reference's
+ * ternary macros (kernel.cu:16-26), NaN behaviour included ------------------------------ */
+#define REF_MAX(a, b) (((a) > (b)) ? (a) : (b))
+#define REF_MIN(a, b) (((a) < (b)) ? (a) : (b))
+static inline int cube_intersect(v3 O, v3 D, v3 b0, v3 b1, float* t_out) {
+    float dirx = 1.f / D.x;
+    float diry = 1.f / D.y;
+    float dirz = 1.f / D.z;
+    float t1 = (b0.x - O.x) * dirx;
+    float t2 = (b1.x - O.x) * dirx;
+    float t3 = (b0.y - O.y) * diry;
+    float t4 = (b1.y - O.y) * diry;
+    float t5 = (b0.z - O.z) * dirz;
+    float t6 = (b1.z - O.z) * dirz;
+    float tmin = REF_MAX(REF_MAX(REF_MIN(t1, t2), REF_MIN(t3, t4)), REF_MIN(t5, t6));
+    float tmax = REF_MIN(REF_MIN(REF_MAX(t1, t2), REF_MAX(t3, t4)), REF_MAX(t5, t6));
+    if (tmax < 0) {
+        *t_out = tmax;
+        return 0;
+    }
+    if (tmax < tmin) {
+        *t_out = tmax;
+        return 0;
+    }
+    *t_out = tmin;
+    return 1;
+}
+static inline v3 cube_b0(const oracle_frame* f, int i) { const float* c = f->cubes + 6 * (size_t)i; v3 r = {c[0], c[1], c[2]}; return r; }
+static inline v3 cube_b1(const oracle_frame* f, int i) { const float* c = f->cubes + 6 * (size_t)i; v3 r = {c[3], c[4], c[5]}; return r; }
+/* cube ctor: orgin = divide(add(c1, c2), 2), kernel.cu:395 */
+static inline v3 cube_origin(const oracle_frame* f, int i) {
+    v3 a = cube_b0(f, i), b = cube_b1(f, i);
+    v3 s = v_add(a, b);
+    v3 r = {s.x / 2, s.y / 2, s.z / 2};
+    return r;
+}
+static inline v3 plane_pos(const oracle_frame* f, int i) { const float* c = f->planes + 6 * (size_t)i; v3 r = {c[0], c[1], c[2]}; return r; }
+static inline v3 plane_nrm(const oracle_frame* f, int i) { const float* c = f->planes + 6 * (size_t)i; v3 r = {c[3], c[4], c[5]}; return r; }
+
 /* ---- camera::rotateDir, kernel.cu:248-258 ------------------------------------------- */
 static inline v3 rotate_dir(v3 v, float yaw, float pitch) {
     float yawRad = yaw * (3.1415 / 180);
@@ -162,6 +213,22 @@ static float cast_light_ray(const oracle_frame* f, v3 start, const float* l, v3 
             }
         }
         *n_tests += (uint64_t)(shadow ? i + 1 : f->n_spheres);
+        if (!shadow)                                                                     /* planes, :1512-1523 */
+            for (i = 0; i < f->n_planes; i++) {
+                float t;
+                if (plane_intersect(start, new_dir, plane_pos(f, i), plane_nrm(f, i), &t)) {
+                    shadow = 1;
+                    break;
+                }
+            }
+        if (!shadow)                                                                     /* cubes, :1524-1536 */
+            for (i = 0; i < f->n_cubes; i++) {
+                float t;
+                if (cube_intersect(start, new_dir, cube_b0(f, i), cube_b1(f, i), &t)) {
+                    shadow = 1;
+                    break;
+                }
+            }
         if (!shadow) b += 0.1;                     /* float += double */                 /* :1537-1539 */
     }
     float a = v_dot(normal, toL);                                                        /* :1541 */
@@ -214,19 +281,58 @@ static uint32_t trace_pixel(const oracle_frame* f, int x, int y, int32_t* id_out
         }
     }
     cnt[0] += (uint64_t)f->n_spheres;
-    if (id_out) *id_out = (nt != INFINITY) ? hit_index : -1;
+    int hit_type = 1;
+    for (int i = 0; i < f->n_cubes; i++) {                                               /* :1344-1357 */
+        float t;
+        if (cube_intersect(O, D, cube_b0(f, i), cube_b1(f, i), &t)) {
+            if (t < nt) {
+                nt = t;
+                hit_index = i;
+                hit_type = 3;
+            }
+        }
+    }
+    for (int i = 0; i < f->n_planes; i++) {                                              /* :1359-1372 */
+        float t;
+        if (plane_intersect(O, D, plane_pos(f, i), plane_nrm(f, i), &t)) {
+            if (t < nt) {
+                nt = t;
+                hit_index = i;
+                hit_type = 2;
+            }
+        }
+    }
+    if (id_out) {
+        int enc = hit_index;
+        if (hit_type == 3) enc += f->n_spheres;
+        if (hit_type == 2) enc += f->n_spheres + f->n_cubes;
+        *id_out = (nt != INFINITY) ? enc : -1;
+    }
     if (t_out) *t_out = nt;
 
     if (nt != INFINITY) {                                                                /* :1375 */
         cnt[3] += 1;
-        /* sphere hit attributes, kernel.cu:1396-1405 */
-        const float* s = f->spheres + 4 * (size_t)hit_index;
-        v3 c = {s[0], s[1], s[2]};
+        /* hit attributes: sphere kernel.cu:1396-1405, plane :1407-1416, cube :1417-1425 */
         v3 new_org = v_add(O, v_scale(D, nt));
-        v3 normal = v_sub(new_org, c);
-        v_normalise(&normal);
-        float tx = (1 + atan2f(normal.z, normal.x) / 3.1415) * 0.5;
-        float ty = acosf(normal.y) / 3.1415;
+        v3 normal;
+        float tx, ty;
+        if (hit_type == 2) {
+            normal = plane_nrm(f, hit_index);
+            tx = 0.5;
+            ty = 0.5;
+        } else {
+            v3 c;
+            if (hit_type == 1) {
+                const float* s = f->spheres + 4 * (size_t)hit_index;
+                c.x = s[0]; c.y = s[1]; c.z = s[2];
+            } else {
+                c = cube_origin(f, hit_index);
+            }
+            normal = v_sub(new_org, c);
+            v_normalise(&normal);
+            tx = (1 + atan2f(normal.z, normal.x) / 3.1415) * 0.5;
+            ty = acosf(normal.y) / 3.1415;
+        }
 
         int maxX = f->tex_w, maxY = f->tex_h;                                            /* :1643-1644 */
         v3 start_O = v_add(v_scale(normal, 0.00001), new_org);                           /* :1647 */

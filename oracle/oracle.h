@@ -37,12 +37,19 @@ typedef struct oracle_frame {
     int32_t sky_w, sky_h;    /* skybox texture                                                 */
     const float *sky_r, *sky_g, *sky_b;
     float sky_size;          /* skybox ctor arg (10000, kernel.cu:1700)                        */
+    /* "next" primitives of castRay / castLightRay (kernel.cu:360-509, loops :1344-1372,1512-1536) */
+    int32_t n_cubes;
+    const float* cubes;      /* n x 6: cube ctor args c1.xyz, c2.xyz (kernel.cu:391-396)       */
+    int32_t n_planes;        /* the reference copies ONE plane to the device (kernel.cu:1213-1217):
+                                the _ref build accepts 0 or 1, the C restatement any count       */
+    const float* planes;     /* n x 6: plane ctor args pos.xyz, normal.xyz (kernel.cu:364-367) */
 } oracle_frame;
 
 /* Renders the selected rows.  Outputs are packed by rendered row (row k of the
  * output = image row y0 + k*y_step), `width` entries per row; any may be NULL.
  *   pixels : 0x00RRGGBB                         (rgbToInt, kernel.cu:546-556)
- *   hit_id : nearest sphere index, -1 = miss    (castRay sphere loop, kernel.cu:1330-1342)
+ *   hit_id : nearest primitive, -1 = miss: sphere i -> i, cube i -> n_spheres + i, plane i ->
+ *            n_spheres + n_cubes + i   (castRay loops, kernel.cu:1330-1372; hit_type 1, 3, 2)
  *   hit_t  : nearest t (bit pattern matters), +inf on miss
  *   counts : [0] primary sphere::intersect calls, [1] shadow-phase calls in the
  *            reference's loop order incl. early break (kernel.cu:1501-1510),

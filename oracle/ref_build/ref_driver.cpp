@@ -72,8 +72,6 @@ extern "C" int oracle_render(const oracle_frame* f, uint32_t* pixels, int32_t* h
     // scene container exactly as the reference holds it (kernel.cu:1176-1244)
     object* o = new object();
     o->sphere_count = f->n_spheres;
-    o->plane_count = 0;
-    o->cube_count = 0;
     o->s1 = new sphere[f->n_spheres > 0 ? f->n_spheres : 1];
     for (int i = 0; i < f->n_spheres; i++) {
         const float* s = f->spheres + 4 * (size_t)i;
@@ -81,6 +79,21 @@ extern "C" int oracle_render(const oracle_frame* f, uint32_t* pixels, int32_t* h
         o->s1[i].radius = s[3];               // stored member (ctor would have squared r)
     }
     o->sphereAllocMem();                       // kernel.cu:1208-1212 (32-byte AoS copy)
+    // cubes (kernel.cu:1186,1193-1199,1224-1228) and the single plane the reference supports (:1187,1213-1217)
+    if (f->n_planes < 0 || f->n_planes > 1) return 3;
+    o->cube_count = f->n_cubes;
+    o->c1 = new cube[f->n_cubes > 0 ? f->n_cubes : 1];
+    for (int i = 0; i < f->n_cubes; i++) {
+        const float* c = f->cubes + 6 * (size_t)i;
+        o->c1[i] = cube({c[0], c[1], c[2]}, {c[3], c[4], c[5]});
+    }
+    o->cubeAllocMem();
+    if (f->n_planes == 1)
+        o->planes = new plane({f->planes[0], f->planes[1], f->planes[2]}, {f->planes[3], f->planes[4], f->planes[5]});
+    else
+        o->planes = new plane({0, -4, 0}, normalise(vec3d({0, 1, 0})));   // kernel.cu:1187
+    o->plane_count = f->n_planes;
+    o->planeAllocMem();
     o->texture = new sprite("ore:tex");
     // a mesh whose file does not exist: the ctor returns early (kernel.cu:583-585) and the
     // calloc-backed managed allocation leaves bvhbox_count == 0, so the triangle loops
@@ -127,6 +140,8 @@ extern "C" int oracle_render(const oracle_frame* f, uint32_t* pixels, int32_t* h
                 float nt, nu, nv, tx, ty;
                 vec3d no, nn;
                 bool hit = castRay(*o, cam_ray, ht, hi, nt, nu, nv, no, nn, tx, ty);
+                if (hit && ht == 3) hi += f->n_spheres;                      // same encoding as oracle.h
+                if (hit && ht == 2) hi += f->n_spheres + f->n_cubes;
                 if (hit_id) hit_id[(size_t)k * W + x] = hit ? hi : -1;
                 if (hit_t) hit_t[(size_t)k * W + x] = nt;
             }
@@ -139,6 +154,10 @@ extern "C" int oracle_render(const oracle_frame* f, uint32_t* pixels, int32_t* h
     delete sky->box;
     delete sky;
     cudaFree(o->d_spheres);
+    cudaFree(o->d_cubes);
+    cudaFree(o->d_planes);
+    delete[] o->c1;
+    delete o->planes;
     delete[] o->s1;
     delete o->mesh1;
     delete o;

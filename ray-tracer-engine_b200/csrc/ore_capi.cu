@@ -57,6 +57,9 @@ struct ore_context {
     float* sky[3] = {nullptr, nullptr, nullptr};
     int sky_w = 0, sky_h = 0;
     float sky_radius = 0.f;
+    float4* cubes = nullptr;   // 3 float4 per cube: bounds[0], bounds[1], orgin
+    float4* planes = nullptr;  // 2 float4 per plane: orgin, normal
+    int n_cubes = 0, n_planes = 0;
 
     // per-frame buffers
     float* dx_tab = nullptr;
@@ -182,7 +185,7 @@ extern "C" int ore_destroy(ore_context* ctx) {
     if (ctx->pixels_b) cudaFree(ctx->pixels_b);
     void* dev[] = {ctx->sph_exact, ctx->sph_prim, ctx->sph_cone, ctx->sph_shad, ctx->tex[0], ctx->tex[1], ctx->tex[2],
                    ctx->sky[0],    ctx->sky[1],   ctx->sky[2],   ctx->dx_tab, ctx->dy_tab, ctx->hit_id,
-                   ctx->hit_t,     ctx->hit_list, ctx->pixels,   ctx->counters};
+                   ctx->hit_t,     ctx->hit_list, ctx->pixels,   ctx->counters, ctx->cubes,   ctx->planes};
     for (void* p : dev)
         if (p) cudaFree(p);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -253,6 +256,52 @@ extern "C" int ore_set_spheres_aos32(ore_context* ctx, const void* records, int3
         tmp[4 * (size_t)i + 3] = f[8 * (size_t)i + 6];
     }
     return upload_spheres(ctx, tmp.data(), 4, 0, n);
+}
+
+extern "C" int ore_set_cubes(ore_context* ctx, const float* c1_c2, int32_t n) {
+    if (!ctx || n < 0 || (n > 0 && !c1_c2)) return fail(ctx, ORE_ERR_INVALID, "ore_set_cubes: bad arguments");
+    ORE_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->cubes) ORE_CUDA(ctx, cudaFree(ctx->cubes));
+    ctx->cubes = nullptr;
+    ctx->n_cubes = 0;
+    if (n == 0) return ORE_OK;
+    int rc;
+    if ((rc = ensure_pinned(ctx, (size_t)n * 3 * sizeof(float4)))) return rc;
+    float4* h = (float4*)ctx->pinned;
+    for (int i = 0; i < n; i++) {
+        const float* c = c1_c2 + 6 * (size_t)i;
+        h[3 * i + 0] = make_float4(c[0], c[1], c[2], 0.f);  // bounds[0] = c1, kernel.cu:393
+        h[3 * i + 1] = make_float4(c[3], c[4], c[5], 0.f);  // bounds[1] = c2
+        // orgin = divide(add(c1, c2), 2), kernel.cu:395 (float add, float divide)
+        h[3 * i + 2] = make_float4((c[0] + c[3]) / 2, (c[1] + c[4]) / 2, (c[2] + c[5]) / 2, 0.f);
+    }
+    ORE_CUDA(ctx, cudaMalloc((void**)&ctx->cubes, (size_t)n * 3 * sizeof(float4)));
+    ORE_CUDA(ctx, cudaMemcpyAsync(ctx->cubes, h, (size_t)n * 3 * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    ORE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->n_cubes = n;
+    return ORE_OK;
+}
+
+extern "C" int ore_set_planes(ore_context* ctx, const float* pos_normal, int32_t n) {
+    if (!ctx || n < 0 || (n > 0 && !pos_normal)) return fail(ctx, ORE_ERR_INVALID, "ore_set_planes: bad arguments");
+    ORE_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->planes) ORE_CUDA(ctx, cudaFree(ctx->planes));
+    ctx->planes = nullptr;
+    ctx->n_planes = 0;
+    if (n == 0) return ORE_OK;
+    int rc;
+    if ((rc = ensure_pinned(ctx, (size_t)n * 2 * sizeof(float4)))) return rc;
+    float4* h = (float4*)ctx->pinned;
+    for (int i = 0; i < n; i++) {
+        const float* c = pos_normal + 6 * (size_t)i;
+        h[2 * i + 0] = make_float4(c[0], c[1], c[2], 0.f);
+        h[2 * i + 1] = make_float4(c[3], c[4], c[5], 0.f);
+    }
+    ORE_CUDA(ctx, cudaMalloc((void**)&ctx->planes, (size_t)n * 2 * sizeof(float4)));
+    ORE_CUDA(ctx, cudaMemcpyAsync(ctx->planes, h, (size_t)n * 2 * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    ORE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->n_planes = n;
+    return ORE_OK;
 }
 
 extern "C" int ore_set_lights(ore_context* ctx, const float* lights7, int32_t n) {
@@ -453,6 +502,10 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
     prm.sky_w = ctx->sky_w;
     prm.sky_h = ctx->sky_h;
     prm.sky_radius = ctx->sky_radius;
+    prm.cubes = ctx->cubes;
+    prm.planes = ctx->planes;
+    prm.n_cubes = ctx->n_cubes;
+    prm.n_planes = ctx->n_planes;
     prm.hit_id = ctx->hit_id;
     prm.hit_t = ctx->hit_t;
     prm.hit_list = ctx->hit_list;
@@ -473,6 +526,8 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
     const bool exh = (fr->flags & ORE_FLAG_EXHAUSTIVE) != 0;
     const bool warp_cull = !(fr->flags & (ORE_FLAG_NO_WARP_CULL | ORE_FLAG_PER_RAY_SHADOW));
     const bool fast_libm = (fr->flags & ORE_FLAG_FAST_LIBM) != 0;  // default-path kernels only
+    if (!warp_cull && (ctx->n_cubes || ctx->n_planes))
+        return fail(ctx, ORE_ERR_INVALID, "cubes/planes are supported by the default kernels only (drop NO_WARP_CULL / PER_RAY_SHADOW)");
     {
         int grid = 0;
         if (warp_cull && fast_libm) {

@@ -85,6 +85,11 @@ struct FrameParams {
     uint32_t* hit_list;
     unsigned long long* counters;
     uint32_t* pixels;
+    // "next" primitives (kernel.cu:360-509): cube i = 3 float4 {bounds[0], bounds[1], orgin}, plane i = 2 float4
+    // {orgin, normal}; hit ids continue after the spheres: cube i -> n_spheres + i, plane i -> n_spheres + n_cubes + i
+    const float4* cubes;
+    const float4* planes;
+    int n_cubes, n_planes;
     LightP lights[MAX_LIGHTS];
 };
 
@@ -161,6 +166,53 @@ __device__ __noinline__ v3 primary_dir_call(const DirArgs a, float dx, float dy)
     float x = n.x * a.cy + z * a.sy;
     z = -n.x * a.sy + z * a.cy;
     return mk(x, y, z);
+}
+
+// ---- cubes and planes: small counts, exact tests, one out-of-line copy ----------------
+// castRay's cube loop then plane loop (kernel.cu:1344-1372), continuing the strict '<' search after the spheres
+__device__ __noinline__ void nearest_cube_plane(const float4* __restrict__ cubes, int nc, const float4* __restrict__ planes,
+                                                int np, int id_base, float Ox, float Oy, float Oz, float Dx, float Dy,
+                                                float Dz, float* best_t, int* best_id) {
+    const v3 O = mk(Ox, Oy, Oz), D = mk(Dx, Dy, Dz);
+    float nt = *best_t;
+    int id = *best_id;
+    for (int i = 0; i < nc; i++) {
+        const float4 b0 = __ldg(&cubes[3 * i]), b1 = __ldg(&cubes[3 * i + 1]);
+        float t;
+        if (ref_cube_intersect(O, D, mk(b0.x, b0.y, b0.z), mk(b1.x, b1.y, b1.z), t)) {
+            if (t < nt) {
+                nt = t;
+                id = id_base + i;
+            }
+        }
+    }
+    for (int i = 0; i < np; i++) {
+        const float4 po = __ldg(&planes[2 * i]), no = __ldg(&planes[2 * i + 1]);
+        float t;
+        if (ref_plane_intersect(O, D, mk(po.x, po.y, po.z), mk(no.x, no.y, no.z), t)) {
+            if (t < nt) {
+                nt = t;
+                id = id_base + nc + i;
+            }
+        }
+    }
+    *best_t = nt;
+    *best_id = id;
+}
+// castLightRay's plane loop then cube loop for one shadow ray (kernel.cu:1512-1536): any hit blocks
+__device__ __noinline__ bool blocked_by_cube_plane(const float4* __restrict__ cubes, int nc, const float4* __restrict__ planes,
+                                                   int np, float Ox, float Oy, float Oz, float Dx, float Dy, float Dz) {
+    const v3 O = mk(Ox, Oy, Oz), D = mk(Dx, Dy, Dz);
+    float t;
+    for (int i = 0; i < np; i++) {
+        const float4 po = __ldg(&planes[2 * i]), no = __ldg(&planes[2 * i + 1]);
+        if (ref_plane_intersect(O, D, mk(po.x, po.y, po.z), mk(no.x, no.y, no.z), t)) return true;
+    }
+    for (int i = 0; i < nc; i++) {
+        const float4 b0 = __ldg(&cubes[3 * i]), b1 = __ldg(&cubes[3 * i + 1]);
+        if (ref_cube_intersect(O, D, mk(b0.x, b0.y, b0.z), mk(b1.x, b1.y, b1.z), t)) return true;
+    }
+    return false;
 }
 
 // ------------------------------------------------------------------------------------
@@ -539,6 +591,16 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) primary_tile_kernel(const Fram
                 }
             }
             tp.release(c);
+        }
+
+        // ---- cubes, then planes (kernel.cu:1344-1372): exact tests continuing the same strict '<' search ----
+        if (prm.n_cubes | prm.n_planes) {
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+                if (x_ok && ty * P + p < prm.n_rows)
+                    nearest_cube_plane(prm.cubes, prm.n_cubes, prm.planes, prm.n_planes, prm.n_spheres, O.x, O.y, O.z, D[p].x,
+                                       D[p].y, D[p].z, &best_t[p], &best_id[p]);
+            }
         }
 
         // ---- epilogue: records, sky for misses, hit-list compaction (row-major inside the tile) ----
@@ -1338,12 +1400,23 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) shadow_beam_kernel(const Frame
             const v3 D = primary_dir(prm, prm.dx_tab[x], prm.dy_tab[k]);
             const float nt = prm.hit_t[o];
             my_id = prm.hit_id[o];
-            const float4 sc = __ldg(&prm.sph_exact[my_id]);
             const v3 new_org = ref_add(O0, ref_scale(D, nt));
-            normal = ref_sub(new_org, mk(sc.x, sc.y, sc.z));
-            ref_normalise(normal);
-            const float txf = (float)((1 + (double)ORE_ATAN2F(normal.z, normal.x) / 3.1415) * 0.5);
-            const float tyf = (float)((double)ORE_ACOSF(normal.y) / 3.1415);
+            float txf, tyf;
+            if (my_id >= prm.n_spheres + prm.n_cubes) {
+                // plane hit, kernel.cu:1407-1416
+                const float4 no = __ldg(&prm.planes[2 * (my_id - prm.n_spheres - prm.n_cubes) + 1]);
+                normal = mk(no.x, no.y, no.z);
+                txf = 0.5f;
+                tyf = 0.5f;
+            } else {
+                // sphere hit kernel.cu:1396-1405 / cube hit :1417-1425: normal from the primitive's `orgin`
+                const float4 sc = (my_id < prm.n_spheres) ? __ldg(&prm.sph_exact[my_id])
+                                                          : __ldg(&prm.cubes[3 * (my_id - prm.n_spheres) + 2]);
+                normal = ref_sub(new_org, mk(sc.x, sc.y, sc.z));
+                ref_normalise(normal);
+                txf = (float)((1 + (double)ORE_ATAN2F(normal.z, normal.x) / 3.1415) * 0.5);
+                tyf = (float)((double)ORE_ACOSF(normal.y) / 3.1415);
+            }
             const int maxX = prm.tex_w, maxY = prm.tex_h;
             start = ref_add(ref_scale(normal, 0.00001f), new_org);
             int c_index = (int)(tyf * (float)maxY) * maxX + (int)(txf * (float)maxX);
@@ -1575,6 +1648,18 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) shadow_beam_kernel(const Frame
                     if (__all_sync(0xffffffffu, !ing || blocked == ALL)) warp_done = true;
                 }
 
+            }
+
+            // ---- planes, then cubes (kernel.cu:1512-1536) for the rays no sphere blocked ----
+            if ((prm.n_cubes | prm.n_planes) && valid) {
+                uint32_t live = ~blocked & ALL;
+                while (live) {
+                    const int j = __ffs(live) - 1;
+                    live &= live - 1;
+                    if (blocked_by_cube_plane(prm.cubes, prm.n_cubes, prm.planes, prm.n_planes, start.x, start.y, start.z,
+                                              dirs[j * 3], dirs[j * 3 + 1], dirs[j * 3 + 2]))
+                        blocked |= 1u << j;
+                }
             }
 
             // ---- light accumulation (kernel.cu:1537-1543, 1673-1675) ----

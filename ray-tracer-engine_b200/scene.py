@@ -77,6 +77,9 @@ class Scene:
     extent: float = 10.0
     name: str = ""
     meta: dict = field(default_factory=dict)
+    # "next" primitives; the reference ships cube_count = plane_count = 0 (kernel.cu:1231)
+    cubes: np.ndarray = field(default_factory=lambda: np.zeros((0, 6), dtype=np.float32))   # [n,6] ctor args c1.xyz, c2.xyz
+    planes: np.ndarray = field(default_factory=lambda: np.zeros((0, 6), dtype=np.float32))  # [n,6] pos.xyz, normal.xyz
 
     @property
     def n_spheres(self) -> int:
@@ -155,6 +158,35 @@ def scaled_scene(n: int, seed: int, texture: Sprite | None = None, sky: Sprite |
         extent=extent,
         name=f"S({n},{seed})",
     )
+
+
+def with_cubes_and_plane(scene: Scene, n_cubes: int, seed: int, plane: bool = True, reference_formula: bool = False) -> Scene:
+    """Adds axis-aligned cubes and (optionally) the reference's floor plane to a scene.
+
+    reference_formula=True reproduces object::loadMesh (kernel.cu:1193-1199): pos = (rand()%100)/0.9 per axis,
+    cube(pos, pos-2) - far outside the sphere cloud; otherwise 2x2x2 cubes are scattered inside the scene's extent.
+    The plane is the reference's `plane({0,-4,0}, normalise({0,1,0}))` (kernel.cu:1187), lifted to y = 0.5 for the
+    scattered variant so that it is visible from the orbit cameras.
+    """
+    rng = Lcg(seed)
+    cubes = np.zeros((n_cubes, 6), dtype=np.float32)
+    for i in range(n_cubes):
+        if reference_formula:
+            p = [np.float32(float(rng.next() % 100) / 0.9) for _ in range(3)]
+            cubes[i, :3] = p
+            cubes[i, 3:] = [np.float32(v - np.float32(2)) for v in p]
+        else:
+            p = [np.float32((rng.next() % 100) / 100.0 * scene.extent) for _ in range(3)]
+            e = np.float32(0.4 + (rng.next() % 100) / 100.0)
+            cubes[i, :3] = [np.float32(v + e) for v in p]   # c1 is the upper corner, as in the reference (c2 = c1 - 2)
+            cubes[i, 3:] = [np.float32(v - e) for v in p]
+    planes = np.zeros((1 if plane else 0, 6), dtype=np.float32)
+    if plane:
+        planes[0] = [0, -4 if reference_formula else 0.5, 0, 0, 1, 0]
+    out = Scene(spheres=scene.spheres, lights=scene.lights, texture=scene.texture, sky=scene.sky, aspect=scene.aspect,
+                sky_size=scene.sky_size, extent=scene.extent, name=scene.name + f"+{n_cubes}cubes" + ("+plane" if plane else ""),
+                cubes=cubes, planes=planes)
+    return out
 
 
 def orbit_camera(scene: Scene, frame: int, n_frames: int = 240, pitch_deg: float = 15.0) -> Camera:

@@ -17,6 +17,17 @@ def _ref(n, seed, checker=False):
     return sc, scene.reference_camera()
 
 
+def _prims(n, seed, frame, n_cubes, cseed, plane=True):
+    base = scene.scaled_scene(n, seed) if n else scene.reference_scene(0, 1)
+    sc = scene.with_cubes_and_plane(base, n_cubes, cseed, plane=plane)
+    return sc, scene.orbit_camera(sc, frame)
+
+
+def _refprims():
+    sc = scene.with_cubes_and_plane(scene.reference_scene(64, 1), 8, 1, reference_formula=True)
+    return sc, scene.reference_camera()
+
+
 # small cases: the oracle finishes each in well under a second
 SMALL = [
     ("R64_refcam_160x120", lambda: _ref(64, 1), 160, 120, {}),
@@ -31,6 +42,11 @@ SMALL = [
     ("R1_one_sphere_64x48", lambda: _ref(1, 9), 64, 48, {}),
     ("R0_empty_scene_64x48", lambda: _ref(0, 1), 64, 48, {}),              # empty input: sky only
     ("R3_single_row", lambda: _ref(3, 4), 257, 480, {"y0": 240, "y1": 241}),
+    # cubes and the plane: hit types 3 and 2, shadows from all three primitive kinds
+    ("S64_cubes_plane_f0_160x90", lambda: _prims(64, 2, 0, 12, 5), 160, 90, {}),
+    ("S64_cubes_plane_f120_96x54", lambda: _prims(64, 2, 120, 12, 5), 96, 54, {}),
+    ("R64_refcubes_plane_128x96", lambda: _refprims(), 128, 96, {}),
+    ("cubes_only_plane_96x72", lambda: _prims(0, 1, 10, 5, 9), 96, 72, {}),
 ]
 
 

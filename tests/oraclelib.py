@@ -31,6 +31,7 @@ class OracleFrame(C.Structure):
         ("tex_w", C.c_int32), ("tex_h", C.c_int32), ("tex_r", _fp), ("tex_g", _fp), ("tex_b", _fp),
         ("sky_w", C.c_int32), ("sky_h", C.c_int32), ("sky_r", _fp), ("sky_g", _fp), ("sky_b", _fp),
         ("sky_size", C.c_float),
+        ("n_cubes", C.c_int32), ("cubes", _fp), ("n_planes", C.c_int32), ("planes", _fp),
     ]
 
 
@@ -81,6 +82,10 @@ class Oracle:
         f.tex_w, f.tex_h, f.tex_r, f.tex_g, f.tex_b = t.width, t.height, _ptr(t.r), _ptr(t.g), _ptr(t.b)
         f.sky_w, f.sky_h, f.sky_r, f.sky_g, f.sky_b = s.width, s.height, _ptr(s.r), _ptr(s.g), _ptr(s.b)
         f.sky_size = float(scene.sky_size)
+        cubes = np.ascontiguousarray(getattr(scene, "cubes", np.zeros((0, 6), np.float32)), dtype=np.float32)
+        planes = np.ascontiguousarray(getattr(scene, "planes", np.zeros((0, 6), np.float32)), dtype=np.float32)
+        f.n_cubes, f.cubes = cubes.shape[0], (_ptr(cubes.reshape(-1)) if cubes.size else None)
+        f.n_planes, f.planes = planes.shape[0], (_ptr(planes.reshape(-1)) if planes.size else None)
         pixels = np.zeros((rows, width), dtype=np.uint32)
         ids = np.zeros((rows, width), dtype=np.int32) if want_ids else None
         tt = np.zeros((rows, width), dtype=np.float32) if want_t else None
