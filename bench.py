@@ -171,6 +171,7 @@ def main():
     ap.add_argument("--workload", default="8k1024", choices=sorted(WORKLOADS))
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--in-flight", type=int, default=4, help="frames in flight per GPU (contexts/streams used round-robin)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank, local, world = dist_env()
@@ -212,10 +213,12 @@ def main():
     # a second context + stream: consecutive frames alternate between the two, so frame f+1's kernels fill the
     # SMs that frame f's persistent CTAs vacate at the end of a kernel (double-buffered rendering; every frame
     # still completes inside the timed region)
-    r2 = pkg.Renderer(local)
-    r2.set_scene(sc)
-    stream2 = torch.cuda.Stream(device=local)
-    ctxs = [(r, stream), (r2, stream2)]
+    ctxs = [(r, stream)]
+    for _ in range(max(1, args.in_flight) - 1):
+        rx = pkg.Renderer(local)
+        rx.set_scene(sc)
+        ctxs.append((rx, torch.cuda.Stream(device=local)))
+    NF = len(ctxs)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")  # > 126 MB L2
     sync_t = torch.zeros(1, dtype=torch.int32, device=f"cuda:{local}")
 
@@ -224,7 +227,7 @@ def main():
     if world > 1 and args.gather == "nccl":
         gatherer = pkg.multigpu.BandGatherer(W, H, torch.device("cuda", local))
     else:
-        peer = pkg.multigpu.PeerFrame(r, W, H, n_buffers=2)
+        peer = pkg.multigpu.PeerFrame(r, W, H, n_buffers=max(2, args.in_flight))
 
     def barrier():
         if world > 1:
@@ -237,7 +240,7 @@ def main():
         rr, st = ctxs[which]
         with torch.cuda.stream(st):
             if peer is not None:
-                rr.render_device(cam, W, H, stream=st.cuda_stream, **peer.band_args(f % 2))
+                rr.render_device(cam, W, H, stream=st.cuda_stream, **peer.band_args(f % len(peer.ptrs)))
                 if world > 1:
                     dist.all_reduce(sync_t)  # completion signal: every rank's rows of frame f have landed
             else:
@@ -260,8 +263,8 @@ def main():
         l2_note = "flushed before every step (256 MiB fill on the step's stream, inside the timed region)"
 
     # warm-up (both contexts)
-    for f in range(max(args.warmup, 2) * (2 if overlap else 1)):
-        render_step(f, f % 2 if overlap else 0)
+    for f in range(max(args.warmup, 2) * (NF if overlap else 1)):
+        render_step(f, f % NF if overlap else 0)
     barrier()
 
     sampler = ClockSampler(local)
@@ -269,18 +272,20 @@ def main():
     kernel_ms = []
     ev_start = torch.cuda.Event(enable_timing=True)
     ev_end = torch.cuda.Event(enable_timing=True)
-    ev_other = torch.cuda.Event()
     barrier()
     ev_start.record(stream)
-    stream2.wait_event(ev_start)
+    for _, st in ctxs[1:]:
+        st.wait_event(ev_start)
     for i in range(args.steps):
-        which = i % 2 if overlap else 0
+        which = i % NF if overlap else 0
         if small_frame:
             with torch.cuda.stream(ctxs[which][1]):
                 flush.fill_(1)
         render_step(args.warmup + i, which)   # no host sync inside the timed region
-    ev_other.record(stream2)
-    stream.wait_event(ev_other)
+    for _, st in ctxs[1:]:
+        ev_other = torch.cuda.Event()
+        ev_other.record(st)
+        stream.wait_event(ev_other)
     ev_end.record(stream)
     barrier()
     clocks = sampler.stop()
@@ -314,7 +319,7 @@ def main():
             stream.synchronize()
             if rank == 0:
                 if peer is not None:
-                    r.copy_to_host(host[f % 2], peer.ptrs[f % 2])
+                    r.copy_to_host(host[f % 2], peer.ptrs[f % len(peer.ptrs)])
                 else:
                     host[f % 2][:] = gatherer.frame.cpu().numpy().view(np.uint32)
 
@@ -467,8 +472,8 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": dict(config, l2=l2_note,
-                           frame_overlap=("consecutive frames alternate between two contexts/streams on each GPU"
-                                          if overlap else "none"),
+                           frame_overlap=(f"{NF} frames in flight per GPU (contexts/streams used round-robin)"
+                                          if overlap and NF > 1 else "none"),
                            parallelism=(f"row-bands x{world} (8-row blocks dealt round-robin), presenter = rank 0, gather = {args.gather}"
                                         if world > 1 else "1 GPU"),
                            hit_pixel_fraction=hits / (W * H * args.steps),
@@ -514,7 +519,8 @@ def main():
             r.host_free(h_)
     if peer is not None:
         peer.close()
-    r2.close()
+    for rx, _ in ctxs[1:]:
+        rx.close()
     r.close()
     if world > 1:
         dist.barrier()
