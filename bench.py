@@ -426,6 +426,25 @@ def main():
                    "ms_per_step": statistics.mean(ms4), "steps": 10,
                    "kernel_ms": {"prep": statistics.mean(m[0] for m in kms4), "primary": statistics.mean(m[1] for m in kms4),
                                  "shadow": statistics.mean(m[2] for m in kms4)}}
+    primary_only = None
+    if world == 1:
+        # the primary-only fraction (light_size = 0 is a legal reference configuration: the light
+        # loop runs zero times, kernel.cu:1665): tests = W*H*N exactly
+        r.set_lights(sc.lights[:0])
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for i in range(3):
+            r.render_device(camera(i), W, H, out_ptr=count_out, stream=stream.cuda_stream)
+        stream.synchronize()
+        ev0.record(stream)
+        for i in range(10):
+            r.render_device(camera(args.warmup + i), W, H, out_ptr=count_out, stream=stream.cuda_stream)
+        ev1.record(stream)
+        ev1.synchronize()
+        po_ms = ev0.elapsed_time(ev1) / 10
+        r.set_lights(sc.lights)
+        po_tf = FLOP_PER_TEST * W * H * sc.n_spheres / (po_ms * 1e-3) / 1e12
+        primary_only = {"what": "n_lights = 0: primary nearest hit + sky only; tests = W*H*N", "ms_per_step": po_ms,
+                        "value": W * H / po_ms / 1e3, "unit": "Mrays/s", "achieved": po_tf, "achieved_unit": "TFLOP/s"}
     fast_libm = None
     if world == 1:
         # the same frames with ORE_FLAG_FAST_LIBM (CUDA's libm: within 1 LSB instead of bit-identical)
@@ -512,6 +531,7 @@ def main():
             "reference_kernel_on_b200": ref_gpu,
             "also_configs2_4k1024": also_4k,
             "fast_libm": fast_libm,
+            "primary_only": (dict(primary_only, frac=primary_only["achieved"] / peak_tf) if primary_only and peak_tf else primary_only),
         }
         print(json.dumps(line))
     if host:
