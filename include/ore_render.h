@@ -134,6 +134,17 @@ int ore_set_cubes(ore_context* ctx, const float* c1_c2, int32_t n);
 /* Replaces object::planeAllocMem (kernel.cu:1213-1217, which copies ONE plane; any count is accepted here):
  * n x {pos.xyz, normal.xyz} = the `plane(pos, normal)` ctor arguments (kernel.cu:364-367). */
 int ore_set_planes(ore_context* ctx, const float* pos_normal, int32_t n);
+/* Triangle mesh with its flat BVH, exactly as the reference's `mesh` holds it once its OBJ
+ * loader and createBvhMesh() have run on the host (kernel.cu:577-936) and mesh::allocMem / Bvhbox::AllocMem would
+ * copy it (kernel.cu:999-1017, 528-535): the loader and the builder stay on the host, this call replaces the copy.
+ *   tris27      : n_tris x 27 floats = `triangle` {points[3], normal, vecNormal[3], vt[3]} (kernel.cu:206-212)
+ *   has_normals : mesh::has_normals
+ *   box_bounds6 : n_boxes x {bounds[0].xyz, bounds[1].xyz} of each leaf's `bvhbox` cube
+ *   box_offsets : n_boxes + 1; leaf j holds box_indices[box_offsets[j] .. box_offsets[j+1])  (Bvhbox::indexes/length)
+ * Hit ids continue after spheres, cubes and planes: triangle i -> n_spheres + n_cubes + n_planes + i.
+ * Exact tests, linear scan over the leaves per ray like the reference (kernel.cu:1293-1328,1475-1497). */
+int ore_set_mesh(ore_context* ctx, const float* tris27, int32_t n_tris, int32_t has_normals, const float* box_bounds6,
+                 const int32_t* box_offsets, const int32_t* box_indices, int32_t n_boxes);
 /* Replaces cudaMalloc+cudaMemcpy of `lights` in update() (kernel.cu:1776-1778):
  * n x {pos.xyz, size, r, g, b} (kernel.cu:1246-1261). */
 int ore_set_lights(ore_context* ctx, const float* lights7, int32_t n);

@@ -116,6 +116,30 @@ static inline v3 cube_origin(const oracle_frame* f, int i) {
 static inline v3 plane_pos(const oracle_frame* f, int i) { const float* c = f->planes + 6 * (size_t)i; v3 r = {c[0], c[1], c[2]}; return r; }
 static inline v3 plane_nrm(const oracle_frame* f, int i) { const float* c = f->planes + 6 * (size_t)i; v3 r = {c[3], c[4], c[5]}; return r; }
 
+/* ---- mesh::rayIntersect (Moeller-Trumbore), kernel.cu:1024-1059 ------------------------ */
+static inline int tri_intersect(v3 O, v3 D, const float* tri, float* t, float* u, float* v) {
+    v3 p0 = {tri[0], tri[1], tri[2]}, p1 = {tri[3], tri[4], tri[5]}, p2 = {tri[6], tri[7], tri[8]};
+    v3 edge1 = v_sub(p1, p0);
+    v3 edge2 = v_sub(p2, p0);
+    v3 h, s, q;
+    float a, f;
+    h = v_cross(D, edge2);
+    a = v_dot(edge1, h);
+    if (a > -0.0000001f && a < 0.0000001) return 0;   /* float literal, then DOUBLE literal */
+    f = 1.f / a;
+    s = v_sub(O, p0);
+    *u = f * v_dot(s, h);
+    if (*u < 0.f || *u > 1.f) return 0;
+    q = v_cross(s, edge1);
+    *v = f * v_dot(D, q);
+    if (*v < 0.f || *u + *v > 1.f) return 0;
+    *t = f * v_dot(edge2, q);
+    if (*t > 0.0000001) return 1;                      /* double compare */
+    return 0;
+}
+static inline v3 box_b0(const oracle_frame* f, int j) { const float* c = f->box_bounds + 6 * (size_t)j; v3 r = {c[0], c[1], c[2]}; return r; }
+static inline v3 box_b1(const oracle_frame* f, int j) { const float* c = f->box_bounds + 6 * (size_t)j; v3 r = {c[3], c[4], c[5]}; return r; }
+
 /* ---- camera::rotateDir, kernel.cu:248-258 ------------------------------------------- */
 static inline v3 rotate_dir(v3 v, float yaw, float pitch) {
     float yawRad = yaw * (3.1415 / 180);
@@ -171,6 +195,15 @@ int oracle_sphere_intersect(const float org[3], const float dir[3], const float 
 
 const char* oracle_kind(void) { return "port"; }
 
+/* only the _ref library (the reference's own loader) can build a mesh from an OBJ file */
+int oracle_ref_build_mesh(const char* obj_path, float* tris, int32_t cap_tris, int32_t* n_tris, int32_t* has_normals,
+                          float* box_bounds, int32_t* box_offsets, int32_t cap_boxes, int32_t* n_boxes,
+                          int32_t* box_indices, int32_t cap_indices) {
+    (void)obj_path; (void)tris; (void)cap_tris; (void)n_tris; (void)has_normals; (void)box_bounds; (void)box_offsets;
+    (void)cap_boxes; (void)n_boxes; (void)box_indices; (void)cap_indices;
+    return 1;
+}
+
 /* texel index clamp: the reference reads up to width+1 floats past a plane at the poles
  * (undefined there); the harness defines those reads as the last texel (see
  * ref_build/sprite_raw.cpp, which pads the reference's buffers accordingly). */
@@ -203,16 +236,31 @@ static float cast_light_ray(const oracle_frame* f, v3 start, const float* l, v3 
         v3 new_dir = v_normalise(&nd);                                                   /* :1468 */
         int shadow = 0;
         int i;
-        for (i = 0; i < f->n_spheres; i++) {                                             /* :1501-1510 */
-            const float* s = f->spheres + 4 * (size_t)i;
-            v3 c = {s[0], s[1], s[2]};
-            float t;
-            if (sphere_intersect(start, new_dir, c, s[3], &t)) {
-                shadow = 1;
-                break;
+        for (int jb = 0; jb < f->n_boxes && !shadow; jb++) {                             /* :1475-1497 */
+            float temp;
+            if (cube_intersect(start, new_dir, box_b0(f, jb), box_b1(f, jb), &temp)) {
+                for (int k = f->box_offsets[jb]; k < f->box_offsets[jb + 1]; k++) {
+                    float t, u, v;
+                    if (tri_intersect(start, new_dir, f->tris + 27 * (size_t)f->box_indices[k], &t, &u, &v)) {
+                        shadow = 1;
+                        break;
+                    }
+                }
             }
         }
-        *n_tests += (uint64_t)(shadow ? i + 1 : f->n_spheres);
+        if (!shadow) {                                                                   /* :1499-1510 */
+            for (i = 0; i < f->n_spheres; i++) {
+                const float* s = f->spheres + 4 * (size_t)i;
+                v3 c = {s[0], s[1], s[2]};
+                float t;
+                if (sphere_intersect(start, new_dir, c, s[3], &t)) {
+                    shadow = 1;
+                    break;
+                }
+            }
+            /* sphere::intersect calls this ray made: up to and including its first blocker */
+            *n_tests += (uint64_t)(shadow ? i + 1 : f->n_spheres);
+        }
         if (!shadow)                                                                     /* planes, :1512-1523 */
             for (i = 0; i < f->n_planes; i++) {
                 float t;
@@ -266,9 +314,29 @@ static uint32_t trace_pixel(const oracle_frame* f, int x, int y, int32_t* id_out
     v3 O = v_add(eyePos, camOrg);
     v3 D = rotate_dir(dn, f->cam_yaw, f->cam_pitch);                                     /* :1631 */
 
-    /* castRay sphere loop, kernel.cu:1330-1342 */
     float nt = INFINITY;
     int hit_index = -1;
+    int hit_type = 1;
+    float nu = 0.f, nv = 0.f;
+    /* castRay triangle loop over the flat BVH, kernel.cu:1293-1328 */
+    for (int jb = 0; jb < f->n_boxes; jb++) {
+        float temp;
+        if (cube_intersect(O, D, box_b0(f, jb), box_b1(f, jb), &temp)) {
+            for (int k = f->box_offsets[jb]; k < f->box_offsets[jb + 1]; k++) {
+                float t, u, v;
+                if (tri_intersect(O, D, f->tris + 27 * (size_t)f->box_indices[k], &t, &u, &v)) {
+                    if (t < nt) {
+                        nt = t;
+                        nv = v;
+                        nu = u;
+                        hit_index = f->box_indices[k];
+                        hit_type = 0;
+                    }
+                }
+            }
+        }
+    }
+    /* castRay sphere loop, kernel.cu:1330-1342 */
     for (int i = 0; i < f->n_spheres; i++) {
         const float* s = f->spheres + 4 * (size_t)i;
         v3 c = {s[0], s[1], s[2]};
@@ -277,11 +345,11 @@ static uint32_t trace_pixel(const oracle_frame* f, int x, int y, int32_t* id_out
             if (t < nt) {
                 nt = t;
                 hit_index = i;
+                hit_type = 1;
             }
         }
     }
     cnt[0] += (uint64_t)f->n_spheres;
-    int hit_type = 1;
     for (int i = 0; i < f->n_cubes; i++) {                                               /* :1344-1357 */
         float t;
         if (cube_intersect(O, D, cube_b0(f, i), cube_b1(f, i), &t)) {
@@ -306,6 +374,7 @@ static uint32_t trace_pixel(const oracle_frame* f, int x, int y, int32_t* id_out
         int enc = hit_index;
         if (hit_type == 3) enc += f->n_spheres;
         if (hit_type == 2) enc += f->n_spheres + f->n_cubes;
+        if (hit_type == 0) enc += f->n_spheres + f->n_cubes + f->n_planes;
         *id_out = (nt != INFINITY) ? enc : -1;
     }
     if (t_out) *t_out = nt;
@@ -316,7 +385,19 @@ static uint32_t trace_pixel(const oracle_frame* f, int x, int y, int32_t* id_out
         v3 new_org = v_add(O, v_scale(D, nt));
         v3 normal;
         float tx, ty;
-        if (hit_type == 2) {
+        if (hit_type == 0) {                                                             /* :1380-1394 */
+            const float* tr = f->tris + 27 * (size_t)hit_index;
+            const v3 vn0 = {tr[12], tr[13], tr[14]}, vn1 = {tr[15], tr[16], tr[17]}, vn2 = {tr[18], tr[19], tr[20]};
+            if (f->mesh_has_normals) {
+                normal = v_add(v_add(v_scale(vn0, (1 - nu - nv)), v_scale(vn1, nu)), v_scale(vn2, nv));
+                v_normalise(&normal);
+            } else {
+                normal.x = tr[9]; normal.y = tr[10]; normal.z = tr[11];
+            }
+            tx = ((1 - nu - nv) * tr[21]) + (nu * tr[23]) + (nv * tr[25]);
+            ty = ((1 - nu - nv) * tr[22]) + (nu * tr[24]) + (nv * tr[26]);
+            new_org = v_add(normal, v_add(O, v_scale(D, nt)));   /* the unit normal is ADDED to the hit point */
+        } else if (hit_type == 2) {
             normal = plane_nrm(f, hit_index);
             tx = 0.5;
             ty = 0.5;

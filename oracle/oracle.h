@@ -43,13 +43,24 @@ typedef struct oracle_frame {
     int32_t n_planes;        /* the reference copies ONE plane to the device (kernel.cu:1213-1217):
                                 the _ref build accepts 0 or 1, the C restatement any count       */
     const float* planes;     /* n x 6: plane ctor args pos.xyz, normal.xyz (kernel.cu:364-367) */
+    /* triangle mesh with its flat BVH, exactly as the reference's `mesh` holds it after its OBJ loader and
+     * createBvhMesh() ran (kernel.cu:559-1017); use oracle_ref_build_mesh (the _ref library) to obtain these from
+     * an OBJ file with the reference's OWN loader/builder */
+    int32_t n_tris;
+    const float* tris;       /* n x 27: `triangle` = points[3], normal, vecNormal[3], vt[3] (kernel.cu:206-212) */
+    int32_t mesh_has_normals;/* mesh::has_normals (kernel.cu:567)                                           */
+    int32_t n_boxes;         /* mesh::bvhbox_count leaf boxes                                                */
+    const float* box_bounds; /* n_boxes x 6: cube bounds[0].xyz, bounds[1].xyz of Bvhbox::bvhbox            */
+    const int32_t* box_offsets; /* n_boxes + 1: leaf j holds box_indices[box_offsets[j] .. box_offsets[j+1]) */
+    const int32_t* box_indices; /* triangle indices per leaf, in the leaf's order (Bvhbox::indexes)          */
 } oracle_frame;
 
 /* Renders the selected rows.  Outputs are packed by rendered row (row k of the
  * output = image row y0 + k*y_step), `width` entries per row; any may be NULL.
  *   pixels : 0x00RRGGBB                         (rgbToInt, kernel.cu:546-556)
  *   hit_id : nearest primitive, -1 = miss: sphere i -> i, cube i -> n_spheres + i, plane i ->
- *            n_spheres + n_cubes + i   (castRay loops, kernel.cu:1330-1372; hit_type 1, 3, 2)
+ *            n_spheres + n_cubes + i, triangle i -> n_spheres + n_cubes + n_planes + i
+ *            (castRay loops, kernel.cu:1293-1372; hit_type 1, 3, 2, 0)
  *   hit_t  : nearest t (bit pattern matters), +inf on miss
  *   counts : [0] primary sphere::intersect calls, [1] shadow-phase calls in the
  *            reference's loop order incl. early break (kernel.cu:1501-1510),
@@ -66,6 +77,13 @@ int oracle_sphere_intersect(const float org[3], const float dir[3], const float 
 
 /* rgbToInt (kernel.cu:546-556) */
 uint32_t oracle_rgb_to_int(int r, int g, int b);
+
+/* _ref library only: runs the reference's OWN OBJ loader and BVH builder (mesh::mesh, createBvhMesh,
+ * kernel.cu:577-936) on `obj_path` and copies out the flat arrays in the oracle_frame layout.
+ * Returns 0 on success, 1 if a capacity is too small or the file cannot be read. */
+int oracle_ref_build_mesh(const char* obj_path, float* tris, int32_t cap_tris, int32_t* n_tris, int32_t* has_normals,
+                          float* box_bounds, int32_t* box_offsets, int32_t cap_boxes, int32_t* n_boxes,
+                          int32_t* box_indices, int32_t cap_indices);
 
 /* "reference" or "port" */
 const char* oracle_kind(void);

@@ -60,6 +60,46 @@ extern "C" int oracle_sphere_intersect(const float org[3], const float dir[3], c
     return hit ? 1 : 0;
 }
 
+// The reference's OWN OBJ loader and BVH builder (mesh::mesh -> createBvhMesh, kernel.cu:577-936), run on a file,
+// with the result copied out as flat arrays (the loader prints every leaf box to stdout: silenced here).
+extern "C" int oracle_ref_build_mesh(const char* obj_path, float* tris, int32_t cap_tris, int32_t* n_tris,
+                                     int32_t* has_normals, float* box_bounds, int32_t* box_offsets, int32_t cap_boxes,
+                                     int32_t* n_boxes, int32_t* box_indices, int32_t cap_indices) {
+    {
+        std::ifstream probe(obj_path);
+        if (!probe.is_open()) return 1;
+    }
+    std::streambuf* old = std::cout.rdbuf();
+    std::ostringstream sink;
+    std::cout.rdbuf(sink.rdbuf());
+    mesh* m = new mesh(std::string(obj_path));
+    std::cout.rdbuf(old);
+    int rc = 0;
+    if (m->poly_count > cap_tris || m->bvhbox_count > cap_boxes) rc = 1;
+    if (!rc) {
+        *n_tris = m->poly_count;
+        *has_normals = m->has_normals ? 1 : 0;
+        *n_boxes = m->bvhbox_count;
+        memcpy(tris, m->h_tri_arr, sizeof(triangle) * (size_t)m->poly_count);
+        int off = 0;
+        for (int j = 0; j < m->bvhbox_count && !rc; j++) {
+            const Bvhbox& b = m->h_box[j];
+            if (off + b.length > cap_indices) {
+                rc = 1;
+                break;
+            }
+            const vec3d lo = b.bvhbox->bounds[0], hi = b.bvhbox->bounds[1];
+            float* bb = box_bounds + 6 * (size_t)j;
+            bb[0] = lo.x; bb[1] = lo.y; bb[2] = lo.z; bb[3] = hi.x; bb[4] = hi.y; bb[5] = hi.z;
+            box_offsets[j] = off;
+            memcpy(box_indices + off, b.indexes, sizeof(int) * (size_t)b.length);
+            off += b.length;
+        }
+        if (!rc) box_offsets[m->bvhbox_count] = off;
+    }
+    return rc;  // the mesh object is leaked on purpose: the reference never frees one either
+}
+
 extern "C" int oracle_render(const oracle_frame* f, uint32_t* pixels, int32_t* hit_id, float* hit_t,
                              uint64_t* counts, int n_threads) {
     if (!f || f->width <= 0 || f->height <= 0 || f->y_step <= 0) return 1;
@@ -100,6 +140,33 @@ extern "C" int oracle_render(const oracle_frame* f, uint32_t* pixels, int32_t* h
     // (kernel.cu:1293-1328,1475-1497) run zero times - the sphere-only scene.
     o->mesh1 = new mesh("/nonexistent/ore-none.obj");
     if (o->mesh1->bvhbox_count != 0) return 2;
+    std::vector<cube*> box_cubes;
+    if (f->n_tris > 0) {
+        // the reference's mesh object filled from the flat arrays exactly as its loader + createBvhMesh + allocMem
+        // leave it (kernel.cu:559-1017): triangle array, has_normals, leaf boxes with their index lists
+        mesh* m = o->mesh1;
+        static_assert(sizeof(triangle) == 27 * sizeof(float), "triangle layout");
+        m->poly_count = f->n_tris;
+        m->h_tri_arr = new triangle[f->n_tris];
+        memcpy(m->h_tri_arr, f->tris, sizeof(triangle) * (size_t)f->n_tris);
+        m->d_tri_arr = m->h_tri_arr;
+        m->has_normals = f->mesh_has_normals != 0;
+        m->bvhbox_count = f->n_boxes;
+        m->h_box = new Bvhbox[f->n_boxes > 0 ? f->n_boxes : 1];
+        for (int j = 0; j < f->n_boxes; j++) {
+            const float* b = f->box_bounds + 6 * (size_t)j;
+            const int len = f->box_offsets[j + 1] - f->box_offsets[j];
+            int* idx = new int[len > 0 ? len : 1];
+            memcpy(idx, f->box_indices + f->box_offsets[j], sizeof(int) * (size_t)len);
+            m->h_box[j] = Bvhbox({b[0], b[1], b[2]}, {b[3], b[4], b[5]}, idx, len);
+            // the loader builds the leaf cube with cube(low, high) whose ctor also derives `orgin`; the bounds are
+            // what the intersection reads.  AllocMem's device copies alias the host objects here.
+            m->h_box[j].d_bvhbox = m->h_box[j].bvhbox;
+            m->h_box[j].d_indexes = idx;
+            box_cubes.push_back(m->h_box[j].bvhbox);
+        }
+        m->d_box = m->h_box;
+    }
 
     skybox* sky = new skybox("ore:sky", f->sky_size);
 
@@ -142,6 +209,7 @@ extern "C" int oracle_render(const oracle_frame* f, uint32_t* pixels, int32_t* h
                 bool hit = castRay(*o, cam_ray, ht, hi, nt, nu, nv, no, nn, tx, ty);
                 if (hit && ht == 3) hi += f->n_spheres;                      // same encoding as oracle.h
                 if (hit && ht == 2) hi += f->n_spheres + f->n_cubes;
+                if (hit && ht == 0) hi += f->n_spheres + f->n_cubes + f->n_planes;
                 if (hit_id) hit_id[(size_t)k * W + x] = hit ? hi : -1;
                 if (hit_t) hit_t[(size_t)k * W + x] = nt;
             }
@@ -159,6 +227,12 @@ extern "C" int oracle_render(const oracle_frame* f, uint32_t* pixels, int32_t* h
     delete[] o->c1;
     delete o->planes;
     delete[] o->s1;
+    if (f->n_tris > 0) {
+        for (int j = 0; j < f->n_boxes; j++) delete[] o->mesh1->h_box[j].indexes;
+        for (cube* c : box_cubes) delete c;
+        delete[] o->mesh1->h_box;
+        delete[] o->mesh1->h_tri_arr;
+    }
     delete o->mesh1;
     delete o;
     sprite_raw_unregister("ore:tex");

@@ -21,7 +21,7 @@ ORE_FLAG_FAST_LIBM = 16
 
 EXPORTS = [
     "ore_create", "ore_destroy", "ore_abi_version", "ore_last_error",
-    "ore_set_spheres", "ore_set_spheres_aos32", "ore_set_cubes", "ore_set_planes", "ore_set_lights", "ore_set_texture", "ore_set_sky",
+    "ore_set_spheres", "ore_set_spheres_aos32", "ore_set_cubes", "ore_set_planes", "ore_set_mesh", "ore_set_lights", "ore_set_texture", "ore_set_sky",
     "ore_render", "ore_render_device", "ore_synchronize",
     "ore_get_hits", "ore_get_counters", "ore_get_kernel_ms", "ore_measure_fp32_peak", "ore_debug_libm",
     "ore_render_async", "ore_wait", "ore_host_alloc", "ore_host_free",
@@ -72,6 +72,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.ore_set_lights.argtypes = [vp, fp, i32]
     lib.ore_set_cubes.argtypes = [vp, fp, i32]
     lib.ore_set_planes.argtypes = [vp, fp, i32]
+    ip = C.POINTER(C.c_int32)
+    lib.ore_set_mesh.argtypes = [vp, fp, i32, i32, fp, ip, ip, i32]
     lib.ore_set_texture.argtypes = [vp, fp, fp, fp, i32, i32]
     lib.ore_set_sky.argtypes = [vp, fp, fp, fp, i32, i32, C.c_float]
     lib.ore_render.argtypes = [vp, C.POINTER(OreCamera), C.POINTER(OreFrame), vp]
@@ -154,6 +156,16 @@ class Renderer:
         a = np.ascontiguousarray(pos_normal, dtype=np.float32).reshape(-1, 6)
         self._check(self.lib.ore_set_planes(self.ctx, _fptr(a.reshape(-1)) if a.size else None, a.shape[0]), "ore_set_planes")
 
+    def set_mesh(self, mesh):
+        """mesh: scene.Mesh (triangles + flat BVH as the reference holds them) or None"""
+        ip = C.POINTER(C.c_int32)
+        if mesh is None or mesh.n_tris == 0:
+            self._check(self.lib.ore_set_mesh(self.ctx, None, 0, 0, None, None, None, 0), "ore_set_mesh")
+            return
+        self._check(self.lib.ore_set_mesh(self.ctx, _fptr(mesh.tris.reshape(-1)), mesh.n_tris, int(mesh.has_normals),
+                                          _fptr(mesh.box_bounds.reshape(-1)), mesh.box_offsets.ctypes.data_as(ip),
+                                          mesh.box_indices.ctypes.data_as(ip), mesh.n_boxes), "ore_set_mesh")
+
     def set_lights(self, lights7: np.ndarray):
         a = np.ascontiguousarray(lights7, dtype=np.float32).reshape(-1, 7)
         self._check(self.lib.ore_set_lights(self.ctx, _fptr(a.reshape(-1)) if a.size else None, a.shape[0]), "ore_set_lights")
@@ -174,6 +186,7 @@ class Renderer:
         self.set_sky(scene.sky, scene.sky_size)
         self.set_cubes(getattr(scene, "cubes", np.zeros((0, 6), np.float32)))
         self.set_planes(getattr(scene, "planes", np.zeros((0, 6), np.float32)))
+        self.set_mesh(getattr(scene, "mesh", None))
         self.scene = scene
 
     # ---- render ----

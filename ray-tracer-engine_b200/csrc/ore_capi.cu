@@ -60,6 +60,11 @@ struct ore_context {
     float4* cubes = nullptr;   // 3 float4 per cube: bounds[0], bounds[1], orgin
     float4* planes = nullptr;  // 2 float4 per plane: orgin, normal
     int n_cubes = 0, n_planes = 0;
+    float* tris = nullptr;     // 27 floats per triangle
+    float4* boxes = nullptr;   // 2 float4 per leaf box
+    int* box_offsets = nullptr;
+    int* box_indices = nullptr;
+    int n_tris = 0, n_boxes = 0, mesh_has_normals = 0;
 
     // per-frame buffers
     float* dx_tab = nullptr;
@@ -185,7 +190,8 @@ extern "C" int ore_destroy(ore_context* ctx) {
     if (ctx->pixels_b) cudaFree(ctx->pixels_b);
     void* dev[] = {ctx->sph_exact, ctx->sph_prim, ctx->sph_cone, ctx->sph_shad, ctx->tex[0], ctx->tex[1], ctx->tex[2],
                    ctx->sky[0],    ctx->sky[1],   ctx->sky[2],   ctx->dx_tab, ctx->dy_tab, ctx->hit_id,
-                   ctx->hit_t,     ctx->hit_list, ctx->pixels,   ctx->counters, ctx->cubes,   ctx->planes};
+                   ctx->hit_t,     ctx->hit_list, ctx->pixels,   ctx->counters, ctx->cubes,   ctx->planes,   ctx->tris,
+                   ctx->boxes,     ctx->box_offsets, ctx->box_indices};
     for (void* p : dev)
         if (p) cudaFree(p);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -301,6 +307,57 @@ extern "C" int ore_set_planes(ore_context* ctx, const float* pos_normal, int32_t
     ORE_CUDA(ctx, cudaMemcpyAsync(ctx->planes, h, (size_t)n * 2 * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     ORE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->n_planes = n;
+    return ORE_OK;
+}
+
+extern "C" int ore_set_mesh(ore_context* ctx, const float* tris27, int32_t n_tris, int32_t has_normals,
+                            const float* box_bounds6, const int32_t* box_offsets, const int32_t* box_indices,
+                            int32_t n_boxes) {
+    if (!ctx || n_tris < 0 || n_boxes < 0) return fail(ctx, ORE_ERR_INVALID, "ore_set_mesh: bad arguments");
+    if (n_tris > 0 && n_boxes > 0 && (!tris27 || !box_bounds6 || !box_offsets || !box_indices))
+        return fail(ctx, ORE_ERR_INVALID, "ore_set_mesh: null array");
+    ORE_CUDA(ctx, cudaSetDevice(ctx->device));
+    void* old[] = {ctx->tris, ctx->boxes, ctx->box_offsets, ctx->box_indices};
+    for (void* p : old)
+        if (p) ORE_CUDA(ctx, cudaFree(p));
+    ctx->tris = nullptr;
+    ctx->boxes = nullptr;
+    ctx->box_offsets = nullptr;
+    ctx->box_indices = nullptr;
+    ctx->n_tris = ctx->n_boxes = ctx->mesh_has_normals = 0;
+    if (n_tris == 0 || n_boxes == 0) return ORE_OK;
+    const int n_idx = box_offsets[n_boxes];
+    if (box_offsets[0] != 0 || n_idx < 0) return fail(ctx, ORE_ERR_INVALID, "ore_set_mesh: bad offsets");
+    for (int j = 0; j < n_boxes; j++)
+        if (box_offsets[j + 1] < box_offsets[j]) return fail(ctx, ORE_ERR_INVALID, "ore_set_mesh: offsets must ascend");
+    for (int k = 0; k < n_idx; k++)
+        if (box_indices[k] < 0 || box_indices[k] >= n_tris) return fail(ctx, ORE_ERR_INVALID, "ore_set_mesh: triangle index out of range");
+    const size_t tb = (size_t)n_tris * 27 * sizeof(float), bb = (size_t)n_boxes * 2 * sizeof(float4);
+    const size_t ob = (size_t)(n_boxes + 1) * sizeof(int), ib = (size_t)(n_idx > 0 ? n_idx : 1) * sizeof(int);
+    int rc;
+    if ((rc = ensure_pinned(ctx, tb + bb + ob + ib))) return rc;
+    char* h = (char*)ctx->pinned;
+    memcpy(h, tris27, tb);
+    float4* hb = (float4*)(h + tb);
+    for (int j = 0; j < n_boxes; j++) {
+        const float* b = box_bounds6 + 6 * (size_t)j;
+        hb[2 * j] = make_float4(b[0], b[1], b[2], 0.f);
+        hb[2 * j + 1] = make_float4(b[3], b[4], b[5], 0.f);
+    }
+    memcpy(h + tb + bb, box_offsets, ob);
+    memcpy(h + tb + bb + ob, box_indices, (size_t)n_idx * sizeof(int));
+    ORE_CUDA(ctx, cudaMalloc((void**)&ctx->tris, tb));
+    ORE_CUDA(ctx, cudaMalloc((void**)&ctx->boxes, bb));
+    ORE_CUDA(ctx, cudaMalloc((void**)&ctx->box_offsets, ob));
+    ORE_CUDA(ctx, cudaMalloc((void**)&ctx->box_indices, ib));
+    ORE_CUDA(ctx, cudaMemcpyAsync(ctx->tris, h, tb, cudaMemcpyHostToDevice, ctx->stream));
+    ORE_CUDA(ctx, cudaMemcpyAsync(ctx->boxes, h + tb, bb, cudaMemcpyHostToDevice, ctx->stream));
+    ORE_CUDA(ctx, cudaMemcpyAsync(ctx->box_offsets, h + tb + bb, ob, cudaMemcpyHostToDevice, ctx->stream));
+    ORE_CUDA(ctx, cudaMemcpyAsync(ctx->box_indices, h + tb + bb + ob, ib, cudaMemcpyHostToDevice, ctx->stream));
+    ORE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->n_tris = n_tris;
+    ctx->n_boxes = n_boxes;
+    ctx->mesh_has_normals = has_normals ? 1 : 0;
     return ORE_OK;
 }
 
@@ -506,6 +563,13 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
     prm.planes = ctx->planes;
     prm.n_cubes = ctx->n_cubes;
     prm.n_planes = ctx->n_planes;
+    prm.tris = ctx->tris;
+    prm.boxes = ctx->boxes;
+    prm.box_offsets = ctx->box_offsets;
+    prm.box_indices = ctx->box_indices;
+    prm.n_tris = ctx->n_tris;
+    prm.n_boxes = ctx->n_boxes;
+    prm.mesh_has_normals = ctx->mesh_has_normals;
     prm.hit_id = ctx->hit_id;
     prm.hit_t = ctx->hit_t;
     prm.hit_list = ctx->hit_list;
@@ -526,8 +590,9 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
     const bool exh = (fr->flags & ORE_FLAG_EXHAUSTIVE) != 0;
     const bool warp_cull = !(fr->flags & (ORE_FLAG_NO_WARP_CULL | ORE_FLAG_PER_RAY_SHADOW));
     const bool fast_libm = (fr->flags & ORE_FLAG_FAST_LIBM) != 0;  // default-path kernels only
-    if (!warp_cull && (ctx->n_cubes || ctx->n_planes))
-        return fail(ctx, ORE_ERR_INVALID, "cubes/planes are supported by the default kernels only (drop NO_WARP_CULL / PER_RAY_SHADOW)");
+    if (!warp_cull && (ctx->n_cubes || ctx->n_planes || ctx->n_boxes))
+        return fail(ctx, ORE_ERR_INVALID,
+                    "cubes/planes/meshes are supported by the default kernels only (drop NO_WARP_CULL / PER_RAY_SHADOW)");
     {
         int grid = 0;
         if (warp_cull && fast_libm) {

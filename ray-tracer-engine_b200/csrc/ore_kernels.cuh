@@ -90,6 +90,14 @@ struct FrameParams {
     const float4* cubes;
     const float4* planes;
     int n_cubes, n_planes;
+    // triangle mesh + flat BVH as the reference's `mesh` holds it (kernel.cu:559-1017): triangle i = 27 floats;
+    // leaf box j = 2 float4 {bounds[0], bounds[1]} with triangles box_indices[box_offsets[j] .. box_offsets[j+1]);
+    // hit id of triangle i = n_spheres + n_cubes + n_planes + i
+    const float* tris;
+    const float4* boxes;
+    const int* box_offsets;
+    const int* box_indices;
+    int n_tris, n_boxes, mesh_has_normals;
     LightP lights[MAX_LIGHTS];
 };
 
@@ -213,6 +221,77 @@ __device__ __noinline__ bool blocked_by_cube_plane(const float4* __restrict__ cu
         if (ref_cube_intersect(O, D, mk(b0.x, b0.y, b0.z), mk(b1.x, b1.y, b1.z), t)) return true;
     }
     return false;
+}
+
+// ---- triangle mesh: linear scan over the leaf boxes, exact tests, one out-of-line copy ----
+struct MeshArgs {
+    const float* tris;
+    const float4* boxes;
+    const int* offsets;
+    const int* indices;
+    int n_boxes;
+};
+// castRay's triangle loop (kernel.cu:1293-1328): runs BEFORE the spheres, so it seeds the strict '<' search
+__device__ __noinline__ void nearest_triangle(const MeshArgs m, int id_base, float Ox, float Oy, float Oz, float Dx, float Dy,
+                                              float Dz, float* best_t, int* best_id) {
+    const v3 O = mk(Ox, Oy, Oz), D = mk(Dx, Dy, Dz);
+    float nt = *best_t;
+    int id = *best_id;
+    for (int j = 0; j < m.n_boxes; j++) {
+        const float4 b0 = __ldg(&m.boxes[2 * j]), b1 = __ldg(&m.boxes[2 * j + 1]);
+        float temp;
+        if (ref_cube_intersect(O, D, mk(b0.x, b0.y, b0.z), mk(b1.x, b1.y, b1.z), temp)) {
+            const int k1 = __ldg(&m.offsets[j + 1]);
+            for (int k = __ldg(&m.offsets[j]); k < k1; k++) {
+                const int ti = __ldg(&m.indices[k]);
+                float t, u, v;
+                if (ref_tri_intersect(O, D, m.tris + 27 * (size_t)ti, t, u, v)) {
+                    if (t < nt) {
+                        nt = t;
+                        id = id_base + ti;
+                    }
+                }
+            }
+        }
+    }
+    *best_t = nt;
+    *best_id = id;
+}
+// castLightRay's triangle part for one shadow ray (kernel.cu:1475-1497): any hit blocks
+__device__ __noinline__ bool blocked_by_mesh(const MeshArgs m, float Ox, float Oy, float Oz, float Dx, float Dy, float Dz) {
+    const v3 O = mk(Ox, Oy, Oz), D = mk(Dx, Dy, Dz);
+    for (int j = 0; j < m.n_boxes; j++) {
+        const float4 b0 = __ldg(&m.boxes[2 * j]), b1 = __ldg(&m.boxes[2 * j + 1]);
+        float temp;
+        if (ref_cube_intersect(O, D, mk(b0.x, b0.y, b0.z), mk(b1.x, b1.y, b1.z), temp)) {
+            const int k1 = __ldg(&m.offsets[j + 1]);
+            for (int k = __ldg(&m.offsets[j]); k < k1; k++) {
+                float t, u, v;
+                if (ref_tri_intersect(O, D, m.tris + 27 * (size_t)__ldg(&m.indices[k]), t, u, v)) return true;
+            }
+        }
+    }
+    return false;
+}
+// triangle hit attributes (kernel.cu:1380-1394): u,v come from re-running the winning test (deterministic)
+__device__ __noinline__ void triangle_attributes(const float* __restrict__ tri, int has_normals, float Ox, float Oy, float Oz,
+                                                 float Dx, float Dy, float Dz, float nt, v3* normal, v3* new_org, float* tx,
+                                                 float* ty) {
+    const v3 O = mk(Ox, Oy, Oz), D = mk(Dx, Dy, Dz);
+    float t, nu = 0.f, nv = 0.f;
+    ref_tri_intersect(O, D, tri, t, nu, nv);
+    v3 n;
+    if (has_normals) {
+        const v3 vn0 = mk(tri[12], tri[13], tri[14]), vn1 = mk(tri[15], tri[16], tri[17]), vn2 = mk(tri[18], tri[19], tri[20]);
+        n = ref_add(ref_add(ref_scale(vn0, (1 - nu - nv)), ref_scale(vn1, nu)), ref_scale(vn2, nv));
+        ref_normalise(n);
+    } else {
+        n = mk(tri[9], tri[10], tri[11]);
+    }
+    *tx = ((1 - nu - nv) * tri[21]) + (nu * tri[23]) + (nv * tri[25]);
+    *ty = ((1 - nu - nv) * tri[22]) + (nu * tri[24]) + (nv * tri[26]);
+    *normal = n;
+    *new_org = ref_add(n, ref_add(O, ref_scale(D, nt)));  // the unit normal is ADDED to the hit point (kernel.cu:1393)
 }
 
 // ------------------------------------------------------------------------------------
@@ -548,6 +627,17 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) primary_tile_kernel(const Fram
             ax = cx * inv;
             ay = cy * inv;
             az = prm.fz * inv;
+        }
+
+        // ---- triangles first (kernel.cu:1293-1328): they seed the strict '<' search the spheres continue ----
+        if (prm.n_boxes) {
+            const MeshArgs ma = {prm.tris, prm.boxes, prm.box_offsets, prm.box_indices, prm.n_boxes};
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+                if (x_ok && ty * P + p < prm.n_rows)
+                    nearest_triangle(ma, prm.n_spheres + prm.n_cubes + prm.n_planes, O.x, O.y, O.z, D[p].x, D[p].y, D[p].z,
+                                     &best_t[p], &best_id[p]);
+            }
         }
 
         tp.begin_round();
@@ -1400,9 +1490,13 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) shadow_beam_kernel(const Frame
             const v3 D = primary_dir(prm, prm.dx_tab[x], prm.dy_tab[k]);
             const float nt = prm.hit_t[o];
             my_id = prm.hit_id[o];
-            const v3 new_org = ref_add(O0, ref_scale(D, nt));
+            v3 new_org = ref_add(O0, ref_scale(D, nt));
             float txf, tyf;
-            if (my_id >= prm.n_spheres + prm.n_cubes) {
+            if (my_id >= prm.n_spheres + prm.n_cubes + prm.n_planes) {
+                // triangle hit, kernel.cu:1380-1394
+                triangle_attributes(prm.tris + 27 * (size_t)(my_id - prm.n_spheres - prm.n_cubes - prm.n_planes),
+                                    prm.mesh_has_normals, O0.x, O0.y, O0.z, D.x, D.y, D.z, nt, &normal, &new_org, &txf, &tyf);
+            } else if (my_id >= prm.n_spheres + prm.n_cubes) {
                 // plane hit, kernel.cu:1407-1416
                 const float4 no = __ldg(&prm.planes[2 * (my_id - prm.n_spheres - prm.n_cubes) + 1]);
                 normal = mk(no.x, no.y, no.z);
@@ -1650,6 +1744,17 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) shadow_beam_kernel(const Frame
 
             }
 
+            // ---- triangles (kernel.cu:1475-1497; tested first in the reference - the result is an OR, order-free) ----
+            if (prm.n_boxes && valid) {
+                const MeshArgs ma = {prm.tris, prm.boxes, prm.box_offsets, prm.box_indices, prm.n_boxes};
+                uint32_t live = ~blocked & ALL;
+                while (live) {
+                    const int j = __ffs(live) - 1;
+                    live &= live - 1;
+                    if (blocked_by_mesh(ma, start.x, start.y, start.z, dirs[j * 3], dirs[j * 3 + 1], dirs[j * 3 + 2]))
+                        blocked |= 1u << j;
+                }
+            }
             // ---- planes, then cubes (kernel.cu:1512-1536) for the rays no sphere blocked ----
             if ((prm.n_cubes | prm.n_planes) && valid) {
                 uint32_t live = ~blocked & ALL;

@@ -67,6 +67,65 @@ class Sprite:
 
 
 @dataclass
+class Mesh:
+    """A triangle mesh WITH its flat BVH, as the reference's `mesh` holds it (kernel.cu:559-1017): the arrays the
+    reference's own OBJ loader and createBvhMesh() produce; this path consumes them, it does not rebuild them."""
+
+    tris: np.ndarray          # [n,27] float32: points[3], normal, vecNormal[3], vt[3] (kernel.cu:206-212)
+    has_normals: bool
+    box_bounds: np.ndarray    # [b,6] float32: leaf cube bounds[0], bounds[1]
+    box_offsets: np.ndarray   # [b+1] int32
+    box_indices: np.ndarray   # [sum] int32 triangle indices per leaf, in leaf order
+
+    @property
+    def n_tris(self) -> int:
+        return int(self.tris.shape[0])
+
+    @property
+    def n_boxes(self) -> int:
+        return int(self.box_bounds.shape[0])
+
+    @staticmethod
+    def from_arrays(d) -> "Mesh":
+        return Mesh(np.ascontiguousarray(d["tris"], dtype=np.float32), bool(d["has_normals"]),
+                    np.ascontiguousarray(d["box_bounds"], dtype=np.float32),
+                    np.ascontiguousarray(d["box_offsets"], dtype=np.int32),
+                    np.ascontiguousarray(d["box_indices"], dtype=np.int32))
+
+
+def write_torus_obj(path: str, centre=(5.0, 5.0, 5.0), major=2.5, minor=0.9, nu=24, nv=12) -> int:
+    """A torus as `v / vt / vn / f a/b/c` triangles - the OBJ dialect the reference's loader parses
+    (kernel.cu:594-700).  Returns the triangle count."""
+    verts, uvs, norms, faces = [], [], [], []
+    for i in range(nu):
+        a = 2 * math.pi * i / nu
+        for j in range(nv):
+            b = 2 * math.pi * j / nv
+            nx, ny, nz = math.cos(a) * math.cos(b), math.sin(b), math.sin(a) * math.cos(b)
+            verts.append((centre[0] + (major + minor * math.cos(b)) * math.cos(a), centre[1] + minor * math.sin(b),
+                          centre[2] + (major + minor * math.cos(b)) * math.sin(a)))
+            norms.append((nx, ny, nz))
+            uvs.append((i / nu, j / nv))
+    def vid(i, j):
+        return (i % nu) * nv + (j % nv) + 1
+    for i in range(nu):
+        for j in range(nv):
+            a, b, c, d = vid(i, j), vid(i + 1, j), vid(i + 1, j + 1), vid(i, j + 1)
+            faces.append((a, b, c))
+            faces.append((a, c, d))
+    with open(path, "w") as fh:
+        for v in verts:
+            fh.write("v %.6f %.6f %.6f\n" % v)
+        for t in uvs:
+            fh.write("vt %.6f %.6f\n" % t)
+        for n in norms:
+            fh.write("vn %.6f %.6f %.6f\n" % n)
+        for f in faces:
+            fh.write("f %d/%d/%d %d/%d/%d %d/%d/%d\n" % (f[0], f[0], f[0], f[1], f[1], f[1], f[2], f[2], f[2]))
+    return len(faces)
+
+
+@dataclass
 class Scene:
     spheres: np.ndarray  # [n,4] float32: cx,cy,cz, radius MEMBER (ctor r*r, kernel.cu:287)
     lights: np.ndarray  # [m,7] float32
@@ -80,6 +139,7 @@ class Scene:
     # "next" primitives; the reference ships cube_count = plane_count = 0 (kernel.cu:1231)
     cubes: np.ndarray = field(default_factory=lambda: np.zeros((0, 6), dtype=np.float32))   # [n,6] ctor args c1.xyz, c2.xyz
     planes: np.ndarray = field(default_factory=lambda: np.zeros((0, 6), dtype=np.float32))  # [n,6] pos.xyz, normal.xyz
+    mesh: "Mesh | None" = None   # triangle mesh + flat BVH
 
     @property
     def n_spheres(self) -> int:

@@ -23,6 +23,22 @@ def _prims(n, seed, frame, n_cubes, cseed, plane=True):
     return sc, scene.orbit_camera(sc, frame)
 
 
+def torus_mesh():
+    import os
+    import numpy as np
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mesh_torus.npz"))
+    return scene.Mesh.from_arrays(d)
+
+
+def _mesh(n, seed, frame, cubes=0):
+    sc = scene.reference_scene(n, seed)
+    if cubes:
+        sc = scene.with_cubes_and_plane(sc, cubes, 5)
+    sc.mesh = torus_mesh()
+    cam = scene.reference_camera() if frame is None else scene.orbit_camera(sc, frame)
+    return sc, cam
+
+
 def _refprims():
     sc = scene.with_cubes_and_plane(scene.reference_scene(64, 1), 8, 1, reference_formula=True)
     return sc, scene.reference_camera()
@@ -47,6 +63,11 @@ SMALL = [
     ("S64_cubes_plane_f120_96x54", lambda: _prims(64, 2, 120, 12, 5), 96, 54, {}),
     ("R64_refcubes_plane_128x96", lambda: _refprims(), 128, 96, {}),
     ("cubes_only_plane_96x72", lambda: _prims(0, 1, 10, 5, 9), 96, 72, {}),
+    # triangle mesh: a torus loaded by the reference's own OBJ loader / BVH builder (fixture)
+    ("R64_torus_refcam_160x120", lambda: _mesh(64, 1, None), 160, 120, {}),
+    ("R64_torus_orbit70_128x96", lambda: _mesh(64, 1, 70), 128, 96, {}),
+    ("R16_cubes_plane_torus_128x96", lambda: _mesh(16, 3, 30, cubes=4), 128, 96, {}),
+    ("torus_only_96x72", lambda: _mesh(0, 1, 100), 96, 72, {}),
 ]
 
 

@@ -24,6 +24,16 @@ import oraclelib  # noqa: E402
 def main():
     ref = oraclelib.load("ref")
     assert ref.kind == "reference"
+    # triangle mesh fixture: a torus OBJ run through the reference's OWN loader + BVH builder
+    import tempfile
+    import rte_b200
+    scn = rte_b200.pkg.scene
+    with tempfile.TemporaryDirectory() as td:
+        obj = os.path.join(td, "torus.obj")
+        scn.write_torus_obj(obj)
+        arr = ref.build_mesh(obj)
+    np.savez_compressed(os.path.join(HERE, "mesh_torus.npz"), **arr)
+    print("mesh_torus", arr["tris"].shape, "boxes", arr["box_bounds"].shape[0])
     for name, make, W, H, kw in cases.SMALL:
         sc, cam = make()
         out = ref.render(sc, cam, W, H, **kw)

@@ -32,6 +32,8 @@ class OracleFrame(C.Structure):
         ("sky_w", C.c_int32), ("sky_h", C.c_int32), ("sky_r", _fp), ("sky_g", _fp), ("sky_b", _fp),
         ("sky_size", C.c_float),
         ("n_cubes", C.c_int32), ("cubes", _fp), ("n_planes", C.c_int32), ("planes", _fp),
+        ("n_tris", C.c_int32), ("tris", _fp), ("mesh_has_normals", C.c_int32), ("n_boxes", C.c_int32),
+        ("box_bounds", _fp), ("box_offsets", C.POINTER(C.c_int32)), ("box_indices", C.POINTER(C.c_int32)),
     ]
 
 
@@ -86,6 +88,13 @@ class Oracle:
         planes = np.ascontiguousarray(getattr(scene, "planes", np.zeros((0, 6), np.float32)), dtype=np.float32)
         f.n_cubes, f.cubes = cubes.shape[0], (_ptr(cubes.reshape(-1)) if cubes.size else None)
         f.n_planes, f.planes = planes.shape[0], (_ptr(planes.reshape(-1)) if planes.size else None)
+        mesh = getattr(scene, "mesh", None)
+        if mesh is not None and mesh.n_tris > 0:
+            _ip = C.POINTER(C.c_int32)
+            f.n_tris, f.tris, f.mesh_has_normals = mesh.n_tris, _ptr(mesh.tris.reshape(-1)), int(mesh.has_normals)
+            f.n_boxes, f.box_bounds = mesh.n_boxes, _ptr(mesh.box_bounds.reshape(-1))
+            f.box_offsets = mesh.box_offsets.ctypes.data_as(_ip)
+            f.box_indices = mesh.box_indices.ctypes.data_as(_ip)
         pixels = np.zeros((rows, width), dtype=np.uint32)
         ids = np.zeros((rows, width), dtype=np.int32) if want_ids else None
         tt = np.zeros((rows, width), dtype=np.float32) if want_t else None
@@ -97,6 +106,25 @@ class Oracle:
         if rc != 0:
             raise RuntimeError(f"oracle_render failed rc={rc}")
         return {"pixels": pixels, "ids": ids, "t": tt, "counts": counts}
+
+    def build_mesh(self, obj_path: str, cap_tris=1 << 20, cap_boxes=4096):
+        """_ref only: the reference's own OBJ loader + BVH builder; returns dict of flat arrays"""
+        tris = np.zeros((cap_tris, 27), dtype=np.float32)
+        bounds = np.zeros((cap_boxes, 6), dtype=np.float32)
+        offs = np.zeros(cap_boxes + 1, dtype=np.int32)
+        idx = np.zeros(cap_tris * 2, dtype=np.int32)
+        nt, hn, nb = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        _ip = C.POINTER(C.c_int32)
+        self.lib.oracle_ref_build_mesh.restype = C.c_int
+        self.lib.oracle_ref_build_mesh.argtypes = [C.c_char_p, _fp, C.c_int32, _ip, _ip, _fp, _ip, C.c_int32, _ip, _ip, C.c_int32]
+        rc = self.lib.oracle_ref_build_mesh(obj_path.encode(), _ptr(tris.reshape(-1)), cap_tris, C.byref(nt), C.byref(hn),
+                                            _ptr(bounds.reshape(-1)), offs.ctypes.data_as(_ip), cap_boxes, C.byref(nb),
+                                            idx.ctypes.data_as(_ip), idx.size)
+        if rc != 0:
+            raise RuntimeError(f"oracle_ref_build_mesh rc={rc}")
+        n, b = nt.value, nb.value
+        return dict(tris=tris[:n].copy(), has_normals=bool(hn.value), box_bounds=bounds[:b].copy(),
+                    box_offsets=offs[: b + 1].copy(), box_indices=idx[: offs[b]].copy())
 
     def sphere_intersect(self, org, direction, centre, radius_member):
         o = (C.c_float * 3)(*org)
