@@ -54,6 +54,44 @@ bool load_ppm(const std::string& file, int& w, int& h, std::vector<unsigned char
     fclose(f);
     return ok;
 }
+// uncompressed 24-bit BMP (bottom-up or top-down), the simplest "real image file" a Windows tool chain writes
+bool load_bmp(const std::string& file, int& w, int& h, std::vector<unsigned char>& rgb) {
+    FILE* f = fopen(file.c_str(), "rb");
+    if (!f) return false;
+    unsigned char hdr[54];
+    bool ok = fread(hdr, 1, 54, f) == 54 && hdr[0] == 'B' && hdr[1] == 'M';
+    auto u32 = [&](int o) { return (unsigned)hdr[o] | ((unsigned)hdr[o + 1] << 8) | ((unsigned)hdr[o + 2] << 16) | ((unsigned)hdr[o + 3] << 24); };
+    int bw = 0, bh = 0;
+    unsigned off = 0;
+    if (ok) {
+        off = u32(10);
+        bw = (int)u32(18);
+        bh = (int)u32(22);
+        const unsigned bpp = (unsigned)hdr[28] | ((unsigned)hdr[29] << 8), comp = u32(30);
+        ok = bpp == 24 && comp == 0 && bw > 0 && bh != 0;
+    }
+    if (ok) {
+        const bool bottom_up = bh > 0;
+        w = bw;
+        h = bottom_up ? bh : -bh;
+        const size_t stride = ((size_t)w * 3 + 3) & ~(size_t)3;
+        std::vector<unsigned char> row(stride);
+        rgb.resize((size_t)w * h * 3);
+        ok = fseek(f, (long)off, SEEK_SET) == 0;
+        for (int y = 0; ok && y < h; y++) {
+            ok = fread(row.data(), 1, stride, f) == stride;
+            const int dst = bottom_up ? h - 1 - y : y;  // plane row 0 = top of the image (cv::imread order)
+            for (int x = 0; ok && x < w; x++) {
+                unsigned char* p = &rgb[((size_t)dst * w + x) * 3];
+                p[0] = row[3 * x + 2];  // BMP stores B,G,R like cv::Vec3b (Sprite.cpp:44-46 reads r = pixel[2])
+                p[1] = row[3 * x + 1];
+                p[2] = row[3 * x + 0];
+            }
+        }
+    }
+    fclose(f);
+    return ok;
+}
 void procedural(const std::string& spec, int& w, int& h, std::vector<unsigned char>& rgb) {
     char kind[32] = {0};
     int a = 0, b = 0, c = 0;
@@ -97,7 +135,7 @@ void procedural(const std::string& spec, int& w, int& h, std::vector<unsigned ch
 sprite::sprite(std::string file) {
     std::vector<unsigned char> rgb;
     int w = 0, h = 0;
-    if (file.rfind("proc:", 0) == 0 || !load_ppm(file, w, h, rgb)) procedural(file, w, h, rgb);
+    if (file.rfind("proc:", 0) == 0 || !(load_ppm(file, w, h, rgb) || load_bmp(file, w, h, rgb))) procedural(file, w, h, rgb);
     width = w;
     height = h;
     std::vector<float> r((size_t)w * h), g((size_t)w * h), b((size_t)w * h);
@@ -114,6 +152,21 @@ sprite::~sprite() {
     delete rBuff;
     delete gBuff;
     delete bBuff;
+}
+// C hook for tests: loads `file` through the sprite constructor and copies the planes out
+extern "C" int ore_host_sprite_load(const char* file, int* w, int* h, float* r, float* g, float* b, int cap) {
+    sprite* s = new sprite(std::string(file));
+    *w = s->width;
+    *h = s->height;
+    const int n = s->width * s->height;
+    int rc = n <= cap ? 0 : 1;
+    if (!rc) {
+        memcpy(r, s->rBuff->data, sizeof(float) * n);
+        memcpy(g, s->gBuff->data, sizeof(float) * n);
+        memcpy(b, s->bBuff->data, sizeof(float) * n);
+    }
+    delete s;
+    return rc;
 }
 int sprite::getBytes() { return (int)sizeof(float) * width * height * 3; }
 int sprite::getWidth() { return this->width - 1; }

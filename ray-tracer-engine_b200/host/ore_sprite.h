@@ -17,7 +17,7 @@ public:
 
 class sprite : public memManager {
 public:
-    // `file` is a binary PPM (P6) path, or a procedural source understood by the headless harness:
+    // `file` is a binary PPM (P6) or an uncompressed 24-bit BMP path, or a procedural source:
     //   "proc:smooth:<w>:<h>:<seed>"  low-frequency sinusoid, "proc:checker:<w>:<h>:<cells>"
     // (the reference decodes image files with OpenCV, Sprite.cpp:30; OpenCV is out of scope here)
     sprite(std::string file);

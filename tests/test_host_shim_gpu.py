@@ -39,3 +39,33 @@ def test_headless_harness_matches_the_python_binding(renderer, pkg, tmp_path):
     same = np.count_nonzero(got == want) / want.size
     assert same >= 0.999, f"only {same:.5f} of the harness frame equals the binding's frame"
     assert info["checksum"] == int(got.astype(np.uint64).sum())
+
+
+def test_sprite_loads_ppm_and_bmp_into_the_reference_plane_format(tmp_path):
+    """sprite(file): planar float r,g,b = byte/255, row-major from the top row (Sprite.cpp:28-52), no OpenCV"""
+    import ctypes as C
+    import struct
+
+    subprocess.check_call(["make", "-s", "-C", HOST])
+    lib = C.CDLL(os.path.join(HOST, "libore_host.so"))
+    fp = C.POINTER(C.c_float)
+    lib.ore_host_sprite_load.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), fp, fp, fp, C.c_int]
+    rng = np.random.default_rng(3)
+    w, h = 37, 21                                    # odd width: BMP rows are padded to 4 bytes
+    img = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)      # R,G,B, row 0 = top
+    ppm = tmp_path / "t.ppm"
+    ppm.write_bytes(b"P6\n# comment\n%d %d\n255\n" % (w, h) + img.tobytes())
+    stride = (w * 3 + 3) & ~3
+    rows = b"".join(img[y, :, ::-1].tobytes() + b"\0" * (stride - w * 3) for y in range(h - 1, -1, -1))  # bottom-up BGR
+    bmp = tmp_path / "t.bmp"
+    bmp.write_bytes(b"BM" + struct.pack("<IHHI", 54 + len(rows), 0, 0, 54) +
+                    struct.pack("<IiiHHIIiiII", 40, w, h, 1, 24, 0, len(rows), 2835, 2835, 0, 0) + rows)
+    want = [np.ascontiguousarray((img[:, :, c].astype(np.float32) / np.float32(255)).reshape(-1)) for c in range(3)]
+    for path in (ppm, bmp):
+        ww, hh = C.c_int(0), C.c_int(0)
+        planes = [np.zeros(w * h, dtype=np.float32) for _ in range(3)]
+        rc = lib.ore_host_sprite_load(str(path).encode(), C.byref(ww), C.byref(hh),
+                                      *[p.ctypes.data_as(fp) for p in planes], w * h)
+        assert rc == 0 and (ww.value, hh.value) == (w, h), path
+        for got, exp in zip(planes, want):
+            assert np.array_equal(got, exp), path
