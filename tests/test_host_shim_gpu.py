@@ -47,7 +47,8 @@ def test_sprite_loads_ppm_and_bmp_into_the_reference_plane_format(tmp_path):
     import struct
 
     subprocess.check_call(["make", "-s", "-C", HOST])
-    lib = C.CDLL(os.path.join(HOST, "libore_host.so"))
+    # the shim leaves the window callbacks (getScreenWidth, ...) to the window layer: bind lazily
+    lib = C.CDLL(os.path.join(HOST, "libore_host.so"), mode=os.RTLD_LAZY)
     fp = C.POINTER(C.c_float)
     lib.ore_host_sprite_load.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), fp, fp, fp, C.c_int]
     rng = np.random.default_rng(3)
