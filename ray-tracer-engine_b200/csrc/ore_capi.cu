@@ -62,6 +62,8 @@ struct ore_context {
     int n_cubes = 0, n_planes = 0;
     float* tris = nullptr;     // 27 floats per triangle
     float4* boxes = nullptr;   // 2 float4 per leaf box
+    float4* box_sph = nullptr; // bounding sphere per leaf box (cone filters)
+    float4* box_cone = nullptr;  // per-frame tile-cone record per leaf box
     int* box_offsets = nullptr;
     int* box_indices = nullptr;
     int n_tris = 0, n_boxes = 0, mesh_has_normals = 0;
@@ -191,7 +193,7 @@ extern "C" int ore_destroy(ore_context* ctx) {
     void* dev[] = {ctx->sph_exact, ctx->sph_prim, ctx->sph_cone, ctx->sph_shad, ctx->tex[0], ctx->tex[1], ctx->tex[2],
                    ctx->sky[0],    ctx->sky[1],   ctx->sky[2],   ctx->dx_tab, ctx->dy_tab, ctx->hit_id,
                    ctx->hit_t,     ctx->hit_list, ctx->pixels,   ctx->counters, ctx->cubes,   ctx->planes,   ctx->tris,
-                   ctx->boxes,     ctx->box_offsets, ctx->box_indices};
+                   ctx->boxes,     ctx->box_offsets, ctx->box_indices, ctx->box_sph, ctx->box_cone};
     for (void* p : dev)
         if (p) cudaFree(p);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -317,13 +319,15 @@ extern "C" int ore_set_mesh(ore_context* ctx, const float* tris27, int32_t n_tri
     if (n_tris > 0 && n_boxes > 0 && (!tris27 || !box_bounds6 || !box_offsets || !box_indices))
         return fail(ctx, ORE_ERR_INVALID, "ore_set_mesh: null array");
     ORE_CUDA(ctx, cudaSetDevice(ctx->device));
-    void* old[] = {ctx->tris, ctx->boxes, ctx->box_offsets, ctx->box_indices};
+    void* old[] = {ctx->tris, ctx->boxes, ctx->box_offsets, ctx->box_indices, ctx->box_sph, ctx->box_cone};
     for (void* p : old)
         if (p) ORE_CUDA(ctx, cudaFree(p));
     ctx->tris = nullptr;
     ctx->boxes = nullptr;
     ctx->box_offsets = nullptr;
     ctx->box_indices = nullptr;
+    ctx->box_sph = nullptr;
+    ctx->box_cone = nullptr;
     ctx->n_tris = ctx->n_boxes = ctx->mesh_has_normals = 0;
     if (n_tris == 0 || n_boxes == 0) return ORE_OK;
     const int n_idx = box_offsets[n_boxes];
@@ -335,14 +339,23 @@ extern "C" int ore_set_mesh(ore_context* ctx, const float* tris27, int32_t n_tri
     const size_t tb = (size_t)n_tris * 27 * sizeof(float), bb = (size_t)n_boxes * 2 * sizeof(float4);
     const size_t ob = (size_t)(n_boxes + 1) * sizeof(int), ib = (size_t)(n_idx > 0 ? n_idx : 1) * sizeof(int);
     int rc;
-    if ((rc = ensure_pinned(ctx, tb + bb + ob + ib))) return rc;
+    const size_t sb = (size_t)n_boxes * sizeof(float4);
+    if ((rc = ensure_pinned(ctx, tb + bb + ob + ib + sb))) return rc;
     char* h = (char*)ctx->pinned;
     memcpy(h, tris27, tb);
     float4* hb = (float4*)(h + tb);
+    float4* hs = (float4*)(h + tb + bb + ob + ib);
     for (int j = 0; j < n_boxes; j++) {
         const float* b = box_bounds6 + 6 * (size_t)j;
         hb[2 * j] = make_float4(b[0], b[1], b[2], 0.f);
         hb[2 * j + 1] = make_float4(b[3], b[4], b[5], 0.f);
+        // bounding sphere for the conservative cone filters: centre, half diagonal + 0.1 % + a little absolute slack
+        // (the float slab test can accept a ray that misses the true box by rounding)
+        const double cx = 0.5 * ((double)b[0] + b[3]), cy = 0.5 * ((double)b[1] + b[4]), cz = 0.5 * ((double)b[2] + b[5]);
+        const double dx = (double)b[3] - b[0], dy = (double)b[4] - b[1], dz = (double)b[5] - b[2];
+        const double rad = 0.5 * sqrt(dx * dx + dy * dy + dz * dz);
+        const double mag = fabs(cx) + fabs(cy) + fabs(cz) + rad;
+        hs[j] = make_float4((float)cx, (float)cy, (float)cz, (float)(rad * 1.001 + 1e-5 * mag + 1e-6));
     }
     memcpy(h + tb + bb, box_offsets, ob);
     memcpy(h + tb + bb + ob, box_indices, (size_t)n_idx * sizeof(int));
@@ -350,6 +363,9 @@ extern "C" int ore_set_mesh(ore_context* ctx, const float* tris27, int32_t n_tri
     ORE_CUDA(ctx, cudaMalloc((void**)&ctx->boxes, bb));
     ORE_CUDA(ctx, cudaMalloc((void**)&ctx->box_offsets, ob));
     ORE_CUDA(ctx, cudaMalloc((void**)&ctx->box_indices, ib));
+    ORE_CUDA(ctx, cudaMalloc((void**)&ctx->box_sph, sb));
+    ORE_CUDA(ctx, cudaMalloc((void**)&ctx->box_cone, sb));
+    ORE_CUDA(ctx, cudaMemcpyAsync(ctx->box_sph, hs, sb, cudaMemcpyHostToDevice, ctx->stream));
     ORE_CUDA(ctx, cudaMemcpyAsync(ctx->tris, h, tb, cudaMemcpyHostToDevice, ctx->stream));
     ORE_CUDA(ctx, cudaMemcpyAsync(ctx->boxes, h + tb, bb, cudaMemcpyHostToDevice, ctx->stream));
     ORE_CUDA(ctx, cudaMemcpyAsync(ctx->box_offsets, h + tb + bb, ob, cudaMemcpyHostToDevice, ctx->stream));
@@ -567,6 +583,8 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
     prm.boxes = ctx->boxes;
     prm.box_offsets = ctx->box_offsets;
     prm.box_indices = ctx->box_indices;
+    prm.box_sph = ctx->box_sph;
+    prm.box_cone = ctx->box_cone;
     prm.n_tris = ctx->n_tris;
     prm.n_boxes = ctx->n_boxes;
     prm.mesh_has_normals = ctx->mesh_has_normals;
@@ -581,6 +599,7 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
     {
         int m = W > n_rows ? W : n_rows;
         if (ctx->n_spheres_pad > m) m = ctx->n_spheres_pad;
+        if (ctx->n_boxes > m) m = ctx->n_boxes;
         if (m < CNT_SLOTS) m = CNT_SLOTS;
         prep_frame_kernel<<<(m + 255) / 256, 256, 0, stream>>>(prm);
         ORE_CUDA(ctx, cudaGetLastError());

@@ -95,6 +95,8 @@ struct FrameParams {
     // hit id of triangle i = n_spheres + n_cubes + n_planes + i
     const float* tris;
     const float4* boxes;
+    const float4* box_sph;    // bounding sphere of each leaf box (centre, radius incl. margin) for the cone filters
+    float4* box_cone;         // per-frame tile-cone record of each leaf box (camera frame), like sph_cone
     const int* box_offsets;
     const int* box_indices;
     int n_tris, n_boxes, mesh_has_normals;
@@ -231,47 +233,71 @@ struct MeshArgs {
     const int* indices;
     int n_boxes;
 };
-// castRay's triangle loop (kernel.cu:1293-1328): runs BEFORE the spheres, so it seeds the strict '<' search
-__device__ __noinline__ void nearest_triangle(const MeshArgs m, int id_base, float Ox, float Oy, float Oz, float Dx, float Dy,
-                                              float Dz, float* best_t, int* best_id) {
+// castRay's triangle loop (kernel.cu:1293-1328) for ONE leaf box: exact slab test, then exact triangle tests in leaf
+// order, continuing the strict '<' search.  The caller visits the leaves in ascending order (all of them in the
+// reference; here those whose bounding sphere the tile cone can touch - a leaf the ray misses contributes nothing).
+__device__ __noinline__ void nearest_in_leaf(const MeshArgs m, int j, int id_base, float Ox, float Oy, float Oz, float Dx,
+                                             float Dy, float Dz, float* best_t, int* best_id) {
     const v3 O = mk(Ox, Oy, Oz), D = mk(Dx, Dy, Dz);
+    const float4 b0 = __ldg(&m.boxes[2 * j]), b1 = __ldg(&m.boxes[2 * j + 1]);
+    float temp;
+    if (!ref_cube_intersect(O, D, mk(b0.x, b0.y, b0.z), mk(b1.x, b1.y, b1.z), temp)) return;
     float nt = *best_t;
     int id = *best_id;
-    for (int j = 0; j < m.n_boxes; j++) {
-        const float4 b0 = __ldg(&m.boxes[2 * j]), b1 = __ldg(&m.boxes[2 * j + 1]);
-        float temp;
-        if (ref_cube_intersect(O, D, mk(b0.x, b0.y, b0.z), mk(b1.x, b1.y, b1.z), temp)) {
-            const int k1 = __ldg(&m.offsets[j + 1]);
-            for (int k = __ldg(&m.offsets[j]); k < k1; k++) {
-                const int ti = __ldg(&m.indices[k]);
-                float t, u, v;
-                if (ref_tri_intersect(O, D, m.tris + 27 * (size_t)ti, t, u, v)) {
-                    if (t < nt) {
-                        nt = t;
-                        id = id_base + ti;
-                    }
-                }
+    const int k1 = __ldg(&m.offsets[j + 1]);
+    for (int k = __ldg(&m.offsets[j]); k < k1; k++) {
+        const int ti = __ldg(&m.indices[k]);
+        float t, u, v;
+        if (ref_tri_intersect(O, D, m.tris + 27 * (size_t)ti, t, u, v)) {
+            if (t < nt) {
+                nt = t;
+                id = id_base + ti;
             }
         }
     }
     *best_t = nt;
     *best_id = id;
 }
-// castLightRay's triangle part for one shadow ray (kernel.cu:1475-1497): any hit blocks
-__device__ __noinline__ bool blocked_by_mesh(const MeshArgs m, float Ox, float Oy, float Oz, float Dx, float Dy, float Dz) {
-    const v3 O = mk(Ox, Oy, Oz), D = mk(Dx, Dy, Dz);
-    for (int j = 0; j < m.n_boxes; j++) {
+// castLightRay's triangle part (kernel.cu:1475-1497) for the live rays `live` (bits 0..9) of ONE light: a leaf is
+// skipped when the light's cone (A, ca, sa; use_cone) cannot touch its bounding sphere; otherwise every live ray
+// runs the exact slab test and the exact triangle tests.  Returns the rays found blocked.
+__device__ __noinline__ uint32_t mesh_blocks_light(const MeshArgs m, const float4* __restrict__ box_sph, float Ox, float Oy,
+                                                   float Oz, float Ax, float Ay, float Az, float ca, float sa, bool use_cone,
+                                                   const float* __restrict__ dirs /* [10][3] */, uint32_t live) {
+    const v3 O = mk(Ox, Oy, Oz);
+    uint32_t hit = 0;
+    for (int j = 0; j < m.n_boxes && live; j++) {
+        if (use_cone) {
+            const float4 q = __ldg(&box_sph[j]);
+            const float lx = Ox - q.x, ly = Oy - q.y, lz = Oz - q.z;
+            const float LL = fmaf(lz, lz, fmaf(ly, ly, lx * lx));
+            const float Cm = fmaf(LL, 1.0f - ORE_KAPPA_SHADOW, -(q.w * q.w));
+            if (Cm > 1e-20f) {
+                const float sv = Cm * rsqrt_approx(Cm);
+                const float T = fmaf(ca, sv, -(sa * q.w));
+                if (!(fmaf(Ax, lx, fmaf(Ay, ly, fmaf(Az, lz, T))) < 0.f)) continue;  // cone misses the leaf
+            }
+        }
         const float4 b0 = __ldg(&m.boxes[2 * j]), b1 = __ldg(&m.boxes[2 * j + 1]);
-        float temp;
-        if (ref_cube_intersect(O, D, mk(b0.x, b0.y, b0.z), mk(b1.x, b1.y, b1.z), temp)) {
-            const int k1 = __ldg(&m.offsets[j + 1]);
-            for (int k = __ldg(&m.offsets[j]); k < k1; k++) {
+        const int k0 = __ldg(&m.offsets[j]), k1 = __ldg(&m.offsets[j + 1]);
+        uint32_t todo = live;
+        while (todo) {
+            const int r = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const v3 D = mk(dirs[r * 3], dirs[r * 3 + 1], dirs[r * 3 + 2]);
+            float temp;
+            if (!ref_cube_intersect(O, D, mk(b0.x, b0.y, b0.z), mk(b1.x, b1.y, b1.z), temp)) continue;
+            for (int k = k0; k < k1; k++) {
                 float t, u, v;
-                if (ref_tri_intersect(O, D, m.tris + 27 * (size_t)__ldg(&m.indices[k]), t, u, v)) return true;
+                if (ref_tri_intersect(O, D, m.tris + 27 * (size_t)__ldg(&m.indices[k]), t, u, v)) {
+                    hit |= 1u << r;
+                    live &= ~(1u << r);
+                    break;
+                }
             }
         }
     }
-    return false;
+    return hit;
 }
 // triangle hit attributes (kernel.cu:1380-1394): u,v come from re-running the winning test (deterministic)
 __device__ __noinline__ void triangle_attributes(const float* __restrict__ tri, int has_normals, float Ox, float Oy, float Oz,
@@ -341,6 +367,24 @@ __global__ void prep_frame_kernel(const FrameParams prm) {
         }
         prm.sph_prim[i] = out;
         prm.sph_cone[i] = cone;
+    }
+    if (i < prm.n_boxes) {
+        // tile-cone record of leaf box i from its bounding sphere (same formula as for the spheres)
+        const float4 q = prm.box_sph[i];
+        const double Lx = (double)prm.Ox - q.x, Ly = (double)prm.Oy - q.y, Lz = (double)prm.Oz - q.z;
+        const double LL = Lx * Lx + Ly * Ly + Lz * Lz;
+        const double Cm = LL * (1.0 - ORE_KAPPA_PRIMARY) - (double)q.w * q.w * (1.0 + ORE_KAPPA_PRIMARY);
+        float4 rec = make_float4(0.f, 0.f, 0.f, -ORE_BIG);  // eye in/near the leaf's sphere: always a candidate
+        if (Cm > 1e-9 * LL && Cm > 1e-30) {
+            const double sv = sqrt(Cm), Rpp = sqrt(LL - Cm);
+            const double cp = prm.cp, sp = prm.sp, cy = prm.cy, sy = prm.sy;
+            const double Mx = cy * Lx - sy * Lz;
+            const double My = sp * sy * Lx + cp * Ly + sp * cy * Lz;
+            const double Mz = cp * sy * Lx - sp * Ly + cp * cy * Lz;
+            const double Wd = (double)prm.tile_ca * sv - (double)prm.tile_sa * Rpp;
+            rec = make_float4((float)Mx, (float)My, (float)Mz, (float)(Wd - 4e-6 * sqrt(LL) - 1e-30));
+        }
+        prm.box_cone[i] = rec;
     }
 }
 
@@ -629,14 +673,29 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) primary_tile_kernel(const Fram
             az = prm.fz * inv;
         }
 
-        // ---- triangles first (kernel.cu:1293-1328): they seed the strict '<' search the spheres continue ----
+        // ---- triangles first (kernel.cu:1293-1328): they seed the strict '<' search the spheres continue.
+        //      Lane i tests leaf box s0+i (its bounding sphere) against the tile cone; surviving leaves, in
+        //      ascending order, get the exact slab + triangle tests per pixel. ----
         if (prm.n_boxes) {
             const MeshArgs ma = {prm.tris, prm.boxes, prm.box_offsets, prm.box_indices, prm.n_boxes};
+            const int id_base = prm.n_spheres + prm.n_cubes + prm.n_planes;
+#pragma unroll 1
+            for (int s0 = 0; s0 < prm.n_boxes; s0 += 32) {
+                bool cand = false;
+                if (s0 + lane < prm.n_boxes) {
+                    const float4 rec = __ldg(&prm.box_cone[s0 + lane]);
+                    cand = EXH || fmaf(ax, rec.x, fmaf(ay, rec.y, fmaf(az, rec.z, rec.w))) <= 0.f;
+                }
+                uint32_t mask = __ballot_sync(0xffffffffu, cand && tile_ok);
+                while (mask) {
+                    const int i = __ffs(mask) - 1;
+                    mask &= mask - 1;
 #pragma unroll
-            for (int p = 0; p < P; p++) {
-                if (x_ok && ty * P + p < prm.n_rows)
-                    nearest_triangle(ma, prm.n_spheres + prm.n_cubes + prm.n_planes, O.x, O.y, O.z, D[p].x, D[p].y, D[p].z,
-                                     &best_t[p], &best_id[p]);
+                    for (int p = 0; p < P; p++) {
+                        if (x_ok && ty * P + p < prm.n_rows)
+                            nearest_in_leaf(ma, s0 + i, id_base, O.x, O.y, O.z, D[p].x, D[p].y, D[p].z, &best_t[p], &best_id[p]);
+                    }
+                }
             }
         }
 
@@ -1744,15 +1803,19 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) shadow_beam_kernel(const Frame
 
             }
 
-            // ---- triangles (kernel.cu:1475-1497; tested first in the reference - the result is an OR, order-free) ----
+            // ---- triangles (kernel.cu:1475-1497; tested first in the reference - the result is an OR, order-free):
+            //      per light, leaves outside the light's cone are skipped ----
             if (prm.n_boxes && valid) {
                 const MeshArgs ma = {prm.tris, prm.boxes, prm.box_offsets, prm.box_indices, prm.n_boxes};
-                uint32_t live = ~blocked & ALL;
-                while (live) {
-                    const int j = __ffs(live) - 1;
-                    live &= live - 1;
-                    if (blocked_by_mesh(ma, start.x, start.y, start.z, dirs[j * 3], dirs[j * 3 + 1], dirs[j * 3 + 2]))
-                        blocked |= 1u << j;
+#pragma unroll
+                for (int l = 0; l < NL; l++) {
+                    const uint32_t live = (~blocked >> (10 * l)) & 0x3ffu;
+                    if (live) {
+                        const bool use_cone = !EXH && !force && ca[l] > 0.f;
+                        const uint32_t hit = mesh_blocks_light(ma, prm.box_sph, start.x, start.y, start.z, Ax[l], Ay[l], Az[l],
+                                                               ca[l], sa[l], use_cone, dirs + 30 * l, live);
+                        blocked |= hit << (10 * l);
+                    }
                 }
             }
             // ---- planes, then cubes (kernel.cu:1512-1536) for the rays no sphere blocked ----
