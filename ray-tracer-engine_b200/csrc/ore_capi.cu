@@ -281,7 +281,13 @@ extern "C" int ore_set_cubes(ore_context* ctx, const float* c1_c2, int32_t n) {
         h[3 * i + 0] = make_float4(c[0], c[1], c[2], 0.f);  // bounds[0] = c1, kernel.cu:393
         h[3 * i + 1] = make_float4(c[3], c[4], c[5], 0.f);  // bounds[1] = c2
         // orgin = divide(add(c1, c2), 2), kernel.cu:395 (float add, float divide)
-        h[3 * i + 2] = make_float4((c[0] + c[3]) / 2, (c[1] + c[4]) / 2, (c[2] + c[5]) / 2, 0.f);
+        // .w = radius of a bounding sphere about orgin (half diagonal + margins) for the light-cone filter
+        const double dx = (double)c[3] - c[0], dy = (double)c[4] - c[1], dz = (double)c[5] - c[2];
+        const double rad = 0.5 * sqrt(dx * dx + dy * dy + dz * dz);
+        const double mag = fabs((double)c[0]) + fabs((double)c[1]) + fabs((double)c[2]) + fabs((double)c[3]) +
+                           fabs((double)c[4]) + fabs((double)c[5]);
+        h[3 * i + 2] = make_float4((c[0] + c[3]) / 2, (c[1] + c[4]) / 2, (c[2] + c[5]) / 2,
+                                   (float)(rad * 1.001 + 1e-5 * mag + 1e-6));
     }
     ORE_CUDA(ctx, cudaMalloc((void**)&ctx->cubes, (size_t)n * 3 * sizeof(float4)));
     ORE_CUDA(ctx, cudaMemcpyAsync(ctx->cubes, h, (size_t)n * 3 * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));

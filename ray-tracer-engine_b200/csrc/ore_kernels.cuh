@@ -209,20 +209,54 @@ __device__ __noinline__ void nearest_cube_plane(const float4* __restrict__ cubes
     *best_t = nt;
     *best_id = id;
 }
-// castLightRay's plane loop then cube loop for one shadow ray (kernel.cu:1512-1536): any hit blocks
-__device__ __noinline__ bool blocked_by_cube_plane(const float4* __restrict__ cubes, int nc, const float4* __restrict__ planes,
-                                                   int np, float Ox, float Oy, float Oz, float Dx, float Dy, float Dz) {
-    const v3 O = mk(Ox, Oy, Oz), D = mk(Dx, Dy, Dz);
+// castLightRay's plane loop then cube loop (kernel.cu:1512-1536) for the live rays `live` (bits 0..9) of ONE light:
+// any hit blocks.  A cube whose bounding sphere (cubes[3*i+2].xyz = orgin, .w = radius incl. margin) the light's cone
+// cannot touch is skipped.  Returns the rays found blocked.
+__device__ __noinline__ uint32_t cubes_planes_block_light(const float4* __restrict__ cubes, int nc,
+                                                          const float4* __restrict__ planes, int np, float Ox, float Oy,
+                                                          float Oz, float Ax, float Ay, float Az, float ca, float sa,
+                                                          bool use_cone, const float* __restrict__ dirs, uint32_t live) {
+    const v3 O = mk(Ox, Oy, Oz);
+    uint32_t hit = 0;
     float t;
-    for (int i = 0; i < np; i++) {
+    for (int i = 0; i < np && live; i++) {
         const float4 po = __ldg(&planes[2 * i]), no = __ldg(&planes[2 * i + 1]);
-        if (ref_plane_intersect(O, D, mk(po.x, po.y, po.z), mk(no.x, no.y, no.z), t)) return true;
+        uint32_t todo = live;
+        while (todo) {
+            const int r = __ffs(todo) - 1;
+            todo &= todo - 1;
+            if (ref_plane_intersect(O, mk(dirs[r * 3], dirs[r * 3 + 1], dirs[r * 3 + 2]), mk(po.x, po.y, po.z),
+                                    mk(no.x, no.y, no.z), t)) {
+                hit |= 1u << r;
+                live &= ~(1u << r);
+            }
+        }
     }
-    for (int i = 0; i < nc; i++) {
+    for (int i = 0; i < nc && live; i++) {
+        const float4 q = __ldg(&cubes[3 * i + 2]);
+        if (use_cone) {
+            const float lx = Ox - q.x, ly = Oy - q.y, lz = Oz - q.z;
+            const float LL = fmaf(lz, lz, fmaf(ly, ly, lx * lx));
+            const float Cm = fmaf(LL, 1.0f - ORE_KAPPA_SHADOW, -(q.w * q.w));
+            if (Cm > 1e-20f) {
+                const float sv = Cm * rsqrt_approx(Cm);
+                const float T = fmaf(ca, sv, -(sa * q.w));
+                if (!(fmaf(Ax, lx, fmaf(Ay, ly, fmaf(Az, lz, T))) < 0.f)) continue;  // cone misses the cube
+            }
+        }
         const float4 b0 = __ldg(&cubes[3 * i]), b1 = __ldg(&cubes[3 * i + 1]);
-        if (ref_cube_intersect(O, D, mk(b0.x, b0.y, b0.z), mk(b1.x, b1.y, b1.z), t)) return true;
+        uint32_t todo = live;
+        while (todo) {
+            const int r = __ffs(todo) - 1;
+            todo &= todo - 1;
+            if (ref_cube_intersect(O, mk(dirs[r * 3], dirs[r * 3 + 1], dirs[r * 3 + 2]), mk(b0.x, b0.y, b0.z),
+                                   mk(b1.x, b1.y, b1.z), t)) {
+                hit |= 1u << r;
+                live &= ~(1u << r);
+            }
+        }
     }
-    return false;
+    return hit;
 }
 
 // ---- triangle mesh: linear scan over the leaf boxes, exact tests, one out-of-line copy ----
@@ -1818,15 +1852,19 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) shadow_beam_kernel(const Frame
                     }
                 }
             }
-            // ---- planes, then cubes (kernel.cu:1512-1536) for the rays no sphere blocked ----
+            // ---- planes, then cubes (kernel.cu:1512-1536) for the rays nothing blocked yet; cubes outside a light's
+            //      cone are skipped ----
             if ((prm.n_cubes | prm.n_planes) && valid) {
-                uint32_t live = ~blocked & ALL;
-                while (live) {
-                    const int j = __ffs(live) - 1;
-                    live &= live - 1;
-                    if (blocked_by_cube_plane(prm.cubes, prm.n_cubes, prm.planes, prm.n_planes, start.x, start.y, start.z,
-                                              dirs[j * 3], dirs[j * 3 + 1], dirs[j * 3 + 2]))
-                        blocked |= 1u << j;
+#pragma unroll
+                for (int l = 0; l < NL; l++) {
+                    const uint32_t live = (~blocked >> (10 * l)) & 0x3ffu;
+                    if (live) {
+                        const bool use_cone = !EXH && !force && ca[l] > 0.f;
+                        const uint32_t hit = cubes_planes_block_light(prm.cubes, prm.n_cubes, prm.planes, prm.n_planes, start.x,
+                                                                      start.y, start.z, Ax[l], Ay[l], Az[l], ca[l], sa[l],
+                                                                      use_cone, dirs + 30 * l, live);
+                        blocked |= hit << (10 * l);
+                    }
                 }
             }
 
