@@ -2,7 +2,7 @@
 // window.h callbacks and a main() that drives onStart()/update() like wWinMain (window.cpp:57-84) does,
 // with a scripted camera orbit instead of the message pump, and writes the last frame as a PPM.
 //
-//   ore_headless [width height frames spheres out.ppm]
+//   ore_headless [width height frames spheres out.ppm mesh.obj]
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -32,6 +32,7 @@ int main(int argc, char** argv) {
     const int frames = argc > 3 ? atoi(argv[3]) : 8;
     const int spheres = argc > 4 ? atoi(argv[4]) : 64;
     const char* out = argc > 5 ? argv[5] : nullptr;
+    if (argc > 6) oreSetMeshFile(argv[6]);
     render.buffmemory.assign((size_t)render.width * render.height, 0u);
 
     oreConfigureScene(spheres, 1u, nullptr, nullptr);

@@ -15,6 +15,7 @@
 
 #include "../../include/ore_render.h"
 #include "ore_memmanager.h"
+#include "ore_mesh.h"
 #include "ore_sprite.h"
 #include "ore_window_callbacks.h"
 
@@ -30,6 +31,7 @@ int g_sphere_count = 64;                                               // the re
 unsigned g_seed = 1;                                                   // unseeded rand()
 std::string g_texture = "proc:smooth:512:512:102";
 std::string g_sky = "proc:smooth:1024:512:203";
+std::string g_obj;                                                     // loadMesh(file, ...), kernel.cu:1706
 sprite* texture = nullptr;
 sprite* skyTex = nullptr;
 unsigned int* g_pixels = nullptr;  // pinned host frame handed to setPixelBuff
@@ -47,6 +49,8 @@ void oreConfigureScene(int sphere_count, unsigned seed, const char* tex, const c
     if (tex) g_texture = tex;
     if (sky) g_sky = sky;
 }
+
+void oreSetMeshFile(const char* obj_path) { g_obj = obj_path ? obj_path : ""; }
 
 void oreSetCamera(float x, float y, float z, float yaw_deg, float pitch_deg) {
     cam.org[0] = x;
@@ -70,6 +74,14 @@ void onStart() {
         s[4 * i + 3] = r * r;
     }
     checkOre(ore_set_spheres(g_ctx, s.data(), g_sphere_count));
+    if (!g_obj.empty()) {
+        // objs->loadMesh(file, ...): mesh(file) parses the OBJ and builds the flat BVH on the host (kernel.cu:1183,
+        // 577-936); ore_set_mesh replaces mesh::allocMem (kernel.cu:1184,999-1017)
+        OreMesh m;
+        if (ore_load_obj(g_obj, m) && m.n_tris() > 0)
+            checkOre(ore_set_mesh(g_ctx, m.tris.data(), m.n_tris(), m.has_normals ? 1 : 0, m.box_bounds.data(),
+                                  m.box_offsets.data(), m.box_indices.data(), m.n_boxes()));
+    }
     texture = new sprite(g_texture);   // objs->texture = new sprite(tex), kernel.cu:1201
     skyTex = new sprite(g_sky);        // new skybox(img, 10000), kernel.cu:1700
     checkOre(ore_set_texture(g_ctx, texture->rBuff->data, texture->gBuff->data, texture->bBuff->data, texture->width,

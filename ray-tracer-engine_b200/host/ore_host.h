@@ -11,5 +11,7 @@ void update();
 void oreSetCamera(float x, float y, float z, float yaw_deg, float pitch_deg);
 // scene size / seed for the reference sphere generator (kernel.cu:1189-1191); call before onStart()
 void oreConfigureScene(int sphere_count, unsigned seed, const char* texture, const char* sky);
+// triangle mesh for onStart(): an OBJ file in the reference's dialect (kernel.cu:1706); call before onStart()
+void oreSetMeshFile(const char* obj_path);
 // release the render context (the reference never frees its globals)
 void oreShutdown();

@@ -41,6 +41,37 @@ def test_headless_harness_matches_the_python_binding(renderer, pkg, tmp_path):
     assert info["checksum"] == int(got.astype(np.uint64).sum())
 
 
+def test_headless_harness_with_an_obj_mesh(renderer, pkg, tmp_path):
+    """onStart() loading an OBJ through the shim's own loader / BVH builder == the Python binding fed with the
+    fixture the reference's loader produced"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cases
+
+    subprocess.check_call(["make", "-s", "-C", HOST])
+    obj = tmp_path / "torus.obj"
+    pkg.scene.write_torus_obj(str(obj))
+    out = tmp_path / "frame.ppm"
+    W, H, frames = 256, 192, 1
+    subprocess.run([os.path.join(HOST, "ore_headless"), str(W), str(H), str(frames), "64", str(out), str(obj)],
+                   capture_output=True, text=True, check=True)
+    data = out.read_bytes()
+    header = b"P6\n%d %d\n255\n" % (W, H)
+    rgb = np.frombuffer(data[len(header):], dtype=np.uint8).reshape(H, W, 3)[::-1]
+    got = (rgb[..., 0].astype(np.uint32) << 16) | (rgb[..., 1].astype(np.uint32) << 8) | rgb[..., 2]
+    sc = pkg.scene.reference_scene(64, 1)
+    sc.mesh = cases.torus_mesh()
+    yaw, pitch = 180.0, 15.0
+    yr, pr = math.radians(yaw), math.radians(pitch)
+    org = tuple(float(np.float32(v)) for v in (5 - 12 * math.cos(pr) * math.sin(yr), 5 + 12 * math.sin(pr),
+                                               5 - 12 * math.cos(pr) * math.cos(yr)))
+    renderer.set_scene(sc)
+    want = renderer.render(pkg.scene.Camera(org=org, yaw=yaw, pitch=pitch), W, H)
+    renderer.set_mesh(None)
+    assert np.count_nonzero(got == want) / want.size >= 0.999
+    ids, _ = renderer.hits(H, W)
+
+
 def test_sprite_loads_ppm_and_bmp_into_the_reference_plane_format(tmp_path):
     """sprite(file): planar float r,g,b = byte/255, row-major from the top row (Sprite.cpp:28-52), no OpenCV"""
     import ctypes as C
