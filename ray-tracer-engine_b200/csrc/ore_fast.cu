@@ -37,8 +37,8 @@ static cudaError_t launch(K kernel, const ore_fast::FrameParams& prm, int sm_cou
 extern "C" ORE_HIDDEN int ore_fast_primary_tile(const void* prm, int sm_count, size_t smem, long long n_batches, int exh,
                                                cudaStream_t stream) {
     const ore_fast::FrameParams& p = *static_cast<const ore_fast::FrameParams*>(prm);
-    return (int)(exh ? launch(ore_fast::primary_tile_kernel<8, true>, p, sm_count, smem, n_batches, stream)
-                     : launch(ore_fast::primary_tile_kernel<8, false>, p, sm_count, smem, n_batches, stream));
+    return (int)(exh ? launch(ore_fast::primary_tile_kernel<ore_fast::TILE_P, true>, p, sm_count, smem, n_batches, stream)
+                     : launch(ore_fast::primary_tile_kernel<ore_fast::TILE_P, false>, p, sm_count, smem, n_batches, stream));
 }
 extern "C" ORE_HIDDEN int ore_fast_shadow_beam(const void* prm, int sm_count, size_t smem, int exh, cudaStream_t stream) {
     const ore_fast::FrameParams& p = *static_cast<const ore_fast::FrameParams*>(prm);

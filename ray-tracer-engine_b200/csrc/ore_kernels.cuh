@@ -33,6 +33,14 @@ constexpr int MAX_STAGES = 4;
 #define ORE_SHADOW_SG 4
 #endif
 constexpr int SHADOW_THREADS = ORE_SHADOW_THREADS;
+// primary tile kernel: rows per 32-wide pixel tile and CTAs/SM it is bounded for
+#ifndef ORE_TILE_P
+#define ORE_TILE_P 8
+#endif
+#ifndef ORE_TILE_MIN_CTAS
+#define ORE_TILE_MIN_CTAS 2
+#endif
+constexpr int TILE_P = ORE_TILE_P;
 constexpr int SPHERE_PAD = 16;  // device sphere arrays are padded to a multiple of this
 
 // conservative filter margins (see DESIGN.md "Filter soundness")
@@ -653,7 +661,7 @@ __global__ void __launch_bounds__(CTA_THREADS) primary_kernel(const FrameParams 
 // ascending order, so the strict '<' tie rule (kernel.cu:1335) is preserved.
 // ------------------------------------------------------------------------------------
 template <int P, bool EXH>
-__global__ void __launch_bounds__(CTA_THREADS, 2) primary_tile_kernel(const FrameParams prm) {
+__global__ void __launch_bounds__(CTA_THREADS, ORE_TILE_MIN_CTAS) primary_tile_kernel(const FrameParams prm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bars[MAX_STAGES];
     __shared__ uint32_t warp_tot[CTA_WARPS];
