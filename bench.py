@@ -239,10 +239,26 @@ def main():
 
     peer = None
     gatherer = None
-    if world > 1 and args.gather == "nccl":
+    gather_mode = args.gather
+    if not (world > 1 and gather_mode == "nccl"):
+        err = None
+        try:
+            peer = pkg.multigpu.PeerFrame(r, W, H, n_buffers=max(2, args.in_flight))
+        except Exception as e:  # CUDA IPC refused (e.g. separate IPC namespaces): decided collectively below
+            err = e
+        if world > 1:
+            bad = torch.tensor([1 if err is not None else 0], dtype=torch.int32, device=f"cuda:{local}")
+            dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+            if int(bad.item()):
+                if rank == 0:
+                    print(f"bench.py: peer-mapped framebuffer unavailable ({err}); using the NCCL band gather", file=sys.stderr)
+                if peer is not None:
+                    peer.close()
+                peer, gather_mode = None, "nccl"
+        elif err is not None:
+            raise err
+    if peer is None:
         gatherer = pkg.multigpu.BandGatherer(W, H, torch.device("cuda", local))
-    else:
-        peer = pkg.multigpu.PeerFrame(r, W, H, n_buffers=max(2, args.in_flight))
 
     def barrier():
         if world > 1:
@@ -508,7 +524,7 @@ def main():
             "config": dict(config, l2=l2_note,
                            frame_overlap=(f"{NF} frames in flight per GPU (contexts/streams used round-robin)"
                                           if overlap and NF > 1 else "none"),
-                           parallelism=(f"row-bands x{world} (8-row blocks dealt round-robin), presenter = rank 0, gather = {args.gather}"
+                           parallelism=(f"row-bands x{world} (8-row blocks dealt round-robin), presenter = rank 0, gather = {gather_mode}"
                                         if world > 1 else "1 GPU"),
                            hit_pixel_fraction=hits / (W * H * args.steps),
                            tests_per_pixel={"primary": tests_primary / (W * H * args.steps),
