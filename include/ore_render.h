@@ -55,7 +55,11 @@ enum ore_flags {
     /* Use CUDA's own cosf/sinf/acosf/atan2f instead of the glibc-bit-compatible device functions of the default
      * path (csrc/ore_libm.cuh).  ~20 % faster; ids and t unchanged; pixels within 1 LSB of the default on
      * >= 99.9 % (measured 99.999 %) instead of bit-identical to the host-compiled reference. */
-    ORE_FLAG_FAST_LIBM = 16
+    ORE_FLAG_FAST_LIBM = 16,
+    /* Default shadow pass as ONE kernel (shading set-up + light directions + sweep fused) instead of the two-stage
+     * pass through a staging buffer.  Same results; slower (its hot code does not fit the SM instruction cache) but
+     * needs no staging memory.  Also used automatically when the staging buffer cannot be allocated. */
+    ORE_FLAG_FUSED_SHADOW = 32
 };
 
 typedef struct ore_context ore_context; /* opaque; owns device buffers, streams, pinned staging */

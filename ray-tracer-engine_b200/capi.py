@@ -18,6 +18,7 @@ ORE_FLAG_COUNT_REFERENCE_TESTS = 2
 ORE_FLAG_PER_RAY_SHADOW = 4
 ORE_FLAG_NO_WARP_CULL = 8
 ORE_FLAG_FAST_LIBM = 16
+ORE_FLAG_FUSED_SHADOW = 32
 
 EXPORTS = [
     "ore_create", "ore_destroy", "ore_abi_version", "ore_last_error",

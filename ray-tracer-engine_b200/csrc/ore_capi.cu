@@ -23,7 +23,10 @@ using namespace ore;
 extern "C" int ore_fast_set_tables(const float* cphi, const float* sphi, const float* bk);
 extern "C" int ore_fast_primary_tile(const void* prm, int sm_count, size_t smem, long long n_batches, int exh,
                                      cudaStream_t stream);
-extern "C" int ore_fast_shadow_beam(const void* prm, int sm_count, size_t smem, int exh, cudaStream_t stream);
+// stage: a StageArgs of identical layout, or null for the fused kernel
+extern "C" int ore_fast_shadow_beam(const void* prm, const void* stage, int sm_count, size_t smem, int exh,
+                                    cudaStream_t stream);
+extern "C" int ore_fast_shade_setup(const void* prm, const void* stage, int sm_count, cudaStream_t stream);
 
 struct ore_context {
     int device = 0;
@@ -79,6 +82,9 @@ struct ore_context {
     uint32_t* pixels = nullptr;
     size_t px_cap = 0;
     unsigned long long* counters = nullptr;
+    float* stage = nullptr;  // staging buffer between the two kernels of the default shadow pass
+    size_t stage_cap = 0;    // floats
+    size_t stage_blocks_override = 0;  // test hook (env ORE_STAGE_BLOCKS at ore_create): staging capacity in 32-item blocks
 
     // last frame
     size_t last_px = 0;
@@ -154,6 +160,10 @@ extern "C" int ore_create(ore_context** out, int device) {
         ORE_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
     }
     for (int i = 0; i < 5; i++) ORE_CUDA(ctx, cudaEventCreate(&ctx->ev[i]));
+    if (const char* e = getenv("ORE_STAGE_BLOCKS")) {
+        const long v = atol(e);
+        if (v > 0) ctx->stage_blocks_override = (size_t)v;
+    }
     ORE_CUDA(ctx, cudaMalloc((void**)&ctx->counters, CNT_SLOTS * sizeof(unsigned long long)));
     ORE_CUDA(ctx, cudaMemset(ctx->counters, 0, CNT_SLOTS * sizeof(unsigned long long)));
     // kernel.cu:1454,1462-1463: phi = (float)j/10 * 2.f * 3.1415f; cosf(phi), sinf(phi)
@@ -190,7 +200,7 @@ extern "C" int ore_destroy(ore_context* ctx) {
     }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->pixels_b) cudaFree(ctx->pixels_b);
-    void* dev[] = {ctx->sph_exact, ctx->sph_prim, ctx->sph_cone, ctx->sph_shad, ctx->tex[0], ctx->tex[1], ctx->tex[2],
+    void* dev[] = {ctx->stage, ctx->sph_exact, ctx->sph_prim, ctx->sph_cone, ctx->sph_shad, ctx->tex[0], ctx->tex[1], ctx->tex[2],
                    ctx->sky[0],    ctx->sky[1],   ctx->sky[2],   ctx->dx_tab, ctx->dy_tab, ctx->hit_id,
                    ctx->hit_t,     ctx->hit_list, ctx->pixels,   ctx->counters, ctx->cubes,   ctx->planes,   ctx->tris,
                    ctx->boxes,     ctx->box_offsets, ctx->box_indices, ctx->box_sph, ctx->box_cone};
@@ -659,14 +669,70 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
         if (warp_cull) {
             // the beam kernel stages the whole record array (resident) or reads it through L1/L2: no ring
             const size_t bsmem = prm.resident ? (size_t)ctx->n_spheres_pad * sizeof(float4) : 0;
-            if (fast_libm) {
-                ORE_CUDA(ctx, (cudaError_t)ore_fast_shadow_beam(&prm, ctx->sm_count, bsmem, exh ? 1 : 0, stream));
-            } else if (exh) {
-                if ((rc = grid_for(ctx, shadow_beam_kernel<true>, bsmem, &grid))) return rc;
-                shadow_beam_kernel<true><<<grid, CTA_THREADS, bsmem, stream>>>(prm);
+            // Two-stage pass (default): shade_setup_kernel -> staging buffer -> staged shadow_beam_kernel, in chunks
+            // of the hit list that fit the staging buffer.  The host does not know the hit count (no sync), so the
+            // chunk count comes from the pixel count; kernels of chunks past the end of the hit list exit at once.
+            StageArgs st{};
+            st.nv = 6 + 31 * ctx->n_lights;
+            const size_t n_blocks_px = (n_px + 31) / 32;
+            size_t cap_blocks = 0;
+            bool staged = !(fr->flags & ORE_FLAG_FUSED_SHADOW);
+            if (staged) {
+                size_t want_items = n_px / 4 > ((size_t)1 << 20) ? n_px / 4 : ((size_t)1 << 20);
+                if (want_items > ((size_t)16 << 20)) want_items = (size_t)16 << 20;
+                if (want_items > n_px) want_items = n_px;
+                cap_blocks = (want_items + 31) / 32;
+                if (ctx->stage_blocks_override) cap_blocks = ctx->stage_blocks_override;
+                while ((n_blocks_px + cap_blocks - 1) / cap_blocks > (size_t)MAX_STAGE_CHUNKS) cap_blocks *= 2;
+                const size_t need = cap_blocks * 32 * (size_t)st.nv;
+                if (need > ctx->stage_cap || !ctx->stage) {
+                    if (ctx->stage) ORE_CUDA(ctx, cudaFree(ctx->stage));
+                    ctx->stage = nullptr;
+                    ctx->stage_cap = 0;
+                    if (cudaMalloc((void**)&ctx->stage, need * sizeof(float)) == cudaSuccess) {
+                        ctx->stage_cap = need;
+                    } else {
+                        (void)cudaGetLastError();  // no room for the staging buffer: the fused kernel needs none
+                        ctx->stage = nullptr;
+                        staged = false;
+                    }
+                }
+            }
+            if (!staged) {
+                if (fast_libm) {
+                    ORE_CUDA(ctx, (cudaError_t)ore_fast_shadow_beam(&prm, nullptr, ctx->sm_count, bsmem, exh ? 1 : 0, stream));
+                } else if (exh) {
+                    if ((rc = grid_for(ctx, shadow_beam_kernel<true, false>, bsmem, &grid))) return rc;
+                    shadow_beam_kernel<true, false><<<grid, CTA_THREADS, bsmem, stream>>>(prm, st);
+                } else {
+                    if ((rc = grid_for(ctx, shadow_beam_kernel<false, false>, bsmem, &grid))) return rc;
+                    shadow_beam_kernel<false, false><<<grid, CTA_THREADS, bsmem, stream>>>(prm, st);
+                }
             } else {
-                if ((rc = grid_for(ctx, shadow_beam_kernel<false>, bsmem, &grid))) return rc;
-                shadow_beam_kernel<false><<<grid, CTA_THREADS, bsmem, stream>>>(prm);
+                st.buf = ctx->stage;
+                st.cap_blocks = (uint32_t)cap_blocks;
+                const int n_chunks = (int)((n_blocks_px + cap_blocks - 1) / cap_blocks);
+                int grid_a = 0, grid_b = 0;
+                if (!fast_libm) {
+                    if ((rc = grid_for(ctx, shade_setup_kernel, 0, &grid_a))) return rc;
+                    if (exh) rc = grid_for(ctx, shadow_beam_kernel<true, true>, bsmem, &grid_b);
+                    else rc = grid_for(ctx, shadow_beam_kernel<false, true>, bsmem, &grid_b);
+                    if (rc) return rc;
+                }
+                for (int c = 0; c < n_chunks; c++) {
+                    st.chunk = c;
+                    st.first_block = (uint32_t)((size_t)c * cap_blocks);
+                    if (fast_libm) {
+                        ORE_CUDA(ctx, (cudaError_t)ore_fast_shade_setup(&prm, &st, ctx->sm_count, stream));
+                        ORE_CUDA(ctx, (cudaError_t)ore_fast_shadow_beam(&prm, &st, ctx->sm_count, bsmem, exh ? 1 : 0, stream));
+                    } else {
+                        shade_setup_kernel<<<grid_a, CTA_THREADS, 0, stream>>>(prm, st);
+                        if (exh) shadow_beam_kernel<true, true><<<grid_b, CTA_THREADS, bsmem, stream>>>(prm, st);
+                        else shadow_beam_kernel<false, true><<<grid_b, CTA_THREADS, bsmem, stream>>>(prm, st);
+                    }
+                    ORE_CUDA(ctx, cudaGetLastError());
+                    ctx->last_launches += (c + 1 < n_chunks) ? 2 : 1;  // the common tail below counts one
+                }
             }
         } else if (!(fr->flags & ORE_FLAG_PER_RAY_SHADOW)) {
             if (exh) {

@@ -18,9 +18,8 @@ extern "C" ORE_HIDDEN int ore_fast_set_tables(const float* cphi, const float* sp
     return 0;
 }
 
-template <typename K>
-static cudaError_t launch(K kernel, const ore_fast::FrameParams& prm, int sm_count, size_t smem, long long max_grid,
-                          cudaStream_t stream) {
+template <typename K, typename... A>
+static cudaError_t launch(K kernel, int sm_count, size_t smem, long long max_grid, cudaStream_t stream, A... args) {
     int occ = 0;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -29,19 +28,31 @@ static cudaError_t launch(K kernel, const ore_fast::FrameParams& prm, int sm_cou
     if (occ < 1) return cudaErrorLaunchOutOfResources;
     long long grid = (long long)occ * sm_count;
     if (max_grid > 0 && grid > max_grid) grid = max_grid;
-    kernel<<<(int)grid, ore_fast::CTA_THREADS, smem, stream>>>(prm);
+    kernel<<<(int)grid, ore_fast::CTA_THREADS, smem, stream>>>(args...);
     return cudaGetLastError();
 }
 
-// prm points at a FrameParams of identical layout (same header)
+// prm / stage point at a FrameParams / StageArgs of identical layout (same header)
 extern "C" ORE_HIDDEN int ore_fast_primary_tile(const void* prm, int sm_count, size_t smem, long long n_batches, int exh,
                                                cudaStream_t stream) {
     const ore_fast::FrameParams& p = *static_cast<const ore_fast::FrameParams*>(prm);
-    return (int)(exh ? launch(ore_fast::primary_tile_kernel<ore_fast::TILE_P, true>, p, sm_count, smem, n_batches, stream)
-                     : launch(ore_fast::primary_tile_kernel<ore_fast::TILE_P, false>, p, sm_count, smem, n_batches, stream));
+    return (int)(exh ? launch(ore_fast::primary_tile_kernel<ore_fast::TILE_P, true>, sm_count, smem, n_batches, stream, p)
+                     : launch(ore_fast::primary_tile_kernel<ore_fast::TILE_P, false>, sm_count, smem, n_batches, stream, p));
 }
-extern "C" ORE_HIDDEN int ore_fast_shadow_beam(const void* prm, int sm_count, size_t smem, int exh, cudaStream_t stream) {
+extern "C" ORE_HIDDEN int ore_fast_shadow_beam(const void* prm, const void* stage, int sm_count, size_t smem, int exh,
+                                              cudaStream_t stream) {
     const ore_fast::FrameParams& p = *static_cast<const ore_fast::FrameParams*>(prm);
-    return (int)(exh ? launch(ore_fast::shadow_beam_kernel<true>, p, sm_count, smem, 0, stream)
-                     : launch(ore_fast::shadow_beam_kernel<false>, p, sm_count, smem, 0, stream));
+    if (!stage) {
+        const ore_fast::StageArgs none{};
+        return (int)(exh ? launch(ore_fast::shadow_beam_kernel<true, false>, sm_count, smem, 0, stream, p, none)
+                         : launch(ore_fast::shadow_beam_kernel<false, false>, sm_count, smem, 0, stream, p, none));
+    }
+    const ore_fast::StageArgs& st = *static_cast<const ore_fast::StageArgs*>(stage);
+    return (int)(exh ? launch(ore_fast::shadow_beam_kernel<true, true>, sm_count, smem, 0, stream, p, st)
+                     : launch(ore_fast::shadow_beam_kernel<false, true>, sm_count, smem, 0, stream, p, st));
+}
+extern "C" ORE_HIDDEN int ore_fast_shade_setup(const void* prm, const void* stage, int sm_count, cudaStream_t stream) {
+    const ore_fast::FrameParams& p = *static_cast<const ore_fast::FrameParams*>(prm);
+    const ore_fast::StageArgs& st = *static_cast<const ore_fast::StageArgs*>(stage);
+    return (int)launch(ore_fast::shade_setup_kernel, sm_count, 0, 0, stream, p, st);
 }

@@ -29,6 +29,9 @@ constexpr int MAX_STAGES = 4;
 #ifndef ORE_SHADOW_MIN_CTAS
 #define ORE_SHADOW_MIN_CTAS 2
 #endif
+#ifndef ORE_BEAM_MIN_CTAS
+#define ORE_BEAM_MIN_CTAS 3  // shadow_beam_kernel: 80 registers, 3 x 256 threads per SM
+#endif
 #ifndef ORE_SHADOW_SG
 #define ORE_SHADOW_SG 4
 #endif
@@ -57,7 +60,22 @@ enum CounterSlot {
     CNT_COUNT_CURSOR = 5,
     CNT_BEAM_L1 = 6,   // spheres passing the warp-level beam test (summed over warps and light passes)
     CNT_BEAM_L2 = 7,   // (pixel, sphere) pairs passing the per-pixel cone test
-    CNT_SLOTS = 8
+    CNT_STAGE_A0 = 8,                          // per-chunk block cursors of shade_setup_kernel
+    CNT_STAGE_B0 = CNT_STAGE_A0 + 32,          // per-chunk block cursors of the staged shadow_beam_kernel
+    CNT_SLOTS = CNT_STAGE_B0 + 32
+};
+constexpr int MAX_STAGE_CHUNKS = 32;
+
+// Staging buffer between shade_setup_kernel and the staged shadow_beam_kernel (DESIGN.md "Two-stage shadow pass"):
+// blocks of 32 hit-list items, value-major inside a block (value v of lane i at (block * nv + v) * 32 + i, so every
+// access is one coalesced 128-byte line).  Values: 0-2 start, 3-5 texel r,g,b, then per light 30 direction
+// components + a = dot(normal, toL).
+struct StageArgs {
+    float* buf;
+    uint32_t first_block;  // hit-list block (32 items) held by stage block 0 of this chunk
+    uint32_t cap_blocks;   // stage capacity in blocks
+    int chunk;             // cursor slot
+    int nv;                // values per item = 6 + 31 * n_lights
 };
 
 struct LightP {
@@ -1042,6 +1060,41 @@ __device__ __noinline__ bool light_cone(const float* __restrict__ d /* [10][3] *
     return true;
 }
 
+// cone_of10: the same cone (axis.xyz, min_j axis.D_j) from a 16-byte aligned bundle of 10 directions, loaded once as
+// vectors and reduced from registers; w = -1 for a degenerate bundle.  One out-of-line copy for all lights.
+__device__ __noinline__ float4 cone_of10(const float* __restrict__ d /* 32 floats, 30 used */) {
+    const float4* __restrict__ d4 = reinterpret_cast<const float4*>(d);
+    float v[32];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const float4 w = d4[q];
+        v[4 * q] = w.x;
+        v[4 * q + 1] = w.y;
+        v[4 * q + 2] = w.z;
+        v[4 * q + 3] = w.w;
+    }
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+#pragma unroll
+    for (int j = 0; j < 10; j++) {
+        sx += v[3 * j];
+        sy += v[3 * j + 1];
+        sz += v[3 * j + 2];
+    }
+    const float inv = rsqrtf(fmaf(sx, sx, fmaf(sy, sy, sz * sz)));
+    float cmin = 1.f;
+    bool ok = isfinite(inv);
+    sx *= inv;
+    sy *= inv;
+    sz *= inv;
+#pragma unroll
+    for (int j = 0; j < 10; j++) {
+        const float dd = fmaf(v[3 * j], v[3 * j], fmaf(v[3 * j + 1], v[3 * j + 1], v[3 * j + 2] * v[3 * j + 2]));
+        ok = ok && fabsf(dd - 1.f) < 1e-4f;  // the filters assume |D| = 1 (normalised by the reference)
+        cmin = fminf(cmin, fmaf(sx, v[3 * j], fmaf(sy, v[3 * j + 1], sz * v[3 * j + 2])));
+    }
+    return make_float4(sx, sy, sz, ok ? cmin : -1.f);
+}
+
 // warp beam of one light over the lanes with part == true.  Called by all 32 lanes.
 // ok == false: the lane axes disagree wildly (no warp-level culling); none == true: no lane takes part.
 struct Beam {
@@ -1524,6 +1577,112 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) shadow_cone_kernel(const Frame
 }
 
 // ------------------------------------------------------------------------------------
+// shade_point: the shading set-up of one hit pixel (kernel.cu:1380-1425, 1643-1655): hit point, normal, shadow-ray
+// origin `start`, texel colour.  `item` indexes the hit list.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ void shade_point(const FrameParams& prm, uint32_t item, const v3 O0, size_t& o_out, int& my_id,
+                                            v3& start, v3& normal, float& tr, float& tg, float& tb) {
+    const uint32_t o = prm.hit_list[item];
+    const int k = (int)(o / (uint32_t)prm.W), x = (int)(o % (uint32_t)prm.W);
+    o_out = out_index(prm, k, x);
+    const v3 D = primary_dir(prm, prm.dx_tab[x], prm.dy_tab[k]);
+    const float nt = prm.hit_t[o];
+    my_id = prm.hit_id[o];
+    v3 new_org = ref_add(O0, ref_scale(D, nt));
+    float txf, tyf;
+    if (my_id >= prm.n_spheres + prm.n_cubes + prm.n_planes) {
+        // triangle hit, kernel.cu:1380-1394
+        triangle_attributes(prm.tris + 27 * (size_t)(my_id - prm.n_spheres - prm.n_cubes - prm.n_planes),
+                            prm.mesh_has_normals, O0.x, O0.y, O0.z, D.x, D.y, D.z, nt, &normal, &new_org, &txf, &tyf);
+    } else if (my_id >= prm.n_spheres + prm.n_cubes) {
+        // plane hit, kernel.cu:1407-1416
+        const float4 no = __ldg(&prm.planes[2 * (my_id - prm.n_spheres - prm.n_cubes) + 1]);
+        normal = mk(no.x, no.y, no.z);
+        txf = 0.5f;
+        tyf = 0.5f;
+    } else {
+        // sphere hit kernel.cu:1396-1405 / cube hit :1417-1425: normal from the primitive's `orgin`
+        const float4 sc = (my_id < prm.n_spheres) ? __ldg(&prm.sph_exact[my_id])
+                                                  : __ldg(&prm.cubes[3 * (my_id - prm.n_spheres) + 2]);
+        normal = ref_sub(new_org, mk(sc.x, sc.y, sc.z));
+        ref_normalise(normal);
+        txf = (float)((1 + (double)ORE_ATAN2F(normal.z, normal.x) / 3.1415) * 0.5);
+        tyf = (float)((double)ORE_ACOSF(normal.y) / 3.1415);
+    }
+    const int maxX = prm.tex_w, maxY = prm.tex_h;
+    start = ref_add(ref_scale(normal, 0.00001f), new_org);
+    int c_index = (int)(tyf * (float)maxY) * maxX + (int)(txf * (float)maxX);
+    c_index = clamp_index(c_index, maxX * maxY);
+    tr = __ldg(&prm.tex_r[c_index]);
+    tg = __ldg(&prm.tex_g[c_index]);
+    tb = __ldg(&prm.tex_b[c_index]);
+}
+
+// ------------------------------------------------------------------------------------
+// shade_setup_kernel (stage A of the default shadow pass)
+//
+// Per hit pixel: shading set-up + the 10 shadow-ray directions of every light, written to the staging buffer.
+// This is all the per-pixel transcendental code (atan2f/acosf/cosf/sinf, ~30 KB of instructions); keeping it out
+// of the sweep kernel lets each kernel's hot loop stay resident in the SM instruction cache.
+// Warps run independently: each fetches blocks of 32 consecutive hit-list items.
+// ------------------------------------------------------------------------------------
+#ifndef ORE_STAGE_A_MIN_CTAS
+#define ORE_STAGE_A_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(CTA_THREADS, ORE_STAGE_A_MIN_CTAS) shade_setup_kernel(const FrameParams prm, const StageArgs st) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t n_items = (uint32_t)prm.counters[CNT_HITS];
+    const v3 O0 = mk(prm.Ox, prm.Oy, prm.Oz);
+    for (;;) {
+        uint32_t wb = 0;
+        if (lane == 0) wb = (uint32_t)atomicAdd(&prm.counters[CNT_STAGE_A0 + st.chunk], 1ull);
+        wb = __shfl_sync(0xffffffffu, wb, 0);
+        if (wb >= st.cap_blocks) break;
+        const uint32_t blk = st.first_block + wb;
+        if ((unsigned long long)blk * 32ull >= n_items) break;
+        const uint32_t item = blk * 32u + lane;
+        const bool valid = item < n_items;
+        size_t o_out = 0;
+        int my_id = -1;
+        v3 start = mk(1e9f, 1e9f, 1e9f), normal = mk(0.f, 0.f, 0.f);
+        float tr = 0.f, tg = 0.f, tb = 0.f;
+        if (valid) shade_point(prm, item, O0, o_out, my_id, start, normal, tr, tg, tb);
+        float* __restrict__ sp = st.buf + ((size_t)wb * (size_t)st.nv) * 32u + lane;
+        sp[0] = start.x;
+        sp[32] = start.y;
+        sp[64] = start.z;
+        sp[96] = tr;
+        sp[128] = tg;
+        sp[160] = tb;
+#pragma unroll 1
+        for (int li = 0; li < prm.n_lights; li++) {
+            __align__(16) float d[32];
+            float a = 0.f;
+            if (valid) {
+                LightP L;
+                const LightP* __restrict__ src = &prm.lights[0];
+                L.px = src[li].px; L.py = src[li].py; L.pz = src[li].pz; L.size = src[li].size;
+                L.r = src[li].r; L.g = src[li].g; L.b = src[li].b;
+                a = light_directions_reuse(L, start, normal, d);
+            }
+            float* __restrict__ q = sp + (size_t)(6 + 31 * li) * 32u;
+            if (valid) {
+                const float4* __restrict__ d4 = reinterpret_cast<const float4*>(d);
+#pragma unroll
+                for (int v = 0; v < 8; v++) {
+                    const float4 w = d4[v];
+                    q[(4 * v) * 32] = w.x;
+                    q[(4 * v + 1) * 32] = w.y;
+                    if (4 * v + 2 < 30) q[(4 * v + 2) * 32] = w.z;
+                    if (4 * v + 3 < 30) q[(4 * v + 3) * 32] = w.w;
+                }
+            }
+            q[30 * 32] = a;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
 // shadow_beam_kernel (default shadow path)
 //
 // shadow_cone_kernel with one more level in front: a warp's 32 hit pixels are neighbours
@@ -1535,8 +1694,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) shadow_cone_kernel(const Frame
 // survivors.  A hit at X = S_i + tD (t >= 0) has axial coordinate <= centre + R and lateral
 // offset <= rho_perp + t sin(a), which is exactly what level 1 bounds.
 // ------------------------------------------------------------------------------------
-template <bool EXH>
-__global__ void __launch_bounds__(CTA_THREADS, 3) shadow_beam_kernel(const FrameParams prm) {
+template <bool EXH, bool STAGED>
+__global__ void __launch_bounds__(CTA_THREADS, ORE_BEAM_MIN_CTAS) shadow_beam_kernel(const FrameParams prm, const StageArgs st) {
     constexpr int NL = 3;        // lights per pass
     constexpr int NR = 10 * NL;
     constexpr uint32_t ALL = (1u << NR) - 1u;
@@ -1573,57 +1732,40 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) shadow_beam_kernel(const Frame
 
     for (;;) {
         uint32_t wb = 0;
-        if (lane == 0) wb = (uint32_t)atomicAdd(&prm.counters[CNT_SHADOW_CURSOR], 1ull);
+        if (lane == 0) wb = (uint32_t)atomicAdd(&prm.counters[STAGED ? CNT_STAGE_B0 + st.chunk : CNT_SHADOW_CURSOR], 1ull);
         wb = __shfl_sync(0xffffffffu, wb, 0);
-        if ((unsigned long long)wb * 32ull >= n_items) break;
-        const uint32_t item = wb * 32u + lane;
+        if (STAGED && wb >= st.cap_blocks) break;
+        const uint32_t blk = STAGED ? st.first_block + wb : wb;
+        if ((unsigned long long)blk * 32ull >= n_items) break;
+        const uint32_t item = blk * 32u + lane;
         const bool valid = item < n_items;
 
-        // ---- shading set-up (kernel.cu:1396-1405, 1643-1655) ----
+        // ---- shading set-up (kernel.cu:1396-1405, 1643-1655), or its staged result ----
         size_t o_out = 0;
         int my_id = -1;
         v3 start = mk(1e9f, 1e9f, 1e9f), normal = mk(0.f, 0.f, 0.f);
         float tr = 0.f, tg = 0.f, tb = 0.f;
-        if (valid) {
-            const uint32_t o = prm.hit_list[item];
-            const int k = (int)(o / (uint32_t)prm.W), x = (int)(o % (uint32_t)prm.W);
-            o_out = out_index(prm, k, x);
-            const v3 D = primary_dir(prm, prm.dx_tab[x], prm.dy_tab[k]);
-            const float nt = prm.hit_t[o];
-            my_id = prm.hit_id[o];
-            v3 new_org = ref_add(O0, ref_scale(D, nt));
-            float txf, tyf;
-            if (my_id >= prm.n_spheres + prm.n_cubes + prm.n_planes) {
-                // triangle hit, kernel.cu:1380-1394
-                triangle_attributes(prm.tris + 27 * (size_t)(my_id - prm.n_spheres - prm.n_cubes - prm.n_planes),
-                                    prm.mesh_has_normals, O0.x, O0.y, O0.z, D.x, D.y, D.z, nt, &normal, &new_org, &txf, &tyf);
-            } else if (my_id >= prm.n_spheres + prm.n_cubes) {
-                // plane hit, kernel.cu:1407-1416
-                const float4 no = __ldg(&prm.planes[2 * (my_id - prm.n_spheres - prm.n_cubes) + 1]);
-                normal = mk(no.x, no.y, no.z);
-                txf = 0.5f;
-                tyf = 0.5f;
-            } else {
-                // sphere hit kernel.cu:1396-1405 / cube hit :1417-1425: normal from the primitive's `orgin`
-                const float4 sc = (my_id < prm.n_spheres) ? __ldg(&prm.sph_exact[my_id])
-                                                          : __ldg(&prm.cubes[3 * (my_id - prm.n_spheres) + 2]);
-                normal = ref_sub(new_org, mk(sc.x, sc.y, sc.z));
-                ref_normalise(normal);
-                txf = (float)((1 + (double)ORE_ATAN2F(normal.z, normal.x) / 3.1415) * 0.5);
-                tyf = (float)((double)ORE_ACOSF(normal.y) / 3.1415);
+        const float* __restrict__ sp = STAGED ? st.buf + ((size_t)wb * (size_t)st.nv) * 32u + lane : nullptr;
+        if (STAGED) {
+            if (valid) {
+                const uint32_t o = prm.hit_list[item];
+                const int k = (int)(o / (uint32_t)prm.W), x = (int)(o % (uint32_t)prm.W);
+                o_out = out_index(prm, k, x);
+                my_id = prm.hit_id[o];
+                start = mk(sp[0], sp[32], sp[64]);
+                tr = sp[96];
+                tg = sp[128];
+                tb = sp[160];
             }
-            const int maxX = prm.tex_w, maxY = prm.tex_h;
-            start = ref_add(ref_scale(normal, 0.00001f), new_org);
-            int c_index = (int)(tyf * (float)maxY) * maxX + (int)(txf * (float)maxX);
-            c_index = clamp_index(c_index, maxX * maxY);
-            tr = __ldg(&prm.tex_r[c_index]);
-            tg = __ldg(&prm.tex_g[c_index]);
-            tb = __ldg(&prm.tex_b[c_index]);
+        } else if (valid) {
+            shade_point(prm, item, O0, o_out, my_id, start, normal, tr, tg, tb);
         }
         float fr = 0.f, fg = 0.f, fb = 0.f;
 
         for (int l0 = 0; l0 < prm.n_lights; l0 += NL) {
-            float dirs[NR * 3];  // local memory (L1): only the rare per-ray path reads it
+            // local memory (L1), 32 floats per light so that a light's 10 directions load as 16-byte vectors
+            constexpr int LS = 32;
+            __align__(16) float dirs[NL * LS];
             float Ax[NL], Ay[NL], Az[NL], ca[NL], sa[NL], a_l[NL];
             uint32_t blocked = ALL;
             bool force = false;  // some light cannot use the cone test: every sphere is a candidate
@@ -1631,13 +1773,21 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) shadow_beam_kernel(const Frame
             for (int l = 0; l < NL; l++) {
                 float a = 0.f;
                 if (valid && (l0 + l) < prm.n_lights) {
-                    LightP L;
-                    const LightP* __restrict__ src = &prm.lights[0];
-                    // copy out of the parameter bank without taking its address into local memory
-                    const int li = l0 + l;
-                    L.px = src[li].px; L.py = src[li].py; L.pz = src[li].pz; L.size = src[li].size;
-                    L.r = src[li].r; L.g = src[li].g; L.b = src[li].b;
-                    a = light_directions_reuse(L, start, normal, dirs + 30 * l);
+                    if (STAGED) {
+                        const float* __restrict__ q = sp + (size_t)(6 + 31 * (l0 + l)) * 32u;
+                        float* __restrict__ d = dirs + LS * l;
+#pragma unroll
+                        for (int j = 0; j < 30; j++) d[j] = q[j * 32];
+                        a = q[30 * 32];
+                    } else {
+                        LightP L;
+                        const LightP* __restrict__ src = &prm.lights[0];
+                        // copy out of the parameter bank without taking its address into local memory
+                        const int li = l0 + l;
+                        L.px = src[li].px; L.py = src[li].py; L.pz = src[li].pz; L.size = src[li].size;
+                        L.r = src[li].r; L.g = src[li].g; L.b = src[li].b;
+                        a = light_directions_reuse(L, start, normal, dirs + LS * l);
+                    }
                 }
                 if (l == 0) a_l[0] = a;
                 if (l == 1) a_l[1] = a;
@@ -1648,30 +1798,10 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) shadow_beam_kernel(const Frame
                 const bool lit = valid && (l0 + l) < prm.n_lights;
                 Ax[l] = Ay[l] = Az[l] = ca[l] = sa[l] = 0.f;
                 if (lit) {
-                    float* d = dirs + 30 * l;
                     blocked &= ~(0x3ffu << (10 * l));
-                    // cone of the 10 rays: axis = normalised sum, cos(a) = min_j axis.D_j
-                    float sx = 0.f, sy = 0.f, sz = 0.f;
-#pragma unroll 1
-                    for (int j = 0; j < 10; j++) {
-                        sx += d[j * 3];
-                        sy += d[j * 3 + 1];
-                        sz += d[j * 3 + 2];
-                    }
-                    const float inv = rsqrtf(fmaf(sx, sx, fmaf(sy, sy, sz * sz)));
-                    float cmin = 1.f;
-                    bool ok = isfinite(inv);
-                    if (ok) {
-                        sx *= inv;
-                        sy *= inv;
-                        sz *= inv;
-#pragma unroll 1
-                        for (int j = 0; j < 10; j++) {
-                            const float dd = fmaf(d[j * 3], d[j * 3], fmaf(d[j * 3 + 1], d[j * 3 + 1], d[j * 3 + 2] * d[j * 3 + 2]));
-                            ok = ok && fabsf(dd - 1.f) < 1e-4f;  // the filters assume |D| = 1 (normalised by the reference)
-                            cmin = fminf(cmin, fmaf(sx, d[j * 3], fmaf(sy, d[j * 3 + 1], sz * d[j * 3 + 2])));
-                        }
-                    }
+                    const float4 cn = cone_of10(dirs + LS * l);
+                    const float sx = cn.x, sy = cn.y, sz = cn.z, cmin = cn.w;
+                    const bool ok = cmin > 0.f;
                     if (ok && cmin > 0.5f && !EXH) {
                         const float cosa = cmin - 4e-6f;
                         const float sina = sqrtf(fmaxf(0.f, fmaf(-cosa, cosa, 1.f))) * 1.0001f + 1e-6f;
@@ -1691,6 +1821,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) shadow_beam_kernel(const Frame
             // normally is one group; a warp straddling a silhouette is two or three): origins on one sphere give
             // a narrow beam.  At most 4 passes; the last pass takes every lane that is left.
             uint32_t pending = __ballot_sync(0xffffffffu, valid);
+#ifdef ORE_EXPERIMENT_A_ONLY
+            pending = 0;
+#endif
 #pragma unroll 1
             for (int pass = 0; pending; pass++) {
                 const int leader = __ffs(pending) - 1;
@@ -1715,12 +1848,19 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) shadow_beam_kernel(const Frame
                 const float ex = ing ? start.x - bx : 0.f, ey = ing ? start.y - by : 0.f, ez = ing ? start.z - bz : 0.f;
                 const float escale = 1e-5f * (fabsf(bx) + fabsf(by) + fabsf(bz) + 1.f);  // rounding slack on offsets
                 bool wforce = __any_sync(0xffffffffu, ing && force);
-                float wAx[NL], wAy[NL], wAz[NL], wtan[NL], wk1[NL], wk2[NL];  // k1 = -a_min, k2 = rho_perp
-    #pragma unroll
+                // One rolled copy of the beam code (instruction-cache footprint): light l's beam is computed by the
+                // whole warp, parked in lane l, and handed back to every lane by shuffles afterwards.
+                float pAx = 0.f, pAy = 0.f, pAz = 0.f, ptan = 0.f, pk1 = -3e38f, pk2 = 0.f;
+#pragma unroll 1
                 for (int l = 0; l < NL; l++) {
-                    const bool part = ing && ca[l] > 0.f;  // lanes of the group whose light l takes part (lit, not degenerate)
-                    float sx = part ? Ax[l] : 0.f, sy = part ? Ay[l] : 0.f, sz = part ? Az[l] : 0.f;
-    #pragma unroll
+                    const float Al_x = l == 0 ? Ax[0] : (l == 1 ? Ax[1] : Ax[2]);
+                    const float Al_y = l == 0 ? Ay[0] : (l == 1 ? Ay[1] : Ay[2]);
+                    const float Al_z = l == 0 ? Az[0] : (l == 1 ? Az[1] : Az[2]);
+                    const float ca_l = l == 0 ? ca[0] : (l == 1 ? ca[1] : ca[2]);
+                    const float sa_l = l == 0 ? sa[0] : (l == 1 ? sa[1] : sa[2]);
+                    const bool part = ing && ca_l > 0.f;  // lanes of the group whose light l takes part (lit, not degenerate)
+                    float sx = part ? Al_x : 0.f, sy = part ? Al_y : 0.f, sz = part ? Al_z : 0.f;
+#pragma unroll
                     for (int d = 16; d > 0; d >>= 1) {
                         sx += __shfl_xor_sync(0xffffffffu, sx, d);
                         sy += __shfl_xor_sync(0xffffffffu, sy, d);
@@ -1734,9 +1874,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) shadow_beam_kernel(const Frame
                     // widest angle between the warp axis and any participating ray: theta_lane + a_lane
                     float cw = 1.f, amin = 3e38f, rp = 0.f;
                     if (part) {
-                        const float sina = sa[l] * (1.f / 1.002f);
-                        const float cosa = ca[l] + 0.00196f * sina;
-                        const float c1 = fminf(1.f, fmaf(sx, Ax[l], fmaf(sy, Ay[l], sz * Az[l])));
+                        const float sina = sa_l * (1.f / 1.002f);
+                        const float cosa = ca_l + 0.00196f * sina;
+                        const float c1 = fminf(1.f, fmaf(sx, Al_x, fmaf(sy, Al_y, sz * Al_z)));
                         const float s1 = sqrtf(fmaxf(0.f, fmaf(-c1, c1, 1.f))) + 1e-6f;
                         cw = fmaf(c1, cosa, -(s1 * sina)) - 2e-6f;
                         const float ai = fmaf(ex, sx, fmaf(ey, sy, ez * sz));  // axial offset of this origin
@@ -1744,30 +1884,35 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) shadow_beam_kernel(const Frame
                         amin = ai;
                         rp = sqrtf(fmaf(px, px, fmaf(py, py, pz * pz)));
                     }
-    #pragma unroll
+#pragma unroll
                     for (int d = 16; d > 0; d >>= 1) {
                         cw = fminf(cw, __shfl_xor_sync(0xffffffffu, cw, d));
                         amin = fminf(amin, __shfl_xor_sync(0xffffffffu, amin, d));
                         rp = fmaxf(rp, __shfl_xor_sync(0xffffffffu, rp, d));
                     }
-                    const bool any_part = __any_sync(0xffffffffu, part);
-                    wAx[l] = wAy[l] = wAz[l] = 0.f;
-                    wtan[l] = 0.f;
-                    wk1[l] = -3e38f;  // u = sc + R' + k1 < 0: never a candidate
-                    wk2[l] = 0.f;
-                    if (any_part) {
+                    if (__any_sync(0xffffffffu, part)) {
                         if (!(n2 > 1e-12f) || !(cw > 0.3f)) {
                             wforce = true;  // bundle axes disagree wildly: no warp-level culling
-                        } else {
+                        } else if (lane == l) {
                             const float sinw = sqrtf(fmaxf(0.f, fmaf(-cw, cw, 1.f))) * 1.0001f + 1e-6f;
-                            wAx[l] = sx;
-                            wAy[l] = sy;
-                            wAz[l] = sz;
-                            wtan[l] = sinw / cw * 1.0001f;
-                            wk1[l] = -(amin - escale);
-                            wk2[l] = rp * 1.0001f + escale;
+                            pAx = sx;
+                            pAy = sy;
+                            pAz = sz;
+                            ptan = sinw / cw * 1.0001f;
+                            pk1 = -(amin - escale);   // u = sc + R' + k1 < 0: never a candidate
+                            pk2 = rp * 1.0001f + escale;
                         }
                     }
+                }
+                float wAx[NL], wAy[NL], wAz[NL], wtan[NL], wk1[NL], wk2[NL];  // k1 = -a_min, k2 = rho_perp
+#pragma unroll
+                for (int l = 0; l < NL; l++) {
+                    wAx[l] = __shfl_sync(0xffffffffu, pAx, l);
+                    wAy[l] = __shfl_sync(0xffffffffu, pAy, l);
+                    wAz[l] = __shfl_sync(0xffffffffu, pAz, l);
+                    wtan[l] = __shfl_sync(0xffffffffu, ptan, l);
+                    wk1[l] = __shfl_sync(0xffffffffu, pk1, l);
+                    wk2[l] = __shfl_sync(0xffffffffu, pk2, l);
                 }
                 if (EXH) wforce = true;
 
@@ -1819,16 +1964,40 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) shadow_beam_kernel(const Frame
                         if (live) {
                             n_l2++;
                             const float4 ex4 = __ldg(&prm.sph_exact[s]);
-                            while (live) {
-                                const int j = __ffs(live) - 1;
-                                live &= live - 1;
-                                const v3 D = mk(dirs[j * 3], dirs[j * 3 + 1], dirs[j * 3 + 2]);
-                                const float h = fmaf(D.x, lx, fmaf(D.y, ly, fmaf(D.z, lz, svu)));
-                                if (h < 0.f) {
-                                    float t;
-                                    n_exact++;
-                                    if (ref_intersect(start, D, ex4.x, ex4.y, ex4.z, ex4.w, t)) blocked |= 1u << j;
+                            // per-ray filter h = D.L + s' < 0 on all 10 rays of each live light at once
+                            // (independent loads and FMAs), then the exact sequence on the few that pass
+                            uint32_t cand = 0;
+#pragma unroll 1
+                            for (int l = 0; l < NL; l++) {
+                                const uint32_t lv = (live >> (10 * l)) & 0x3ffu;
+                                if (lv) {
+                                    const float4* __restrict__ d4 = reinterpret_cast<const float4*>(dirs + LS * l);
+                                    float dd[32];
+#pragma unroll
+                                    for (int v = 0; v < 8; v++) {
+                                        const float4 w = d4[v];
+                                        dd[4 * v] = w.x;
+                                        dd[4 * v + 1] = w.y;
+                                        dd[4 * v + 2] = w.z;
+                                        dd[4 * v + 3] = w.w;
+                                    }
+                                    uint32_t m = 0;
+#pragma unroll
+                                    for (int j = 0; j < 10; j++) {
+                                        const float h = fmaf(dd[3 * j], lx, fmaf(dd[3 * j + 1], ly, fmaf(dd[3 * j + 2], lz, svu)));
+                                        if (h < 0.f) m |= 1u << j;
+                                    }
+                                    cand |= (m & lv) << (10 * l);
                                 }
+                            }
+                            while (cand) {
+                                const int j = __ffs(cand) - 1;
+                                cand &= cand - 1;
+                                const int l = (j >= 20) ? 2 : (j >= 10 ? 1 : 0);
+                                const float* __restrict__ d = dirs + LS * l + 3 * (j - 10 * l);
+                                float t;
+                                n_exact++;
+                                if (ref_intersect(start, mk(d[0], d[1], d[2]), ex4.x, ex4.y, ex4.z, ex4.w, t)) blocked |= 1u << j;
                             }
     #pragma unroll
                             for (int l = 0; l < NL; l++) {
@@ -1855,7 +2024,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) shadow_beam_kernel(const Frame
                     if (live) {
                         const bool use_cone = !EXH && !force && ca[l] > 0.f;
                         const uint32_t hit = mesh_blocks_light(ma, prm.box_sph, start.x, start.y, start.z, Ax[l], Ay[l], Az[l],
-                                                               ca[l], sa[l], use_cone, dirs + 30 * l, live);
+                                                               ca[l], sa[l], use_cone, dirs + LS * l, live);
                         blocked |= hit << (10 * l);
                     }
                 }
@@ -1870,7 +2039,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) shadow_beam_kernel(const Frame
                         const bool use_cone = !EXH && !force && ca[l] > 0.f;
                         const uint32_t hit = cubes_planes_block_light(prm.cubes, prm.n_cubes, prm.planes, prm.n_planes, start.x,
                                                                       start.y, start.z, Ax[l], Ay[l], Az[l], ca[l], sa[l],
-                                                                      use_cone, dirs + 30 * l, live);
+                                                                      use_cone, dirs + LS * l, live);
                         blocked |= hit << (10 * l);
                     }
                 }
