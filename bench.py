@@ -121,7 +121,8 @@ def hbm_block(traffic_bytes, kernel_ms):
         return {"peak_gbs": peak, "peak_source": src, "achieved_gbs": None, "frac": None}
     ach = traffic_bytes / (kernel_ms * 1e-3) / 1e9
     return {"peak_gbs": peak, "peak_source": src, "achieved_gbs": ach, "frac": ach / peak,
-            "note": "ncu dram bytes of one launch / CUDA-event kernel time: the kernel is nowhere near HBM-bound"}
+            "note": "ncu dram bytes of the shadow pass of one frame / its CUDA-event time (the staging buffer between the "
+                    "two shadow kernels is most of it); the pass is instruction-issue bound, not HBM-bound"}
 
 
 def dist_env():
@@ -326,6 +327,7 @@ def main():
         render_step(args.warmup + i, 0)
         stream.synchronize()
         kernel_ms.append(r.kernel_ms())
+    launches_per_frame = int(r.counters()["kernel_launches"])   # counted by the library per render call
     barrier()
     total_ms = torch.tensor([ev_start.elapsed_time(ev_end)], dtype=torch.float64, device=f"cuda:{local}")
     if world > 1:
@@ -537,9 +539,13 @@ def main():
                             "output per step is the whole framebuffer read back to pinned host memory; "
                             "synchronous_value = ore_render (launch + sync + copy per call, the reference update() semantics)",
                     "sharded_frame_check": frame_check},
-            "gpu_launches": 3 * args.steps,
+            "gpu_launches": launches_per_frame * args.steps,
+            "gpu_launches_per_frame": {"count": launches_per_frame,
+                                       "kernels": "prep_frame, primary_tile, then per hit-list chunk shade_setup + shadow_beam "
+                                                  "(chunks past the end of the hit list exit at once); one fused "
+                                                  "shadow_beam instead when the sphere records exceed shared memory"},
             "roofline": {
-                "bound": "fp32", "kernel": "shadow_beam_kernel (soft-shadow any-hit + shading; default path)",
+                "bound": "fp32", "kernel": "shadow pass = shade_setup_kernel + shadow_beam_kernel (soft-shadow any-hit + shading; default path)",
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None,
                 "traffic": traffic,
                 "peak_source": "measured: FFMA burn on this GPU in this run (MEASURED_PEAKS.json carries HBM and bf16 only); "

@@ -1060,6 +1060,15 @@ __device__ __noinline__ bool light_cone(const float* __restrict__ d /* [10][3] *
     return true;
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// direction of sample ray j (0..29: light j / 10, sample j % 10) in a per-thread bundle with `ls` floats per light
+__device__ __forceinline__ v3 load_dir(const float* __restrict__ dirs, int ls, int j) {
+    const int l = (j >= 20) ? 2 : (j >= 10 ? 1 : 0);
+    const float* __restrict__ d = dirs + ls * l + 3 * (j - 10 * l);
+    return mk(d[0], d[1], d[2]);
+}
+
 // cone_of10: the same cone (axis.xyz, min_j axis.D_j) from a 16-byte aligned bundle of 10 directions, loaded once as
 // vectors and reduced from registers; w = -1 for a degenerate bundle.  One out-of-line copy for all lights.
 __device__ __noinline__ float4 cone_of10(const float* __restrict__ d /* 32 floats, 30 used */) {
@@ -1089,7 +1098,9 @@ __device__ __noinline__ float4 cone_of10(const float* __restrict__ d /* 32 float
 #pragma unroll
     for (int j = 0; j < 10; j++) {
         const float dd = fmaf(v[3 * j], v[3 * j], fmaf(v[3 * j + 1], v[3 * j + 1], v[3 * j + 2] * v[3 * j + 2]));
-        ok = ok && fabsf(dd - 1.f) < 1e-4f;  // the filters assume |D| = 1 (normalised by the reference)
+        // the filters and the sure-hit shortcut assume |D| = 1: the reference's normalise() leaves | |D|^2 - 1 |
+        // below 5e-7 unless it degenerated (zero or denormal input), which is what this check catches
+        ok = ok && fabsf(dd - 1.f) < 4e-6f;
         cmin = fminf(cmin, fmaf(sx, v[3 * j], fmaf(sy, v[3 * j + 1], sz * v[3 * j + 2])));
     }
     return make_float4(sx, sy, sz, ok ? cmin : -1.f);
@@ -1730,15 +1741,30 @@ __global__ void __launch_bounds__(CTA_THREADS, ORE_BEAM_MIN_CTAS) shadow_beam_ke
     unsigned long long n_exact = 0;
     unsigned int n_l1 = 0, n_l2 = 0;
 
-    for (;;) {
-        uint32_t wb = 0;
-        if (lane == 0) wb = (uint32_t)atomicAdd(&prm.counters[STAGED ? CNT_STAGE_B0 + st.chunk : CNT_SHADOW_CURSOR], 1ull);
-        wb = __shfl_sync(0xffffffffu, wb, 0);
+    // the block cursor is fetched one block ahead, so that the next block's staged values can be pulled into L2
+    // while this one is processed
+    unsigned long long* const cursor = &prm.counters[STAGED ? CNT_STAGE_B0 + st.chunk : CNT_SHADOW_CURSOR];
+    uint32_t wb = 0;
+    if (lane == 0) wb = (uint32_t)atomicAdd(cursor, 1ull);
+    wb = __shfl_sync(0xffffffffu, wb, 0);
+    for (;; ) {
         if (STAGED && wb >= st.cap_blocks) break;
         const uint32_t blk = STAGED ? st.first_block + wb : wb;
         if ((unsigned long long)blk * 32ull >= n_items) break;
         const uint32_t item = blk * 32u + lane;
         const bool valid = item < n_items;
+        // not near the end of the list / chunk, where a reserved block would wait behind this one while other
+        // warps run dry
+        const bool ahead = (unsigned long long)(blk + 8192u) * 32ull < n_items && (!STAGED || wb + 8192u < st.cap_blocks);
+        uint32_t wb_next = 0;
+        if (ahead) {
+            if (lane == 0) wb_next = (uint32_t)atomicAdd(cursor, 1ull);
+            wb_next = __shfl_sync(0xffffffffu, wb_next, 0);
+            if (STAGED && wb_next < st.cap_blocks) {
+                const float* nb = st.buf + ((size_t)wb_next * (size_t)st.nv) * 32u;
+                for (int v = lane; v < st.nv; v += 32) prefetch_l2(nb + (size_t)v * 32u);
+            }
+        }
 
         // ---- shading set-up (kernel.cu:1396-1405, 1643-1655), or its staged result ----
         size_t o_out = 0;
@@ -1966,6 +1992,15 @@ __global__ void __launch_bounds__(CTA_THREADS, ORE_BEAM_MIN_CTAS) shadow_beam_ke
                             const float4 ex4 = __ldg(&prm.sph_exact[s]);
                             // per-ray filter h = D.L + s' < 0 on all 10 rays of each live light at once
                             // (independent loads and FMAs), then the exact sequence on the few that pass
+                            // "Sure hit" (DESIGN.md 2.5): sphere::intersect returns true whenever its discriminant is
+                            // positive and the far root passes the 0.0001 gate.  With b = D.L < 0 and | |D|^2 - 1 | <
+                            // 5e-6 (cone_of10 admits nothing else), b^2 > (|L|^2 - r^2) + 2e-5 |L|^2 keeps the
+                            // float discriminant positive (its rounding error is below 7e-6 |L|^2) and b^2 >
+                            // 1e-6 |L|^2 + 1e-6 keeps the far root above 9e-4: the ray is blocked without running
+                            // the exact sequence.  Everything in between is re-adjudicated exactly as before.
+                            const float sure_thr = (EXH || force)
+                                                       ? ORE_BIG
+                                                       : fmaxf(fmaf(LL, 1e-6f, 1e-6f), fmaf(LL, 2e-5f, fmaf(-ex4.w, ex4.w, LL)));
                             uint32_t cand = 0;
 #pragma unroll 1
                             for (int l = 0; l < NL; l++) {
@@ -1981,23 +2016,39 @@ __global__ void __launch_bounds__(CTA_THREADS, ORE_BEAM_MIN_CTAS) shadow_beam_ke
                                         dd[4 * v + 2] = w.z;
                                         dd[4 * v + 3] = w.w;
                                     }
-                                    uint32_t m = 0;
+                                    uint32_t m = 0, sure = 0;
 #pragma unroll
                                     for (int j = 0; j < 10; j++) {
-                                        const float h = fmaf(dd[3 * j], lx, fmaf(dd[3 * j + 1], ly, fmaf(dd[3 * j + 2], lz, svu)));
-                                        if (h < 0.f) m |= 1u << j;
+                                        const float b = fmaf(dd[3 * j], lx, fmaf(dd[3 * j + 1], ly, dd[3 * j + 2] * lz));
+                                        if (b + svu < 0.f) m |= 1u << j;
+                                        if (b < 0.f && b * b > sure_thr) sure |= 1u << j;
                                     }
-                                    cand |= (m & lv) << (10 * l);
+                                    sure &= m & lv;  // only rays the filter lets through, that are still unblocked
+                                    blocked |= sure << (10 * l);
+                                    cand |= (m & lv & ~sure) << (10 * l);
                                 }
                             }
-                            while (cand) {
-                                const int j = __ffs(cand) - 1;
+                            if (cand) {
+                                // exact re-adjudication; the next candidate's direction is loaded (local memory)
+                                // before the current one's exact sequence runs
+                                int j = __ffs(cand) - 1;
                                 cand &= cand - 1;
-                                const int l = (j >= 20) ? 2 : (j >= 10 ? 1 : 0);
-                                const float* __restrict__ d = dirs + LS * l + 3 * (j - 10 * l);
-                                float t;
-                                n_exact++;
-                                if (ref_intersect(start, mk(d[0], d[1], d[2]), ex4.x, ex4.y, ex4.z, ex4.w, t)) blocked |= 1u << j;
+                                v3 D = load_dir(dirs, LS, j);
+                                for (;;) {
+                                    int jn = -1;
+                                    v3 Dn = D;
+                                    if (cand) {
+                                        jn = __ffs(cand) - 1;
+                                        cand &= cand - 1;
+                                        Dn = load_dir(dirs, LS, jn);
+                                    }
+                                    float t;
+                                    n_exact++;
+                                    if (ref_intersect(start, D, ex4.x, ex4.y, ex4.z, ex4.w, t)) blocked |= 1u << j;
+                                    if (jn < 0) break;
+                                    j = jn;
+                                    D = Dn;
+                                }
                             }
     #pragma unroll
                             for (int l = 0; l < NL; l++) {
@@ -2062,6 +2113,11 @@ __global__ void __launch_bounds__(CTA_THREADS, ORE_BEAM_MIN_CTAS) shadow_beam_ke
             }
         }
         if (valid) prm.pixels[o_out] = ref_rgb_to_int((int)(fr * 254.f), (int)(fg * 254.f), (int)(fb * 254.f));
+        if (!ahead) {
+            if (lane == 0) wb_next = (uint32_t)atomicAdd(cursor, 1ull);
+            wb_next = __shfl_sync(0xffffffffu, wb_next, 0);
+        }
+        wb = wb_next;
     }
     if (n_exact) atomicAdd(&prm.counters[CNT_EXACT_SHADOW], n_exact);
     if (lane == 0 && n_l1) atomicAdd(&prm.counters[CNT_BEAM_L1], (unsigned long long)n_l1);
