@@ -209,7 +209,8 @@ int ore_get_kernel_ms(ore_context* ctx, float ms[4]);
  * and returns the nominal SM clock; used by bench.py only. */
 int ore_measure_fp32_peak(ore_context* ctx, double* tflops, double* sm_clock_mhz_nominal);
 /* Tests only: evaluates the device libm the path uses on n host inputs.
- * op 0 cosf(a), 1 sinf(a), 2 acosf(a), 3 atan2f(a, b).  The path's versions return glibc's bits (ore_libm.cuh). */
+ * op 0 cosf(a), 1 sinf(a), 2 acosf(a), 3 atan2f(a, b).  The path's versions return glibc's bits (ore_libm.cuh).
+ * op 4, 5, 6: x, y, z of the path's normalise() applied to (a[i], b[i], a[(i + 1) % n]) - IEEE x / |v| bit for bit. */
 int ore_debug_libm(ore_context* ctx, int op, int n, const float* a_host, const float* b_host, float* out_host);
 
 #ifdef __cplusplus

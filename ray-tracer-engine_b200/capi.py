@@ -315,7 +315,7 @@ class Renderer:
 
     def debug_libm(self, op: str, a: np.ndarray, b: np.ndarray | None = None) -> np.ndarray:
         """device libm of the path on host inputs (tests): op in cosf, sinf, acosf, atan2f(a=y, b=x)"""
-        code = {"cosf": 0, "sinf": 1, "acosf": 2, "atan2f": 3}[op]
+        code = {"cosf": 0, "sinf": 1, "acosf": 2, "atan2f": 3, "normalise_x": 4, "normalise_y": 5, "normalise_z": 6}[op]
         a = np.ascontiguousarray(a, dtype=np.float32)
         b = np.ascontiguousarray(a if b is None else b, dtype=np.float32)
         out = np.empty_like(a)

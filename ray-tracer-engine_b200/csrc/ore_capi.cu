@@ -940,7 +940,7 @@ extern "C" int ore_get_kernel_ms(ore_context* ctx, float ms[4]) {
 }
 
 extern "C" int ore_debug_libm(ore_context* ctx, int op, int n, const float* a_host, const float* b_host, float* out_host) {
-    if (!ctx || n <= 0 || !a_host || !out_host || op < 0 || op > 3) return ORE_ERR_INVALID;
+    if (!ctx || n <= 0 || !a_host || !out_host || op < 0 || op > 6) return ORE_ERR_INVALID;
     ORE_CUDA(ctx, cudaSetDevice(ctx->device));
     float *a = nullptr, *b = nullptr, *o = nullptr;
     const size_t bytes = (size_t)n * sizeof(float);

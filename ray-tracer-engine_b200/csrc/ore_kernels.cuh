@@ -875,6 +875,8 @@ __global__ void __launch_bounds__(CTA_THREADS, ORE_TILE_MIN_CTAS) primary_tile_k
             const int k = ty * P + p;
             if (x_ok && k < prm.n_rows && best_id[p] >= 0) prm.hit_list[wbase + my_off[p]] = (uint32_t)((size_t)k * prm.W + x);
         }
+        // (the barriers also keep the CTA's warps in step, which keeps its code resident in the instruction cache:
+        // per-warp reservations without them measured 14 % slower)
         __syncthreads();  // warp_tot / cta_base reuse
     }
     if (n_exact) atomicAdd(&prm.counters[CNT_EXACT_PRIMARY], n_exact);
@@ -2209,8 +2211,14 @@ __global__ void libm_probe_kernel(int op, int n, const float* a, const float* b,
         r = ORE_SINF(a[i]);
     else if (op == 2)
         r = ORE_ACOSF(a[i]);
-    else
+    else if (op == 3)
         r = ORE_ATAN2F(a[i], b[i]);
+    else {
+        // ops 4-6: component (op - 4) of ref_normalise((a[i], b[i], a[(i + 1) % n]))
+        v3 v = mk(a[i], b[i], a[(i + 1) % n]);
+        ref_normalise(v);
+        r = op == 4 ? v.x : (op == 5 ? v.y : v.z);
+    }
     out[i] = r;
 }
 
