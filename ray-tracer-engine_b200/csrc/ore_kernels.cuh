@@ -1946,31 +1946,37 @@ __global__ void __launch_bounds__(CTA_THREADS, ORE_BEAM_MIN_CTAS) shadow_beam_ke
 
                 bool warp_done = false;
     #pragma unroll 1
-                for (int s0 = 0; s0 < n_sph && !warp_done; s0 += 32) {
-                    // ---- level 1: lane i tests sphere s0+i against the warp's beams ----
-                    const bool in = s0 + lane < n_sph;
-                    bool wc = false;
-                    if (in) {
-                        const float4 q = spheres[s0 + lane];
-                        const float Lx = bx - q.x, Ly = by - q.y, Lz = bz - q.z;
-                        const float LL = fmaf(Lz, Lz, fmaf(Ly, Ly, Lx * Lx));
-                        const float Rq = fmaf(q.w, 1.0001f, fmaf(LL, 1e-12f, 1e-6f));  // radius + rounding slack
-                        const float slack = LL * 2e-6f;                                 // cancellation in LL - sc^2
+                for (int s0 = 0; s0 < n_sph && !warp_done; s0 += 64) {
+                    // ---- level 1: lane i tests spheres s0+i and s0+32+i against the warp's beams (two independent
+                    //      chains per lane) ----
+                    uint32_t wm2[2];
     #pragma unroll
-                        for (int l = 0; l < NL; l++) {
-                            const float sc = -fmaf(wAx[l], Lx, fmaf(wAy[l], Ly, wAz[l] * Lz));  // centre's axial coordinate
-                            const float u = sc + Rq + wk1[l];                                     // >= 0 unless wholly behind
-                            const float thr = fmaf(u, wtan[l], Rq + wk2[l]);
-                            const float d2 = fmaf(-sc, sc, LL);
-                            wc = wc || (u >= 0.f && d2 <= fmaf(thr, thr, slack));
+                    for (int h = 0; h < 2; h++) {
+                        const bool in = s0 + 32 * h + lane < n_sph;
+                        bool wc = false;
+                        if (in) {
+                            const float4 q = spheres[s0 + 32 * h + lane];
+                            const float Lx = bx - q.x, Ly = by - q.y, Lz = bz - q.z;
+                            const float LL = fmaf(Lz, Lz, fmaf(Ly, Ly, Lx * Lx));
+                            const float Rq = fmaf(q.w, 1.0001f, fmaf(LL, 1e-12f, 1e-6f));  // radius + rounding slack
+                            const float slack = LL * 2e-6f;                                 // cancellation in LL - sc^2
+    #pragma unroll
+                            for (int l = 0; l < NL; l++) {
+                                const float sc = -fmaf(wAx[l], Lx, fmaf(wAy[l], Ly, wAz[l] * Lz));  // centre's axial coordinate
+                                const float u = sc + Rq + wk1[l];                                     // >= 0 unless wholly behind
+                                const float thr = fmaf(u, wtan[l], Rq + wk2[l]);
+                                const float d2 = fmaf(-sc, sc, LL);
+                                wc = wc || (u >= 0.f && d2 <= fmaf(thr, thr, slack));
+                            }
+                            wc = wc || wforce;
                         }
-                        wc = wc || wforce;
+                        wm2[h] = __ballot_sync(0xffffffffu, wc);
                     }
-                    uint32_t wmask = __ballot_sync(0xffffffffu, wc);
-                    n_l1 += __popc(wmask);
+                    unsigned long long wmask = (unsigned long long)wm2[0] | ((unsigned long long)wm2[1] << 32);
+                    n_l1 += __popcll(wmask);
                     // ---- level 2: every lane runs its own cone test on the surviving spheres ----
                     while (wmask) {
-                        const int i = __ffs(wmask) - 1;
+                        const int i = __ffsll((long long)wmask) - 1;
                         wmask &= wmask - 1;
                         const int s = s0 + i;
                         const float4 q = spheres[s];
