@@ -439,6 +439,8 @@ def main():
         except Exception:
             traffic = None
 
+    if traffic and world > 1:
+        traffic = traffic / world   # the ncu capture is a whole frame on one GPU; a rank sweeps 1/world of the hit pixels
     also_4k = None
     if world == 1 and args.workload == "8k1024":
         # configs[2] (4K / 1024 spheres, the single-GPU roofline scene): same scene, quarter of the pixels
