@@ -184,13 +184,6 @@ __device__ __noinline__ uint32_t sky_pixel(const SkyArgs sk, float Ox, float Oy,
     return ref_rgb_to_int((int)(r * 254.f), (int)(g * 254.f), (int)(b * 254.f));
 }
 // exact sphere test out of line: returns the hit flag, t through the pointer
-__device__ __noinline__ bool ref_intersect_t(float Ox, float Oy, float Oz, float Dx, float Dy, float Dz, float4 s,
-                                             float* t_out) {
-    float t;
-    const bool hit = ref_intersect(mk(Ox, Oy, Oz), mk(Dx, Dy, Dz), s.x, s.y, s.z, s.w, t);
-    *t_out = t;
-    return hit;
-}
 struct DirArgs {
     float ez, cp, sp, cy, sy;
 };
@@ -1024,44 +1017,6 @@ __device__ __noinline__ float light_directions_reuse(const LightP L, const v3 st
     return ref_dot(normal, toL);
 }
 
-// cone of one light's 10 sample directions: axis = normalised sum, cos(a) = min_j axis.D_j.
-// Returns false for a degenerate bundle (zero-length direction, very wide cone): no cone test for that light.
-struct Cone {
-    float ax, ay, az, ca, sa;
-};
-__device__ __noinline__ bool light_cone(const float* __restrict__ d /* [10][3] */, Cone* out) {
-    float sx = 0.f, sy = 0.f, sz = 0.f;
-#pragma unroll 1
-    for (int j = 0; j < 10; j++) {
-        sx += d[j * 3];
-        sy += d[j * 3 + 1];
-        sz += d[j * 3 + 2];
-    }
-    const float inv = rsqrtf(fmaf(sx, sx, fmaf(sy, sy, sz * sz)));
-    float cmin = 1.f;
-    bool ok = isfinite(inv);
-    if (ok) {
-        sx *= inv;
-        sy *= inv;
-        sz *= inv;
-#pragma unroll 1
-        for (int j = 0; j < 10; j++) {
-            const float dd = fmaf(d[j * 3], d[j * 3], fmaf(d[j * 3 + 1], d[j * 3 + 1], d[j * 3 + 2] * d[j * 3 + 2]));
-            ok = ok && fabsf(dd - 1.f) < 1e-4f;  // the filters assume |D| = 1 (normalised by the reference)
-            cmin = fminf(cmin, fmaf(sx, d[j * 3], fmaf(sy, d[j * 3 + 1], sz * d[j * 3 + 2])));
-        }
-    }
-    if (!(ok && cmin > 0.5f)) return false;
-    const float cosa = cmin - 4e-6f;
-    const float sina = sqrtf(fmaxf(0.f, fmaf(-cosa, cosa, 1.f))) * 1.0001f + 1e-6f;
-    out->ax = sx;
-    out->ay = sy;
-    out->az = sz;
-    out->ca = cosa - 0.00196f * sina;
-    out->sa = 1.002f * sina;
-    return true;
-}
-
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // direction of sample ray j (0..29: light j / 10, sample j % 10) in a per-thread bundle with `ls` floats per light
@@ -1071,8 +1026,9 @@ __device__ __forceinline__ v3 load_dir(const float* __restrict__ dirs, int ls, i
     return mk(d[0], d[1], d[2]);
 }
 
-// cone_of10: the same cone (axis.xyz, min_j axis.D_j) from a 16-byte aligned bundle of 10 directions, loaded once as
-// vectors and reduced from registers; w = -1 for a degenerate bundle.  One out-of-line copy for all lights.
+// cone_of10: cone of one light's 10 sample directions: axis = normalised sum, w = min_j axis.D_j, from a
+// 16-byte aligned bundle loaded once as vectors and reduced from registers; w = -1 for a degenerate bundle (zero-length
+// or non-unit direction).  One out-of-line copy for all lights.
 __device__ __noinline__ float4 cone_of10(const float* __restrict__ d /* 32 floats, 30 used */) {
     const float4* __restrict__ d4 = reinterpret_cast<const float4*>(d);
     float v[32];
@@ -1106,68 +1062,6 @@ __device__ __noinline__ float4 cone_of10(const float* __restrict__ d /* 32 float
         cmin = fminf(cmin, fmaf(sx, v[3 * j], fmaf(sy, v[3 * j + 1], sz * v[3 * j + 2])));
     }
     return make_float4(sx, sy, sz, ok ? cmin : -1.f);
-}
-
-// warp beam of one light over the lanes with part == true.  Called by all 32 lanes.
-// ok == false: the lane axes disagree wildly (no warp-level culling); none == true: no lane takes part.
-struct Beam {
-    float ax, ay, az, tan_a, k1, k2;
-    bool ok, none;
-};
-__device__ __noinline__ Beam warp_beam(bool part, float Ax, float Ay, float Az, float ca, float sa, float ex, float ey,
-                                       float ez, float escale) {
-    float sx = part ? Ax : 0.f, sy = part ? Ay : 0.f, sz = part ? Az : 0.f;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        sx += __shfl_xor_sync(0xffffffffu, sx, d);
-        sy += __shfl_xor_sync(0xffffffffu, sy, d);
-        sz += __shfl_xor_sync(0xffffffffu, sz, d);
-    }
-    const float n2 = fmaf(sx, sx, fmaf(sy, sy, sz * sz));
-    const float inv = rsqrtf(fmaxf(n2, 1e-30f));
-    sx *= inv;
-    sy *= inv;
-    sz *= inv;
-    // widest angle between the warp axis and any participating ray: theta_lane + a_lane
-    float cw = 1.f, amin = 3e38f, rp = 0.f;
-    if (part) {
-        const float sina = sa * (1.f / 1.002f);
-        const float cosa = ca + 0.00196f * sina;
-        const float c1 = fminf(1.f, fmaf(sx, Ax, fmaf(sy, Ay, sz * Az)));
-        const float s1 = sqrtf(fmaxf(0.f, fmaf(-c1, c1, 1.f))) + 1e-6f;
-        cw = fmaf(c1, cosa, -(s1 * sina)) - 2e-6f;
-        const float ai = fmaf(ex, sx, fmaf(ey, sy, ez * sz));  // axial offset of this origin
-        const float px = ex - ai * sx, py = ey - ai * sy, pz = ez - ai * sz;
-        amin = ai;
-        rp = sqrtf(fmaf(px, px, fmaf(py, py, pz * pz)));
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        cw = fminf(cw, __shfl_xor_sync(0xffffffffu, cw, d));
-        amin = fminf(amin, __shfl_xor_sync(0xffffffffu, amin, d));
-        rp = fmaxf(rp, __shfl_xor_sync(0xffffffffu, rp, d));
-    }
-    Beam b;
-    b.none = !__any_sync(0xffffffffu, part);
-    b.ok = true;
-    b.ax = b.ay = b.az = 0.f;
-    b.tan_a = 0.f;
-    b.k1 = -3e38f;  // u = sc + R' + k1 < 0: never a candidate
-    b.k2 = 0.f;
-    if (!b.none) {
-        if (!(n2 > 1e-12f) || !(cw > 0.3f)) {
-            b.ok = false;
-        } else {
-            const float sinw = sqrtf(fmaxf(0.f, fmaf(-cw, cw, 1.f))) * 1.0001f + 1e-6f;
-            b.ax = sx;
-            b.ay = sy;
-            b.az = sz;
-            b.tan_a = sinw / cw * 1.0001f;
-            b.k1 = -(amin - escale);
-            b.k2 = rp * 1.0001f + escale;
-        }
-    }
-    return b;
 }
 
 // ------------------------------------------------------------------------------------
