@@ -12,6 +12,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <algorithm>
+#include <utility>
 #include <vector>
 
 #include "../../include/ore_render.h"
@@ -82,9 +84,15 @@ struct ore_context {
     uint32_t* pixels = nullptr;
     size_t px_cap = 0;
     unsigned long long* counters = nullptr;
+    float4* sph_sort = nullptr;   // shadow records in Morton order, clusters of 32 (beam kernel sweep)
+    float4* sph_xsort = nullptr;  // exact records in the same order
+    float4* clu_sph = nullptr;    // bounding sphere per cluster
+    size_t sort_cap = 0, clu_cap = 0;
+    int n_clusters = 0;
     float* stage = nullptr;  // staging buffer between the two kernels of the default shadow pass
     size_t stage_cap = 0;    // floats
     size_t stage_blocks_override = 0;  // test hook (env ORE_STAGE_BLOCKS at ore_create): staging capacity in 32-item blocks
+    bool stage_always = false;         // test hook (env ORE_STAGE_ALWAYS=1): two-stage pass also for non-resident scenes
 
     // last frame
     size_t last_px = 0;
@@ -160,6 +168,7 @@ extern "C" int ore_create(ore_context** out, int device) {
         ORE_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
     }
     for (int i = 0; i < 5; i++) ORE_CUDA(ctx, cudaEventCreate(&ctx->ev[i]));
+    if (const char* e = getenv("ORE_STAGE_ALWAYS")) ctx->stage_always = atoi(e) != 0;
     if (const char* e = getenv("ORE_STAGE_BLOCKS")) {
         const long v = atol(e);
         if (v > 0) ctx->stage_blocks_override = (size_t)v;
@@ -200,7 +209,7 @@ extern "C" int ore_destroy(ore_context* ctx) {
     }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->pixels_b) cudaFree(ctx->pixels_b);
-    void* dev[] = {ctx->stage, ctx->sph_exact, ctx->sph_prim, ctx->sph_cone, ctx->sph_shad, ctx->tex[0], ctx->tex[1], ctx->tex[2],
+    void* dev[] = {ctx->stage, ctx->sph_sort, ctx->sph_xsort, ctx->clu_sph, ctx->sph_exact, ctx->sph_prim, ctx->sph_cone, ctx->sph_shad, ctx->tex[0], ctx->tex[1], ctx->tex[2],
                    ctx->sky[0],    ctx->sky[1],   ctx->sky[2],   ctx->dx_tab, ctx->dy_tab, ctx->hit_id,
                    ctx->hit_t,     ctx->hit_list, ctx->pixels,   ctx->counters, ctx->cubes,   ctx->planes,   ctx->tris,
                    ctx->boxes,     ctx->box_offsets, ctx->box_indices, ctx->box_sph, ctx->box_cone};
@@ -215,6 +224,90 @@ extern "C" int ore_destroy(ore_context* ctx) {
 }
 
 // ---- scene upload -----------------------------------------------------------------------
+
+// Shadow-sweep clusters: the spheres in Morton order of their centres, 32 per cluster, one bounding sphere per
+// cluster.  The any-hit result does not depend on the order spheres are visited in, so the beam kernel walks clusters
+// first (one per lane) and only opens the ones its beams can touch.  ex/sh: the records just uploaded (pinned staging).
+static int upload_clusters(ore_context* ctx, const float4* ex, const float4* sh, int n) {
+    const int n_clu = (n + 31) / 32;
+    ctx->n_clusters = n_clu;
+    if (n_clu == 0) return ORE_OK;
+    const size_t n_sort = (size_t)n_clu * 32, n_clu_pad = ((size_t)n_clu + 3) & ~(size_t)3;
+    int rc;
+    size_t c1 = ctx->sort_cap, c2 = ctx->sort_cap;
+    if ((rc = ensure_dev(ctx, &ctx->sph_sort, &c1, n_sort))) return rc;
+    if ((rc = ensure_dev(ctx, &ctx->sph_xsort, &c2, n_sort))) return rc;
+    ctx->sort_cap = c1 < c2 ? c1 : c2;
+    if ((rc = ensure_dev(ctx, &ctx->clu_sph, &ctx->clu_cap, n_clu_pad))) return rc;
+
+    // Morton keys (10 bits per axis) over the bounding box of the finite centres
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    auto fin = [](float v) { return std::isfinite(v) && std::fabs(v) < 1e15f; };
+    for (int i = 0; i < n; i++) {
+        const float c[3] = {sh[i].x, sh[i].y, sh[i].z};
+        for (int k = 0; k < 3; k++)
+            if (fin(c[k])) {
+                lo[k] = std::min(lo[k], (double)c[k]);
+                hi[k] = std::max(hi[k], (double)c[k]);
+            }
+    }
+    auto spread = [](uint32_t v) {
+        v &= 1023u;
+        v = (v | (v << 16)) & 0x030000FFu;
+        v = (v | (v << 8)) & 0x0300F00Fu;
+        v = (v | (v << 4)) & 0x030C30C3u;
+        v = (v | (v << 2)) & 0x09249249u;
+        return v;
+    };
+    std::vector<std::pair<uint32_t, int>> order((size_t)n);
+    for (int i = 0; i < n; i++) {
+        const float c[3] = {sh[i].x, sh[i].y, sh[i].z};
+        uint32_t q[3];
+        for (int k = 0; k < 3; k++) {
+            double t = 0.0;
+            if (fin(c[k]) && hi[k] > lo[k]) t = ((double)c[k] - lo[k]) / (hi[k] - lo[k]);
+            q[k] = (uint32_t)std::min(1023.0, std::max(0.0, t * 1023.0));
+        }
+        order[(size_t)i] = {spread(q[0]) | (spread(q[1]) << 1) | (spread(q[2]) << 2), i};
+    }
+    std::stable_sort(order.begin(), order.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+
+    std::vector<float4> ss(n_sort), xs(n_sort), cl(n_clu_pad);
+    for (size_t p = 0; p < n_sort; p++) {
+        const int i = order[p < (size_t)n ? p : (size_t)n - 1].second;  // tail padding = copies (never read: index >= n)
+        ss[p] = sh[i];
+        xs[p] = ex[i];
+    }
+    for (size_t j = 0; j < n_clu_pad; j++) {
+        if (j >= (size_t)n_clu) {
+            cl[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            continue;
+        }
+        const size_t p0 = j * 32, p1 = std::min(p0 + 32, (size_t)n);
+        double cx = 0, cy = 0, cz = 0;
+        bool tame = true;
+        for (size_t p = p0; p < p1; p++) {
+            tame = tame && fin(ss[p].x) && fin(ss[p].y) && fin(ss[p].z) && fin(ss[p].w);
+            cx += ss[p].x;
+            cy += ss[p].y;
+            cz += ss[p].z;
+        }
+        const double m = (double)(p1 - p0);
+        const float fx = (float)(cx / m), fy = (float)(cy / m), fz = (float)(cz / m);
+        double rad = 0;
+        for (size_t p = p0; p < p1 && tame; p++) {
+            const double dx = (double)ss[p].x - fx, dy = (double)ss[p].y - fy, dz = (double)ss[p].z - fz;
+            rad = std::max(rad, std::sqrt(dx * dx + dy * dy + dz * dz) + (double)ss[p].w);
+        }
+        float fr = INFINITY;  // "always a candidate": a member the float tests cannot bound
+        if (tame && std::isfinite(rad) && rad < 1e15) fr = nextafterf((float)(rad * (1.0 + 1e-6) + 1e-30), INFINITY);
+        cl[j] = make_float4(fx, fy, fz, fr);
+    }
+    ORE_CUDA(ctx, cudaMemcpy(ctx->sph_sort, ss.data(), n_sort * sizeof(float4), cudaMemcpyHostToDevice));
+    ORE_CUDA(ctx, cudaMemcpy(ctx->sph_xsort, xs.data(), n_sort * sizeof(float4), cudaMemcpyHostToDevice));
+    ORE_CUDA(ctx, cudaMemcpy(ctx->clu_sph, cl.data(), n_clu_pad * sizeof(float4), cudaMemcpyHostToDevice));
+    return ORE_OK;
+}
 
 static int upload_spheres(ore_context* ctx, const float* src, size_t stride_floats, size_t first, int32_t n) {
     if (!ctx || n < 0 || (n > 0 && !src)) return fail(ctx, ORE_ERR_INVALID, "ore_set_spheres: bad arguments");
@@ -254,7 +347,7 @@ static int upload_spheres(ore_context* ctx, const float* src, size_t stride_floa
     ORE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->n_spheres = n;
     ctx->n_spheres_pad = n_pad;
-    return ORE_OK;
+    return upload_clusters(ctx, ex, sh, n);
 }
 
 extern "C" int ore_set_spheres(ore_context* ctx, const float* xyz_radius, int32_t n) {
@@ -581,6 +674,12 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
     prm.sph_prim = ctx->sph_prim;
     prm.sph_cone = ctx->sph_cone;
     prm.sph_shad = ctx->sph_shad;
+    prm.sph_sort = ctx->sph_sort;
+    prm.sph_xsort = ctx->sph_xsort;
+    prm.clu_sph = ctx->clu_sph;
+    prm.n_clusters = ctx->n_clusters;
+    const size_t beam_bytes = ((size_t)ctx->n_clusters * 32 + (((size_t)ctx->n_clusters + 3) & ~(size_t)3)) * sizeof(float4);
+    prm.beam_resident = (ctx->n_clusters > 0 && beam_bytes <= RESIDENT_BYTES) ? 1 : 0;
     prm.tex_r = ctx->tex[0];
     prm.tex_g = ctx->tex[1];
     prm.tex_b = ctx->tex[2];
@@ -668,7 +767,7 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
     } while (0)
         if (warp_cull) {
             // the beam kernel stages the whole record array (resident) or reads it through L1/L2: no ring
-            const size_t bsmem = prm.resident ? (size_t)ctx->n_spheres_pad * sizeof(float4) : 0;
+            const size_t bsmem = prm.beam_resident ? beam_bytes : 0;
             // Two-stage pass (default): shade_setup_kernel -> staging buffer -> staged shadow_beam_kernel, in chunks
             // of the hit list that fit the staging buffer.  The host does not know the hit count (no sync), so the
             // chunk count comes from the pixel count; kernels of chunks past the end of the hit list exit at once.
@@ -679,7 +778,7 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
             // Scenes whose sphere records do not fit in shared memory sweep them through L1; that sweep is bound
             // by L1 bandwidth and the fused kernel hides the set-up arithmetic under it, so it stays the better
             // choice there (4K / 16384 spheres: 8.1 ms fused, 10.3 ms two-stage; 8K / 1024: 4.5 vs 3.7 ms).
-            bool staged = !(fr->flags & ORE_FLAG_FUSED_SHADOW) && prm.resident;
+            bool staged = !(fr->flags & ORE_FLAG_FUSED_SHADOW) && (prm.beam_resident || ctx->stage_always);
             if (staged) {
                 size_t want_items = n_px / 4 > ((size_t)1 << 20) ? n_px / 4 : ((size_t)1 << 20);
                 if (want_items > ((size_t)16 << 20)) want_items = (size_t)16 << 20;

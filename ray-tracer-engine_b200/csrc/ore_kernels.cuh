@@ -101,6 +101,12 @@ struct FrameParams {
     float tile_ca, tile_sa;   // cos/sin of the largest pixel-tile half-angle (+ margins), host-computed
     float px_delta;           // image-plane pixel pitch 2*aspect/width
     const float4* sph_shad;   // cx,cy,cz,R' = effective radius rounded up: R'^2 >= (1+k)*radius^2 (shadow filter)
+    // the same records in Morton order of the centres, in clusters of 32 with one bounding sphere per cluster
+    // (shadow sweep of the beam kernel: any-hit is order-free); sph_xsort = the exact records in that order
+    const float4* sph_sort;
+    const float4* sph_xsort;
+    const float4* clu_sph;    // cx,cy,cz,radius of cluster j = spheres [32j, 32j+32) of sph_sort; radius >= 1e18: always a candidate
+    int n_clusters, beam_resident;
     const float *tex_r, *tex_g, *tex_b;
     int tex_w, tex_h;
     const float *sky_r, *sky_g, *sky_b;
@@ -1589,6 +1595,29 @@ __global__ void __launch_bounds__(CTA_THREADS, ORE_STAGE_A_MIN_CTAS) shade_setup
     }
 }
 
+// beam_may_touch: can any ray of the warp's (up to three) beams touch the ball q = (centre, radius)?  (DESIGN.md 2.4;
+// used for single spheres and for the bounding spheres of 32-sphere clusters.)  bx,by,bz = centroid of the group's
+// origins; per light: axis wA*, tan of the beam half-angle, k1 = -a_min, k2 = rho_perp.  A radius >= 1e18 (or NaN)
+// means "always".
+__device__ __forceinline__ bool beam_may_touch(const float4 q, float bx, float by, float bz, const float (&wAx)[3],
+                                               const float (&wAy)[3], const float (&wAz)[3], const float (&wtan)[3],
+                                               const float (&wk1)[3], const float (&wk2)[3], bool wforce) {
+    const float Lx = bx - q.x, Ly = by - q.y, Lz = bz - q.z;
+    const float LL = fmaf(Lz, Lz, fmaf(Ly, Ly, Lx * Lx));
+    const float Rq = fmaf(q.w, 1.0001f, fmaf(LL, 1e-12f, 1e-6f));  // radius + rounding slack
+    const float slack = LL * 2e-6f;                                 // cancellation in LL - sc^2
+    bool wc = wforce || !(q.w < 1e18f);
+#pragma unroll
+    for (int l = 0; l < 3; l++) {
+        const float sc = -fmaf(wAx[l], Lx, fmaf(wAy[l], Ly, wAz[l] * Lz));  // centre's axial coordinate
+        const float u = sc + Rq + wk1[l];                                     // >= 0 unless wholly behind
+        const float thr = fmaf(u, wtan[l], Rq + wk2[l]);
+        const float d2 = fmaf(-sc, sc, LL);
+        wc = wc || (u >= 0.f && d2 <= fmaf(thr, thr, slack));
+    }
+    return wc;
+}
+
 // ------------------------------------------------------------------------------------
 // shadow_beam_kernel (default shadow path)
 //
@@ -1614,8 +1643,10 @@ __global__ void __launch_bounds__(CTA_THREADS, ORE_BEAM_MIN_CTAS) shadow_beam_ke
     // Sphere records (cx,cy,cz,R'): the whole array is staged once per CTA into shared memory by one
     // TMA bulk copy when it fits; larger scenes are read through L1/L2 (256 KiB for 16384 spheres).
     // Either way warps run independently: each fetches 32 consecutive hit pixels at a time.
-    const float4* __restrict__ spheres = prm.sph_shad;
-    if (prm.resident) {
+    const float4* __restrict__ spheres = prm.sph_sort;
+    const float4* __restrict__ clusters = prm.clu_sph;
+    const int n_clu = prm.n_clusters;
+    if (prm.beam_resident) {
         float4* slot = reinterpret_cast<float4*>(smem_raw);
         if (tid == 0) {
             mbar_init(&bars[0], 1);
@@ -1623,12 +1654,14 @@ __global__ void __launch_bounds__(CTA_THREADS, ORE_BEAM_MIN_CTAS) shadow_beam_ke
         }
         __syncthreads();
         if (tid == 0) {
-            const uint32_t bytes = (uint32_t)prm.n_spheres_pad * 16u;
-            mbar_expect_tx(&bars[0], bytes);
-            tma_bulk_g2s(slot, prm.sph_shad, bytes, &bars[0]);
+            const uint32_t sbytes = (uint32_t)n_clu * 32u * 16u, cbytes = (uint32_t)((n_clu + 3) & ~3) * 16u;
+            mbar_expect_tx(&bars[0], sbytes + cbytes);
+            tma_bulk_g2s(slot, prm.sph_sort, sbytes, &bars[0]);
+            tma_bulk_g2s(slot + (size_t)n_clu * 32, prm.clu_sph, cbytes, &bars[0]);
         }
         mbar_wait(&bars[0], 0);
         spheres = slot;
+        clusters = slot + (size_t)n_clu * 32;
     }
     const int n_sph = prm.n_spheres;
 
@@ -1840,37 +1873,20 @@ __global__ void __launch_bounds__(CTA_THREADS, ORE_BEAM_MIN_CTAS) shadow_beam_ke
 
                 bool warp_done = false;
     #pragma unroll 1
-                for (int s0 = 0; s0 < n_sph && !warp_done; s0 += 64) {
-                    // ---- level 1: lane i tests spheres s0+i and s0+32+i against the warp's beams (two independent
-                    //      chains per lane) ----
-                    uint32_t wm2[2];
-    #pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        const bool in = s0 + 32 * h + lane < n_sph;
-                        bool wc = false;
-                        if (in) {
-                            const float4 q = spheres[s0 + 32 * h + lane];
-                            const float Lx = bx - q.x, Ly = by - q.y, Lz = bz - q.z;
-                            const float LL = fmaf(Lz, Lz, fmaf(Ly, Ly, Lx * Lx));
-                            const float Rq = fmaf(q.w, 1.0001f, fmaf(LL, 1e-12f, 1e-6f));  // radius + rounding slack
-                            const float slack = LL * 2e-6f;                                 // cancellation in LL - sc^2
-    #pragma unroll
-                            for (int l = 0; l < NL; l++) {
-                                const float sc = -fmaf(wAx[l], Lx, fmaf(wAy[l], Ly, wAz[l] * Lz));  // centre's axial coordinate
-                                const float u = sc + Rq + wk1[l];                                     // >= 0 unless wholly behind
-                                const float thr = fmaf(u, wtan[l], Rq + wk2[l]);
-                                const float d2 = fmaf(-sc, sc, LL);
-                                wc = wc || (u >= 0.f && d2 <= fmaf(thr, thr, slack));
-                            }
-                            wc = wc || wforce;
-                        }
-                        wm2[h] = __ballot_sync(0xffffffffu, wc);
-                    }
-                    unsigned long long wmask = (unsigned long long)wm2[0] | ((unsigned long long)wm2[1] << 32);
-                    n_l1 += __popcll(wmask);
+                for (int c0 = 0; c0 < n_clu && !warp_done; c0 += 32) {
+                    // ---- level 0: lane i tests the bounding sphere of cluster c0+i (32 spheres) against the beams ----
+                    uint32_t cmask = __ballot_sync(0xffffffffu, c0 + lane < n_clu &&
+                                                   beam_may_touch(clusters[min(c0 + lane, n_clu - 1)], bx, by, bz, wAx, wAy, wAz, wtan, wk1, wk2, wforce));
+                  while (cmask && !warp_done) {
+                    const int s0 = (c0 + __ffs(cmask) - 1) * 32;
+                    cmask &= cmask - 1;
+                    // ---- level 1: lane i tests sphere s0+i of that cluster ----
+                    uint32_t wmask = __ballot_sync(0xffffffffu, s0 + lane < n_sph &&
+                                                   beam_may_touch(spheres[s0 + lane], bx, by, bz, wAx, wAy, wAz, wtan, wk1, wk2, wforce));
+                    n_l1 += __popc(wmask);
                     // ---- level 2: every lane runs its own cone test on the surviving spheres ----
                     while (wmask) {
-                        const int i = __ffsll((long long)wmask) - 1;
+                        const int i = __ffs(wmask) - 1;
                         wmask &= wmask - 1;
                         const int s = s0 + i;
                         const float4 q = spheres[s];
@@ -1891,7 +1907,7 @@ __global__ void __launch_bounds__(CTA_THREADS, ORE_BEAM_MIN_CTAS) shadow_beam_ke
                         }
                         if (live) {
                             n_l2++;
-                            const float4 ex4 = __ldg(&prm.sph_exact[s]);
+                            const float4 ex4 = __ldg(&prm.sph_xsort[s]);
                             // per-ray filter h = D.L + s' < 0 on all 10 rays of each live light at once
                             // (independent loads and FMAs), then the exact sequence on the few that pass
                             // "Sure hit" (DESIGN.md 2.5): sphere::intersect returns true whenever its discriminant is
@@ -1963,6 +1979,7 @@ __global__ void __launch_bounds__(CTA_THREADS, ORE_BEAM_MIN_CTAS) shadow_beam_ke
                         }
                     }
                     if (__all_sync(0xffffffffu, !ing || blocked == ALL)) warp_done = true;
+                  }
                 }
 
             }
