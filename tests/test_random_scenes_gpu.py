@@ -75,3 +75,37 @@ def test_random_scenes_match_the_oracle(seed, renderer, oracle_best, pkg):
     for sh in (0, 8, 16):
         d = np.maximum(d, np.abs(((px >> sh) & 255).astype(np.int32) - ((ref["pixels"] >> sh) & 255).astype(np.int32)))
     assert np.count_nonzero(d <= 1) / d.size >= 0.999
+
+
+@pytest.mark.parametrize("seed", [0, 1, 3, 13, 29])
+def test_untame_spheres_do_not_hide_their_cluster_neighbours(seed, renderer, oracle_best, pkg):
+    """the shadow sweep walks 32-sphere clusters through one bounding sphere each; a member with huge, infinite or
+    NaN coordinates / radius makes its cluster 'always open' instead of poisoning the bound - the frame must still
+    equal the exhaustive mode's (and the oracle's)"""
+    sc, cam = random_scene(pkg, seed)
+    rng = np.random.default_rng(1000 + seed)
+    sp = np.repeat(sc.spheres, 2, axis=0)[: max(40, len(sc.spheres))].copy()     # at least two clusters
+    sp[:, :3] += rng.uniform(-0.5, 0.5, size=sp[:, :3].shape).astype(np.float32)
+    # (none of these is ever hit: the reference's own arithmetic overflows or goes NaN on them)
+    weird = [(1e17, 0, 0, 1.0), (0, -3e19, 0, 1e10), (np.inf, 0, 0, 1.0), (-np.inf, np.inf, 0, 2.0), (np.nan, 1, 1, 0.5),
+             (1, 1, 1, np.nan), (5e15, 5e15, 5e15, 1e3)]
+    for k, w in enumerate(weird):
+        sp[(k * 5 + seed) % len(sp)] = np.array(w, dtype=np.float32)
+    sc2 = pkg.scene.Scene(spheres=np.ascontiguousarray(sp), lights=sc.lights, texture=sc.texture, sky=sc.sky,
+                          extent=sc.extent, name=f"untame{seed}")
+    renderer.set_scene(sc2)
+    W, H = 72, 44
+    a = renderer.render(cam, W, H)
+    ia, ta = renderer.hits(H, W)
+    b = renderer.render(cam, W, H, flags=pkg.capi.ORE_FLAG_EXHAUSTIVE)
+    ib, tb = renderer.hits(H, W)
+    assert np.array_equal(ia, ib) and np.array_equal(ta.view(np.uint32), tb.view(np.uint32))
+    assert np.array_equal(a, b), int(np.count_nonzero(a != b))
+    c = renderer.render(cam, W, H, flags=pkg.capi.ORE_FLAG_FUSED_SHADOW)
+    assert np.array_equal(a, c)
+    ref = oracle_best.render(sc2, cam, W, H)
+    assert np.array_equal(ia, ref["ids"]) and np.array_equal(ta.view(np.uint32), ref["t"].view(np.uint32))
+    d = np.zeros(a.shape, dtype=np.int32)
+    for sh in (0, 8, 16):
+        d = np.maximum(d, np.abs(((a >> sh) & 255).astype(np.int32) - ((ref["pixels"] >> sh) & 255).astype(np.int32)))
+    assert np.count_nonzero(d <= 1) >= 0.999 * d.size
