@@ -1916,8 +1916,9 @@ __global__ void __launch_bounds__(CTA_THREADS, ORE_BEAM_MIN_CTAS) shadow_beam_ke
                             // float discriminant positive (its rounding error is below 7e-6 |L|^2) and b^2 >
                             // 1e-6 |L|^2 + 1e-6 keeps the far root above 9e-4: the ray is blocked without running
                             // the exact sequence.  Everything in between is re-adjudicated exactly as before.
+                            // (disabled = +inf, not a large finite number: b*b is +inf for a sphere at infinity)
                             const float sure_thr = (EXH || force)
-                                                       ? ORE_BIG
+                                                       ? INFINITY
                                                        : fmaxf(fmaf(LL, 1e-6f, 1e-6f), fmaf(LL, 2e-5f, fmaf(-ex4.w, ex4.w, LL)));
                             uint32_t cand = 0;
 #pragma unroll 1
