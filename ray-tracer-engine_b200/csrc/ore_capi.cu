@@ -25,8 +25,8 @@ using namespace ore;
 extern "C" int ore_fast_set_tables(const float* cphi, const float* sphi, const float* bk);
 extern "C" int ore_fast_primary_tile(const void* prm, int sm_count, size_t smem, long long n_batches, int exh,
                                      cudaStream_t stream);
-// stage: a StageArgs of identical layout, or null for the fused kernel
-extern "C" int ore_fast_shadow_beam(const void* prm, const void* stage, int sm_count, size_t smem, int exh,
+// stage: a StageArgs of identical layout; staged = 0 selects the fused kernel (only first_block is used then)
+extern "C" int ore_fast_shadow_beam(const void* prm, const void* stage, int staged, int sm_count, size_t smem, int exh,
                                     cudaStream_t stream);
 extern "C" int ore_fast_shade_setup(const void* prm, const void* stage, int sm_count, cudaStream_t stream);
 
@@ -93,6 +93,11 @@ struct ore_context {
     size_t stage_cap = 0;    // floats
     size_t stage_blocks_override = 0;  // test hook (env ORE_STAGE_BLOCKS at ore_create): staging capacity in 32-item blocks
     bool stage_always = false;         // test hook (env ORE_STAGE_ALWAYS=1): two-stage pass also for non-resident scenes
+    // hit count of this context's previous frame, copied to pinned memory at the end of every frame and read
+    // WITHOUT synchronisation by the next one: only a hint for how many staged chunk pairs to launch - whatever
+    // lies beyond them is swept by one catch-all fused launch, so any value (stale, zero, mid-copy) is safe
+    unsigned long long* hits_hint = nullptr;
+    bool hits_hint_set = false;
 
     // last frame
     size_t last_px = 0;
@@ -168,6 +173,8 @@ extern "C" int ore_create(ore_context** out, int device) {
         ORE_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
     }
     for (int i = 0; i < 5; i++) ORE_CUDA(ctx, cudaEventCreate(&ctx->ev[i]));
+    ORE_CUDA(ctx, cudaMallocHost((void**)&ctx->hits_hint, sizeof(unsigned long long)));
+    *ctx->hits_hint = 0;
     if (const char* e = getenv("ORE_STAGE_ALWAYS")) ctx->stage_always = atoi(e) != 0;
     if (const char* e = getenv("ORE_STAGE_BLOCKS")) {
         const long v = atol(e);
@@ -216,6 +223,7 @@ extern "C" int ore_destroy(ore_context* ctx) {
     for (void* p : dev)
         if (p) cudaFree(p);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->hits_hint) cudaFreeHost(ctx->hits_hint);
     for (int i = 0; i < 5; i++)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -802,7 +810,7 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
             }
             if (!staged) {
                 if (fast_libm) {
-                    ORE_CUDA(ctx, (cudaError_t)ore_fast_shadow_beam(&prm, nullptr, ctx->sm_count, bsmem, exh ? 1 : 0, stream));
+                    ORE_CUDA(ctx, (cudaError_t)ore_fast_shadow_beam(&prm, &st, 0, ctx->sm_count, bsmem, exh ? 1 : 0, stream));
                 } else if (exh) {
                     if ((rc = grid_for(ctx, shadow_beam_kernel<true, false>, bsmem, &grid))) return rc;
                     shadow_beam_kernel<true, false><<<grid, CTA_THREADS, bsmem, stream>>>(prm, st);
@@ -813,7 +821,15 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
             } else {
                 st.buf = ctx->stage;
                 st.cap_blocks = (uint32_t)cap_blocks;
-                const int n_chunks = (int)((n_blocks_px + cap_blocks - 1) / cap_blocks);
+                const int n_chunks_max = (int)((n_blocks_px + cap_blocks - 1) / cap_blocks);
+                int n_chunks = n_chunks_max;
+                if (ctx->hits_hint_set) {
+                    // previous frame's hit count + 25 % + 64 K items; the catch-all below covers a wrong guess
+                    const unsigned long long h = *(volatile unsigned long long*)ctx->hits_hint;
+                    const unsigned long long est_blocks = (h + h / 4 + 65536ull + 31ull) / 32ull;
+                    const unsigned long long want = (est_blocks + cap_blocks - 1) / cap_blocks;
+                    if (want < (unsigned long long)n_chunks_max) n_chunks = want < 1 ? 1 : (int)want;
+                }
                 int grid_a = 0, grid_b = 0;
                 if (!fast_libm) {
                     if ((rc = grid_for(ctx, shade_setup_kernel, 0, &grid_a))) return rc;
@@ -821,12 +837,29 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
                     else rc = grid_for(ctx, shadow_beam_kernel<false, true>, bsmem, &grid_b);
                     if (rc) return rc;
                 }
+                if (n_chunks < n_chunks_max) {
+                    // catch-all: hit-list blocks beyond the staged chunks (normally none: exits at once), one fused launch
+                    StageArgs rest{};
+                    rest.first_block = (uint32_t)((size_t)n_chunks * cap_blocks);
+                    rest.nv = st.nv;
+                    if (fast_libm) {
+                        ORE_CUDA(ctx, (cudaError_t)ore_fast_shadow_beam(&prm, &rest, 0, ctx->sm_count, bsmem, exh ? 1 : 0, stream));
+                    } else if (exh) {
+                        if ((rc = grid_for(ctx, shadow_beam_kernel<true, false>, bsmem, &grid))) return rc;
+                        shadow_beam_kernel<true, false><<<grid, CTA_THREADS, bsmem, stream>>>(prm, rest);
+                    } else {
+                        if ((rc = grid_for(ctx, shadow_beam_kernel<false, false>, bsmem, &grid))) return rc;
+                        shadow_beam_kernel<false, false><<<grid, CTA_THREADS, bsmem, stream>>>(prm, rest);
+                    }
+                    ORE_CUDA(ctx, cudaGetLastError());
+                    ctx->last_launches++;
+                }
                 for (int c = 0; c < n_chunks; c++) {
                     st.chunk = c;
                     st.first_block = (uint32_t)((size_t)c * cap_blocks);
                     if (fast_libm) {
                         ORE_CUDA(ctx, (cudaError_t)ore_fast_shade_setup(&prm, &st, ctx->sm_count, stream));
-                        ORE_CUDA(ctx, (cudaError_t)ore_fast_shadow_beam(&prm, &st, ctx->sm_count, bsmem, exh ? 1 : 0, stream));
+                        ORE_CUDA(ctx, (cudaError_t)ore_fast_shadow_beam(&prm, &st, 1, ctx->sm_count, bsmem, exh ? 1 : 0, stream));
                     } else {
                         shade_setup_kernel<<<grid_a, CTA_THREADS, 0, stream>>>(prm, st);
                         if (exh) shadow_beam_kernel<true, true><<<grid_b, CTA_THREADS, bsmem, stream>>>(prm, st);
@@ -856,6 +889,10 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
         ctx->last_launches++;
     }
     ORE_CUDA(ctx, cudaEventRecord(ctx->ev[3], stream));
+    // hint for the next frame of this context (see hits_hint): 8 bytes, no synchronisation
+    ORE_CUDA(ctx, cudaMemcpyAsync(ctx->hits_hint, ctx->counters + CNT_HITS, sizeof(unsigned long long),
+                                  cudaMemcpyDeviceToHost, stream));
+    ctx->hits_hint_set = true;
     if (fr->flags & ORE_FLAG_COUNT_REFERENCE_TESTS) {
         count_reference_tests_kernel<<<ctx->sm_count * 8, CTA_THREADS, 0, stream>>>(prm);
         ORE_CUDA(ctx, cudaGetLastError());

@@ -39,15 +39,13 @@ extern "C" ORE_HIDDEN int ore_fast_primary_tile(const void* prm, int sm_count, s
     return (int)(exh ? launch(ore_fast::primary_tile_kernel<ore_fast::TILE_P, true>, sm_count, smem, n_batches, stream, p)
                      : launch(ore_fast::primary_tile_kernel<ore_fast::TILE_P, false>, sm_count, smem, n_batches, stream, p));
 }
-extern "C" ORE_HIDDEN int ore_fast_shadow_beam(const void* prm, const void* stage, int sm_count, size_t smem, int exh,
-                                              cudaStream_t stream) {
+extern "C" ORE_HIDDEN int ore_fast_shadow_beam(const void* prm, const void* stage, int staged, int sm_count, size_t smem,
+                                              int exh, cudaStream_t stream) {
     const ore_fast::FrameParams& p = *static_cast<const ore_fast::FrameParams*>(prm);
-    if (!stage) {
-        const ore_fast::StageArgs none{};
-        return (int)(exh ? launch(ore_fast::shadow_beam_kernel<true, false>, sm_count, smem, 0, stream, p, none)
-                         : launch(ore_fast::shadow_beam_kernel<false, false>, sm_count, smem, 0, stream, p, none));
-    }
     const ore_fast::StageArgs& st = *static_cast<const ore_fast::StageArgs*>(stage);
+    if (!staged)
+        return (int)(exh ? launch(ore_fast::shadow_beam_kernel<true, false>, sm_count, smem, 0, stream, p, st)
+                         : launch(ore_fast::shadow_beam_kernel<false, false>, sm_count, smem, 0, stream, p, st));
     return (int)(exh ? launch(ore_fast::shadow_beam_kernel<true, true>, sm_count, smem, 0, stream, p, st)
                      : launch(ore_fast::shadow_beam_kernel<false, true>, sm_count, smem, 0, stream, p, st));
 }

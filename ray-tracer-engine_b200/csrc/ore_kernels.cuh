@@ -1678,7 +1678,7 @@ __global__ void __launch_bounds__(CTA_THREADS, ORE_BEAM_MIN_CTAS) shadow_beam_ke
     wb = __shfl_sync(0xffffffffu, wb, 0);
     for (;; ) {
         if (STAGED && wb >= st.cap_blocks) break;
-        const uint32_t blk = STAGED ? st.first_block + wb : wb;
+        const uint32_t blk = st.first_block + wb;  // fused: 0, or the first block past the staged chunks (catch-all)
         if ((unsigned long long)blk * 32ull >= n_items) break;
         const uint32_t item = blk * 32u + lane;
         const bool valid = item < n_items;
