@@ -543,9 +543,10 @@ def main():
                     "sharded_frame_check": frame_check},
             "gpu_launches": launches_per_frame * args.steps,
             "gpu_launches_per_frame": {"count": launches_per_frame,
-                                       "kernels": "prep_frame, primary_tile, then per hit-list chunk shade_setup + shadow_beam "
-                                                  "(chunks past the end of the hit list exit at once); one fused "
-                                                  "shadow_beam instead when the sphere records exceed shared memory"},
+                                       "kernels": "prep_frame, primary_tile, one catch-all fused shadow_beam (normally empty), then per "
+                                                  "hit-list chunk shade_setup + shadow_beam (as many chunks as the previous "
+                                                  "frame's hit count suggests); one fused shadow_beam only when the sphere "
+                                                  "records exceed shared memory"},
             "roofline": {
                 "bound": "fp32", "kernel": "shadow pass = shade_setup_kernel + shadow_beam_kernel (soft-shadow any-hit + shading; default path)",
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None,
