@@ -50,3 +50,16 @@ def test_product_code_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
                 txt = open(os.path.join(base, f), errors="replace").read()
                 assert "oracle/" not in txt and "liboracle" not in txt and "oraclelib" not in txt, os.path.join(base, f)
+
+
+def test_python_flag_constants_match_the_header(pkg):
+    text = open(os.path.join(ROOT, "include", "ore_render.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    header = {k: int(v) for k, v in re.findall(r"\b(ORE_FLAG_[A-Z_]+)\s*=\s*(\d+)", text)}
+    assert len(header) >= 6
+    for name, value in header.items():
+        if name == "ORE_FLAG_NONE":
+            continue
+        assert getattr(pkg.capi, name) == value, name
+    values = [v for k, v in header.items() if k != "ORE_FLAG_NONE"]
+    assert len(set(values)) == len(values) and all(v & (v - 1) == 0 for v in values), "flags must be distinct bits"
