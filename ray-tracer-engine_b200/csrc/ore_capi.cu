@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "../../include/ore_render.h"
+#include "ore_clusters.h"
 #include "ore_kernels.cuh"
 
 using namespace ore;
@@ -248,69 +249,11 @@ static int upload_clusters(ore_context* ctx, const float4* ex, const float4* sh,
     ctx->sort_cap = c1 < c2 ? c1 : c2;
     if ((rc = ensure_dev(ctx, &ctx->clu_sph, &ctx->clu_cap, n_clu_pad))) return rc;
 
-    // Morton keys (10 bits per axis) over the bounding box of the finite centres
-    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-    auto fin = [](float v) { return std::isfinite(v) && std::fabs(v) < 1e15f; };
-    for (int i = 0; i < n; i++) {
-        const float c[3] = {sh[i].x, sh[i].y, sh[i].z};
-        for (int k = 0; k < 3; k++)
-            if (fin(c[k])) {
-                lo[k] = std::min(lo[k], (double)c[k]);
-                hi[k] = std::max(hi[k], (double)c[k]);
-            }
-    }
-    auto spread = [](uint32_t v) {
-        v &= 1023u;
-        v = (v | (v << 16)) & 0x030000FFu;
-        v = (v | (v << 8)) & 0x0300F00Fu;
-        v = (v | (v << 4)) & 0x030C30C3u;
-        v = (v | (v << 2)) & 0x09249249u;
-        return v;
-    };
-    std::vector<std::pair<uint32_t, int>> order((size_t)n);
-    for (int i = 0; i < n; i++) {
-        const float c[3] = {sh[i].x, sh[i].y, sh[i].z};
-        uint32_t q[3];
-        for (int k = 0; k < 3; k++) {
-            double t = 0.0;
-            if (fin(c[k]) && hi[k] > lo[k]) t = ((double)c[k] - lo[k]) / (hi[k] - lo[k]);
-            q[k] = (uint32_t)std::min(1023.0, std::max(0.0, t * 1023.0));
-        }
-        order[(size_t)i] = {spread(q[0]) | (spread(q[1]) << 1) | (spread(q[2]) << 2), i};
-    }
-    std::stable_sort(order.begin(), order.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
-
-    std::vector<float4> ss(n_sort), xs(n_sort), cl(n_clu_pad);
-    for (size_t p = 0; p < n_sort; p++) {
-        const int i = order[p < (size_t)n ? p : (size_t)n - 1].second;  // tail padding = copies (never read: index >= n)
-        ss[p] = sh[i];
-        xs[p] = ex[i];
-    }
-    for (size_t j = 0; j < n_clu_pad; j++) {
-        if (j >= (size_t)n_clu) {
-            cl[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            continue;
-        }
-        const size_t p0 = j * 32, p1 = std::min(p0 + 32, (size_t)n);
-        double cx = 0, cy = 0, cz = 0;
-        bool tame = true;
-        for (size_t p = p0; p < p1; p++) {
-            tame = tame && fin(ss[p].x) && fin(ss[p].y) && fin(ss[p].z) && fin(ss[p].w);
-            cx += ss[p].x;
-            cy += ss[p].y;
-            cz += ss[p].z;
-        }
-        const double m = (double)(p1 - p0);
-        const float fx = (float)(cx / m), fy = (float)(cy / m), fz = (float)(cz / m);
-        double rad = 0;
-        for (size_t p = p0; p < p1 && tame; p++) {
-            const double dx = (double)ss[p].x - fx, dy = (double)ss[p].y - fy, dz = (double)ss[p].z - fz;
-            rad = std::max(rad, std::sqrt(dx * dx + dy * dy + dz * dz) + (double)ss[p].w);
-        }
-        float fr = INFINITY;  // "always a candidate": a member the float tests cannot bound
-        if (tame && std::isfinite(rad) && rad < 1e15) fr = nextafterf((float)(rad * (1.0 + 1e-6) + 1e-30), INFINITY);
-        cl[j] = make_float4(fx, fy, fz, fr);
-    }
+    // host-only builder (csrc/ore_clusters.h, unit-tested on the CPU by tests/test_clusters_cpu.py)
+    std::vector<ore_host::Rec4> ss, xs, cl;
+    ore_host::build_clusters(reinterpret_cast<const ore_host::Rec4*>(ex), reinterpret_cast<const ore_host::Rec4*>(sh), n, ss, xs, cl);
+    static_assert(sizeof(ore_host::Rec4) == sizeof(float4), "Rec4 must have float4's layout");
+    if (ss.size() != n_sort || cl.size() != n_clu_pad) return fail(ctx, ORE_ERR_INVALID, "cluster builder size mismatch");
     ORE_CUDA(ctx, cudaMemcpy(ctx->sph_sort, ss.data(), n_sort * sizeof(float4), cudaMemcpyHostToDevice));
     ORE_CUDA(ctx, cudaMemcpy(ctx->sph_xsort, xs.data(), n_sort * sizeof(float4), cudaMemcpyHostToDevice));
     ORE_CUDA(ctx, cudaMemcpy(ctx->clu_sph, cl.data(), n_clu_pad * sizeof(float4), cudaMemcpyHostToDevice));
