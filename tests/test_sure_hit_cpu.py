@@ -85,6 +85,25 @@ def test_numpy_restatement_matches_the_c_oracle(oracle_port):
         assert np.array_equal(ref_hit(O, D, Cn, rad), want), name
 
 
+def test_numpy_restatement_matches_the_references_own_code(oracle_ref):
+    """same check against sphere::intersect of the reference itself (kernel.cu compiled for the host, oracle/_ref)"""
+    rng = np.random.default_rng(6)
+    for name, O, D, Cn, rad in families(rng, 400):
+        want = np.array([oracle_ref.sphere_intersect(O[i], D[i], Cn[i], rad[i])[0] for i in range(len(rad))])
+        assert np.array_equal(ref_hit(O, D, Cn, rad), want), name
+
+
+def test_every_sure_hit_sample_is_a_hit_of_the_references_own_code(oracle_ref):
+    rng = np.random.default_rng(7)
+    checked = 0
+    for name, O, D, Cn, rad in families(rng, 20_000):
+        idx = np.flatnonzero(sure_hit(O, D, Cn, rad))[:1500]
+        for i in idx:
+            assert oracle_ref.sphere_intersect(O[i], D[i], Cn[i], rad[i])[0], (name, int(i))
+        checked += len(idx)
+    assert checked > 3000
+
+
 @pytest.mark.parametrize("seed", [0, 1, 2])
 def test_every_sure_hit_is_a_hit_of_the_reference_sequence(seed):
     rng = np.random.default_rng(100 + seed)
