@@ -109,6 +109,34 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def issue_block(workload):
+    """Executed-instruction side of the default path's kernels, from the committed ncu summaries (profiles/): how busy
+    the issue slots and the FMA pipe are.  Static context for the line (ncu never runs inside bench.py); None when the
+    summaries are for another workload or unreadable."""
+    try:
+        if workload != "8k1024":
+            return None
+        out = {"source": "profiles/r01_ncu_{shade_setup,shadow_beam_staged,primary_tile}_8k1024.json (ncu --set full, "
+                         "one launch each, --clock-control none)", "kernels": {}}
+        for key, fn in (("shade_setup_kernel", "r01_ncu_shade_setup_8k1024.json"),
+                        ("shadow_beam_kernel (staged)", "r01_ncu_shadow_beam_staged_8k1024.json"),
+                        ("primary_tile_kernel", "r01_ncu_primary_tile_8k1024.json")):
+            m = json.load(open(os.path.join(ROOT, "profiles", fn)))["metrics"]
+
+            def num(name):
+                return float(str(m[name]).split()[0])
+
+            out["kernels"][key] = {
+                "issue_slot_utilisation": num("smsp__issue_active.avg.pct_of_peak_sustained_active") / 100.0,
+                "fma_pipe_utilisation": num("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active") / 100.0,
+                "ncu_ms": num("gpu__time_duration.sum"),
+                "registers": int(num("launch__registers_per_thread")),
+            }
+        return out
+    except Exception:
+        return None
+
+
 def hbm_block(traffic_bytes, kernel_ms):
     """DRAM side of the dominant kernel against the measured HBM peak (MEASURED_PEAKS.json, else the recipe's fallback)"""
     peak, src = 6650.0, "fallback (B200_PROFILING.md)"
@@ -559,14 +587,16 @@ def main():
                 "definition": "achieved = 18 FLOP x reference-order sphere tests of the launch / CUDA-event kernel time "
                               "(SURVEY.md 8d). The kernel reaches the reference's results with far fewer executed FLOP "
                               "(shared L/C per pixel, 3-FMA filter, per-light cone and per-warp beam tests ahead of the "
-                              "per-ray tests), so frac is an ALGORITHMIC-work rate and exceeds 1; executed-pipe "
-                              "utilisation is in profiles/ (ncu) and under per_ray_kernel.",
+                              "per-ray tests), so frac is an ALGORITHMIC-work rate and exceeds 1; executed-instruction "
+                              "utilisation of the kernels (ncu, profiles/) is under `executed`, the FP32-pipe-bound "
+                              "kernel generation under per_ray_kernel.",
                 "per_ray_kernel": (dict(per_ray, frac=per_ray["achieved"] / peak_tf) if per_ray and peak_tf else per_ray),
                 "whole_step": {"achieved": step_tf, "frac": step_tf / peak_tf if peak_tf else None,
                                "frac_of_nominal": step_tf / NOMINAL_FP32_TFLOPS},
                 "kernel_ms_all": {"prep": k_prep_ms, "primary": k_primary_ms, "shadow": k_shadow_ms},
                 "dram_write_gbs_framebuffer": W * H * 4 / world / ((k_primary_ms + k_shadow_ms) * 1e-3) / 1e9,
                 "hbm": hbm_block(traffic, k_shadow_ms),
+                "executed": issue_block(args.workload),
             },
             "cpu_baseline": cpu,
             "reference_kernel_on_b200": ref_gpu,
