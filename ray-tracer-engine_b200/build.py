@@ -13,7 +13,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libore_b200.so")
 SOURCES = ["ore_capi.cu", "ore_fast.cu"]
-HEADERS = ["ore_kernels.cuh", "ore_device.cuh", "ore_libm.cuh", os.path.join("..", "..", "include", "ore_render.h")]
+HEADERS = ["ore_kernels.cuh", "ore_device.cuh", "ore_libm.cuh", "ore_clusters.h", os.path.join("..", "..", "include", "ore_render.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
