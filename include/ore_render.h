@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define ORE_ABI_VERSION 1
+#define ORE_ABI_VERSION 2
 
 enum ore_status {
     ORE_OK = 0,
@@ -59,7 +59,10 @@ enum ore_flags {
     /* Default shadow pass as ONE kernel (shading set-up + light directions + sweep fused) instead of the two-stage
      * pass through a staging buffer.  Same results; slower (its hot code does not fit the SM instruction cache) but
      * needs no staging memory.  Also used automatically when the staging buffer cannot be allocated. */
-    ORE_FLAG_FUSED_SHADOW = 32
+    ORE_FLAG_FUSED_SHADOW = 32,
+    /* Do not record the per-kernel CUDA events behind ore_get_kernel_ms for this call (five event records per
+     * frame; throughput loops set this, ore_get_kernel_ms then reports zeros). */
+    ORE_FLAG_NO_KERNEL_TIMING = 64
 };
 
 typedef struct ore_context ore_context; /* opaque; owns device buffers, streams, pinned staging */
@@ -180,6 +183,17 @@ int ore_synchronize(ore_context* ctx);
  * following ore_render_async call.  Same pixels as ore_render. */
 int ore_render_async(ore_context* ctx, const ore_camera* cam, const ore_frame* frame, uint32_t* out_host);
 int ore_wait(ore_context* ctx);
+/* Rows in place: with frame->out_pitch == frame->width, `out_host` is image row y0 of a FULL host frame and every
+ * rendered row is copied to its image position (y_block / y_step honoured: one strided copy of the row blocks).
+ * This is how the ranks of a multi-GPU job each send their own rows to ONE shared pinned host frame - the buffer
+ * setPixelBuff reads (window.cpp:130-132) - over their own PCIe link.  out_pitch == 0 keeps the packed layout.
+ * ore_render_async_signal additionally writes `done_value` to `*done_flag` (registered host memory or device
+ * memory) in stream order AFTER the copy has landed, without blocking the caller. */
+int ore_render_async_signal(ore_context* ctx, const ore_camera* cam, const ore_frame* frame, uint32_t* out_host,
+                            uint32_t* done_flag, uint32_t done_value);
+/* Pin caller memory (e.g. a POSIX shared-memory frame mapped by every rank) for asynchronous copies and flags. */
+int ore_host_register(ore_context* ctx, void* host_ptr, size_t bytes);
+int ore_host_unregister(ore_context* ctx, void* host_ptr);
 /* pinned host memory for framebuffers (the shim's `pixels` handed to setPixelBuff) */
 int ore_host_alloc(ore_context* ctx, size_t bytes, void** host_ptr);
 int ore_host_free(ore_context* ctx, void* host_ptr);
@@ -194,6 +208,20 @@ int ore_dev_free(ore_context* ctx, void* dev_ptr);
 int ore_ipc_export(ore_context* ctx, void* dev_ptr, unsigned char handle[64]);
 int ore_ipc_import(ore_context* ctx, const unsigned char handle[64], void** dev_ptr);
 int ore_ipc_close(ore_context* ctx, void* dev_ptr);
+/* Stream-ordered 32-bit flags: the completion / back-pressure signals of multi-GPU presentation, in place of a
+ * collective.  ore_flag_write stores `value` to `*flag` after everything already enqueued on `stream` (NULL = the
+ * context's render stream; ore_get_stream(ctx, 1) = its copy stream) has completed; ore_flag_wait_geq makes later
+ * work on `stream` wait until (int32)(*flag - value) >= 0.  `flag` may be device memory of this GPU, registered
+ * host memory, or - for writes - a peer GPU's memory imported with ore_ipc_import (stored over NVLink).  Neither
+ * call blocks the host.  Implemented with cuStreamWriteValue32 / cuStreamWaitValue32 (no SM involved); a one-thread
+ * kernel is the fallback for peer addresses and for drivers without stream memory operations. */
+int ore_flag_write(ore_context* ctx, void* stream, uint32_t* flag, uint32_t value);
+int ore_flag_wait_geq(ore_context* ctx, void* stream, const uint32_t* flag, uint32_t value);
+/* Like ore_flag_write, but the store is issued from the context's in-order signal stream once the work enqueued on
+ * `stream` so far is complete: flags written through one context appear in CALL order even when frames rendered on
+ * different streams (several frames in flight) finish out of order. */
+int ore_flag_write_after(ore_context* ctx, void* stream, uint32_t* flag, uint32_t value);
+void* ore_get_stream(ore_context* ctx, int which); /* 0: render stream, 1: copy stream (cudaStream_t) */
 /* device -> host copy on the context's stream, synchronous (the setPixelBuff copy) */
 int ore_copy_to_host(ore_context* ctx, void* host_dst, const void* dev_src, size_t bytes);
 

@@ -19,6 +19,7 @@ ORE_FLAG_PER_RAY_SHADOW = 4
 ORE_FLAG_NO_WARP_CULL = 8
 ORE_FLAG_FAST_LIBM = 16
 ORE_FLAG_FUSED_SHADOW = 32
+ORE_FLAG_NO_KERNEL_TIMING = 64
 
 EXPORTS = [
     "ore_create", "ore_destroy", "ore_abi_version", "ore_last_error",
@@ -27,6 +28,8 @@ EXPORTS = [
     "ore_get_hits", "ore_get_counters", "ore_get_kernel_ms", "ore_measure_fp32_peak", "ore_debug_libm",
     "ore_render_async", "ore_wait", "ore_host_alloc", "ore_host_free",
     "ore_dev_alloc", "ore_dev_free", "ore_ipc_export", "ore_ipc_import", "ore_ipc_close", "ore_copy_to_host",
+    "ore_render_async_signal", "ore_host_register", "ore_host_unregister", "ore_flag_write", "ore_flag_wait_geq",
+    "ore_flag_write_after", "ore_get_stream",
 ]
 
 
@@ -95,8 +98,16 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.ore_ipc_import.argtypes = [vp, C.POINTER(C.c_ubyte * 64), C.POINTER(vp)]
     lib.ore_ipc_close.argtypes = [vp, vp]
     lib.ore_copy_to_host.argtypes = [vp, vp, vp, C.c_size_t]
+    lib.ore_render_async_signal.argtypes = [vp, C.POINTER(OreCamera), C.POINTER(OreFrame), vp, vp, C.c_uint32]
+    lib.ore_host_register.argtypes = [vp, vp, C.c_size_t]
+    lib.ore_host_unregister.argtypes = [vp, vp]
+    lib.ore_flag_write.argtypes = [vp, vp, vp, C.c_uint32]
+    lib.ore_flag_wait_geq.argtypes = [vp, vp, vp, C.c_uint32]
+    lib.ore_flag_write_after.argtypes = [vp, vp, vp, C.c_uint32]
+    lib.ore_get_stream.argtypes = [vp, C.c_int]
+    lib.ore_get_stream.restype = vp
     for name in EXPORTS:
-        if name != "ore_last_error":
+        if name not in ("ore_last_error", "ore_get_stream"):
             getattr(lib, name).restype = C.c_int
     if path == _build.LIB_PATH:
         _lib = lib
@@ -285,10 +296,42 @@ class Renderer:
         if p is not None:
             self._check(self.lib.ore_host_free(self.ctx, C.c_void_p(p)), "ore_host_free")
 
-    def render_async(self, camera, width, height, out: np.ndarray, y0=0, y1=None, y_step=1, aspect=None, flags=0):
-        f = self._frame(width, height, y0, y1, y_step, aspect, flags)
+    def render_async(self, camera, width, height, out, y0=0, y1=None, y_step=1, aspect=None, flags=0, y_block=1,
+                     in_place=False, done_flag: int = 0, done_value: int = 0):
+        """Pipelined render + device->host copy.  `out`: numpy array (packed band) or, with in_place=True, the address
+        (int) / array of image row y0 inside a FULL host frame.  done_flag: address of a 32-bit flag written with
+        done_value once the copy has landed (0 = none)."""
+        f = self._frame(width, height, y0, y1, y_step, aspect, flags, width if in_place else 0, y_block)
         cam = self._cam(camera)
-        self._check(self.lib.ore_render_async(self.ctx, C.byref(cam), C.byref(f), out.ctypes.data), "ore_render_async")
+        ptr = out if isinstance(out, int) else out.ctypes.data
+        if done_flag:
+            self._check(self.lib.ore_render_async_signal(self.ctx, C.byref(cam), C.byref(f), C.c_void_p(ptr),
+                                                         C.c_void_p(done_flag), int(done_value)), "ore_render_async_signal")
+        else:
+            self._check(self.lib.ore_render_async(self.ctx, C.byref(cam), C.byref(f), C.c_void_p(ptr)), "ore_render_async")
+
+    # ---- stream-ordered flags / registered host memory (multi-GPU presentation) ----
+    def host_register(self, ptr: int, nbytes: int):
+        self._check(self.lib.ore_host_register(self.ctx, C.c_void_p(ptr), nbytes), "ore_host_register")
+
+    def host_unregister(self, ptr: int):
+        self._check(self.lib.ore_host_unregister(self.ctx, C.c_void_p(ptr)), "ore_host_unregister")
+
+    def stream_handle(self, which: int = 0) -> int:
+        return int(self.lib.ore_get_stream(self.ctx, which) or 0)
+
+    def flag_write(self, flag_ptr: int, value: int, stream: int = 0):
+        self._check(self.lib.ore_flag_write(self.ctx, C.c_void_p(stream) if stream else None, C.c_void_p(flag_ptr),
+                                            int(value) & 0xffffffff), "ore_flag_write")
+
+    def flag_write_after(self, flag_ptr: int, value: int, stream: int = 0):
+        """ordered variant: issued from this context's signal stream once `stream`'s work so far is complete"""
+        self._check(self.lib.ore_flag_write_after(self.ctx, C.c_void_p(stream) if stream else None, C.c_void_p(flag_ptr),
+                                                  int(value) & 0xffffffff), "ore_flag_write_after")
+
+    def flag_wait_geq(self, flag_ptr: int, value: int, stream: int = 0):
+        self._check(self.lib.ore_flag_wait_geq(self.ctx, C.c_void_p(stream) if stream else None, C.c_void_p(flag_ptr),
+                                               int(value) & 0xffffffff), "ore_flag_wait_geq")
 
     def wait(self):
         self._check(self.lib.ore_wait(self.ctx), "ore_wait")

@@ -94,11 +94,27 @@ struct ore_context {
     size_t stage_cap = 0;    // floats
     size_t stage_blocks_override = 0;  // test hook (env ORE_STAGE_BLOCKS at ore_create): staging capacity in 32-item blocks
     bool stage_always = false;         // test hook (env ORE_STAGE_ALWAYS=1): two-stage pass also for non-resident scenes
+    bool no_memops = false;            // test hook (env ORE_NO_STREAM_MEMOPS=1): flags through the one-thread kernels
     // hit count of this context's previous frame, copied to pinned memory at the end of every frame and read
     // WITHOUT synchronisation by the next one: only a hint for how many staged chunk pairs to launch - whatever
     // lies beyond them is swept by one catch-all fused launch, so any value (stale, zero, mid-copy) is safe
     unsigned long long* hits_hint = nullptr;
     bool hits_hint_set = false;
+
+    // occupancy-sized grids, computed once per (kernel, dynamic shared memory, block size)
+    struct GridEntry {
+        const void* fn;
+        size_t smem;
+        int threads, grid;
+    };
+    std::vector<GridEntry> grid_cache;
+    // end of the last render on whichever stream it ran (scene setters wait for it before touching scene buffers)
+    cudaEvent_t ev_done = nullptr;
+    bool ev_done_set = false;
+    // ordered flag writes (ore_flag_write_after)
+    cudaStream_t signal_stream = nullptr;
+    cudaEvent_t ev_signal[8] = {};
+    unsigned n_signals = 0;
 
     // last frame
     size_t last_px = 0;
@@ -146,6 +162,12 @@ static int ensure_dev(ore_context* ctx, T** p, size_t* cap, size_t n) {
     return ORE_OK;
 }
 
+// scene setters: the previous render may still be running on a caller-supplied stream
+static int wait_last_render(ore_context* ctx) {
+    if (ctx->ev_done_set) ORE_CUDA(ctx, cudaEventSynchronize(ctx->ev_done));
+    return ORE_OK;
+}
+
 extern "C" int ore_abi_version(void) { return ORE_ABI_VERSION; }
 
 extern "C" const char* ore_last_error(const ore_context* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
@@ -174,9 +196,11 @@ extern "C" int ore_create(ore_context** out, int device) {
         ORE_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
     }
     for (int i = 0; i < 5; i++) ORE_CUDA(ctx, cudaEventCreate(&ctx->ev[i]));
+    ORE_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming));
     ORE_CUDA(ctx, cudaMallocHost((void**)&ctx->hits_hint, sizeof(unsigned long long)));
     *ctx->hits_hint = 0;
     if (const char* e = getenv("ORE_STAGE_ALWAYS")) ctx->stage_always = atoi(e) != 0;
+    if (const char* e = getenv("ORE_NO_STREAM_MEMOPS")) ctx->no_memops = atoi(e) != 0;
     if (const char* e = getenv("ORE_STAGE_BLOCKS")) {
         const long v = atol(e);
         if (v > 0) ctx->stage_blocks_override = (size_t)v;
@@ -216,6 +240,13 @@ extern "C" int ore_destroy(ore_context* ctx) {
         if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
     }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
+    if (ctx->signal_stream) {
+        cudaStreamSynchronize(ctx->signal_stream);
+        for (auto& e : ctx->ev_signal)
+            if (e) cudaEventDestroy(e);
+        cudaStreamDestroy(ctx->signal_stream);
+    }
     if (ctx->pixels_b) cudaFree(ctx->pixels_b);
     void* dev[] = {ctx->stage, ctx->sph_sort, ctx->sph_xsort, ctx->clu_sph, ctx->sph_exact, ctx->sph_prim, ctx->sph_cone, ctx->sph_shad, ctx->tex[0], ctx->tex[1], ctx->tex[2],
                    ctx->sky[0],    ctx->sky[1],   ctx->sky[2],   ctx->dx_tab, ctx->dy_tab, ctx->hit_id,
@@ -263,6 +294,7 @@ static int upload_clusters(ore_context* ctx, const float4* ex, const float4* sh,
 static int upload_spheres(ore_context* ctx, const float* src, size_t stride_floats, size_t first, int32_t n) {
     if (!ctx || n < 0 || (n > 0 && !src)) return fail(ctx, ORE_ERR_INVALID, "ore_set_spheres: bad arguments");
     ORE_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (int rcw = wait_last_render(ctx)) return rcw;
     const int n_pad = ((n + SPHERE_PAD - 1) / SPHERE_PAD) * SPHERE_PAD + SPHERE_PAD;  // >= 1 pad block
     size_t cap_e = ctx->sph_cap, cap_p = ctx->sph_cap, cap_s = ctx->sph_cap, cap_c = ctx->sph_cap;
     int rc;
@@ -270,7 +302,7 @@ static int upload_spheres(ore_context* ctx, const float* src, size_t stride_floa
     if ((rc = ensure_dev(ctx, &ctx->sph_prim, &cap_p, (size_t)n_pad))) return rc;
     if ((rc = ensure_dev(ctx, &ctx->sph_cone, &cap_c, (size_t)n_pad))) return rc;
     if ((rc = ensure_dev(ctx, &ctx->sph_shad, &cap_s, (size_t)n_pad))) return rc;
-    ctx->sph_cap = cap_e < cap_p ? (cap_e < cap_s ? cap_e : cap_s) : (cap_p < cap_s ? cap_p : cap_s);
+    ctx->sph_cap = std::min(std::min(cap_e, cap_p), std::min(cap_s, cap_c));
     if ((rc = ensure_pinned(ctx, 2 * (size_t)n_pad * sizeof(float4)))) return rc;
     float4* ex = (float4*)ctx->pinned;
     float4* sh = ex + n_pad;
@@ -323,6 +355,7 @@ extern "C" int ore_set_spheres_aos32(ore_context* ctx, const void* records, int3
 extern "C" int ore_set_cubes(ore_context* ctx, const float* c1_c2, int32_t n) {
     if (!ctx || n < 0 || (n > 0 && !c1_c2)) return fail(ctx, ORE_ERR_INVALID, "ore_set_cubes: bad arguments");
     ORE_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (int rcw = wait_last_render(ctx)) return rcw;
     if (ctx->cubes) ORE_CUDA(ctx, cudaFree(ctx->cubes));
     ctx->cubes = nullptr;
     ctx->n_cubes = 0;
@@ -353,6 +386,7 @@ extern "C" int ore_set_cubes(ore_context* ctx, const float* c1_c2, int32_t n) {
 extern "C" int ore_set_planes(ore_context* ctx, const float* pos_normal, int32_t n) {
     if (!ctx || n < 0 || (n > 0 && !pos_normal)) return fail(ctx, ORE_ERR_INVALID, "ore_set_planes: bad arguments");
     ORE_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (int rcw = wait_last_render(ctx)) return rcw;
     if (ctx->planes) ORE_CUDA(ctx, cudaFree(ctx->planes));
     ctx->planes = nullptr;
     ctx->n_planes = 0;
@@ -379,6 +413,7 @@ extern "C" int ore_set_mesh(ore_context* ctx, const float* tris27, int32_t n_tri
     if (n_tris > 0 && n_boxes > 0 && (!tris27 || !box_bounds6 || !box_offsets || !box_indices))
         return fail(ctx, ORE_ERR_INVALID, "ore_set_mesh: null array");
     ORE_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (int rcw = wait_last_render(ctx)) return rcw;
     void* old[] = {ctx->tris, ctx->boxes, ctx->box_offsets, ctx->box_indices, ctx->box_sph, ctx->box_cone};
     for (void* p : old)
         if (p) ORE_CUDA(ctx, cudaFree(p));
@@ -400,11 +435,14 @@ extern "C" int ore_set_mesh(ore_context* ctx, const float* tris27, int32_t n_tri
     const size_t ob = (size_t)(n_boxes + 1) * sizeof(int), ib = (size_t)(n_idx > 0 ? n_idx : 1) * sizeof(int);
     int rc;
     const size_t sb = (size_t)n_boxes * sizeof(float4);
-    if ((rc = ensure_pinned(ctx, tb + bb + ob + ib + sb))) return rc;
+    // pinned staging layout: the two float4 sections first (16-byte aligned: bb and sb are multiples of 16 and the
+    // pinned base is page aligned), then the 4-byte-aligned sections
+    const size_t off_b = 0, off_s = bb, off_t = bb + sb, off_o = off_t + tb, off_i = off_o + ob;
+    if ((rc = ensure_pinned(ctx, off_i + ib))) return rc;
     char* h = (char*)ctx->pinned;
-    memcpy(h, tris27, tb);
-    float4* hb = (float4*)(h + tb);
-    float4* hs = (float4*)(h + tb + bb + ob + ib);
+    float4* hb = (float4*)(h + off_b);
+    float4* hs = (float4*)(h + off_s);
+    memcpy(h + off_t, tris27, tb);
     for (int j = 0; j < n_boxes; j++) {
         const float* b = box_bounds6 + 6 * (size_t)j;
         hb[2 * j] = make_float4(b[0], b[1], b[2], 0.f);
@@ -417,8 +455,8 @@ extern "C" int ore_set_mesh(ore_context* ctx, const float* tris27, int32_t n_tri
         const double mag = fabs(cx) + fabs(cy) + fabs(cz) + rad;
         hs[j] = make_float4((float)cx, (float)cy, (float)cz, (float)(rad * 1.001 + 1e-5 * mag + 1e-6));
     }
-    memcpy(h + tb + bb, box_offsets, ob);
-    memcpy(h + tb + bb + ob, box_indices, (size_t)n_idx * sizeof(int));
+    memcpy(h + off_o, box_offsets, ob);
+    memcpy(h + off_i, box_indices, (size_t)n_idx * sizeof(int));
     ORE_CUDA(ctx, cudaMalloc((void**)&ctx->tris, tb));
     ORE_CUDA(ctx, cudaMalloc((void**)&ctx->boxes, bb));
     ORE_CUDA(ctx, cudaMalloc((void**)&ctx->box_offsets, ob));
@@ -426,10 +464,10 @@ extern "C" int ore_set_mesh(ore_context* ctx, const float* tris27, int32_t n_tri
     ORE_CUDA(ctx, cudaMalloc((void**)&ctx->box_sph, sb));
     ORE_CUDA(ctx, cudaMalloc((void**)&ctx->box_cone, sb));
     ORE_CUDA(ctx, cudaMemcpyAsync(ctx->box_sph, hs, sb, cudaMemcpyHostToDevice, ctx->stream));
-    ORE_CUDA(ctx, cudaMemcpyAsync(ctx->tris, h, tb, cudaMemcpyHostToDevice, ctx->stream));
-    ORE_CUDA(ctx, cudaMemcpyAsync(ctx->boxes, h + tb, bb, cudaMemcpyHostToDevice, ctx->stream));
-    ORE_CUDA(ctx, cudaMemcpyAsync(ctx->box_offsets, h + tb + bb, ob, cudaMemcpyHostToDevice, ctx->stream));
-    ORE_CUDA(ctx, cudaMemcpyAsync(ctx->box_indices, h + tb + bb + ob, ib, cudaMemcpyHostToDevice, ctx->stream));
+    ORE_CUDA(ctx, cudaMemcpyAsync(ctx->tris, h + off_t, tb, cudaMemcpyHostToDevice, ctx->stream));
+    ORE_CUDA(ctx, cudaMemcpyAsync(ctx->boxes, hb, bb, cudaMemcpyHostToDevice, ctx->stream));
+    ORE_CUDA(ctx, cudaMemcpyAsync(ctx->box_offsets, h + off_o, ob, cudaMemcpyHostToDevice, ctx->stream));
+    ORE_CUDA(ctx, cudaMemcpyAsync(ctx->box_indices, h + off_i, ib, cudaMemcpyHostToDevice, ctx->stream));
     ORE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->n_tris = n_tris;
     ctx->n_boxes = n_boxes;
@@ -440,6 +478,7 @@ extern "C" int ore_set_mesh(ore_context* ctx, const float* tris27, int32_t n_tri
 extern "C" int ore_set_lights(ore_context* ctx, const float* lights7, int32_t n) {
     if (!ctx || n < 0 || n > MAX_LIGHTS || (n > 0 && !lights7))
         return fail(ctx, ORE_ERR_INVALID, "ore_set_lights: 0..16 lights of 7 floats");
+    // lights travel as kernel arguments: nothing on the device to wait for
     for (int i = 0; i < n; i++) {
         const float* l = lights7 + 7 * (size_t)i;
         ctx->lights[i] = LightP{l[0], l[1], l[2], l[3], l[4], l[5], l[6]};
@@ -452,6 +491,7 @@ static int upload_planes(ore_context* ctx, float* dst[3], const float* r, const 
                          int32_t h) {
     if (!ctx || w <= 0 || h <= 0 || !r || !g || !b) return fail(ctx, ORE_ERR_INVALID, "sprite planes: bad arguments");
     ORE_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (int rcw = wait_last_render(ctx)) return rcw;
     const size_t n = (size_t)w * h;
     int rc;
     if ((rc = ensure_pinned(ctx, n * sizeof(float)))) return rc;
@@ -496,11 +536,22 @@ static constexpr int STREAM_STAGES = 3;
 
 template <typename K>
 static int grid_for(ore_context* ctx, K kernel, size_t smem, int* grid, int threads = CTA_THREADS) {
+    const void* fn = reinterpret_cast<const void*>(kernel);
+    for (const auto& e : ctx->grid_cache)
+        if (e.fn == fn && e.smem == smem && e.threads == threads) {
+            *grid = e.grid;
+            return ORE_OK;
+        }
     int occ = 0;
-    ORE_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // the opt-in limit only ever grows, so that earlier (cached) configurations of this kernel stay launchable
+    size_t limit = smem;
+    for (const auto& e : ctx->grid_cache)
+        if (e.fn == fn && e.smem > limit) limit = e.smem;
+    ORE_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
     ORE_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
     if (occ < 1) return fail(ctx, ORE_ERR_CUDA, "kernel does not fit on an SM");
     *grid = occ * ctx->sm_count;
+    ctx->grid_cache.push_back({fn, smem, threads, *grid});
     return ORE_OK;
 }
 
@@ -518,7 +569,8 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
                        cudaStream_t stream) {
     if (!ctx) return ORE_ERR_INVALID;
     if (!cam || !fr) return fail(ctx, ORE_ERR_INVALID, "ore_render: null camera/frame");
-    if (fr->width <= 0 || fr->height <= 0 || fr->y_step <= 0 || fr->y0 < 0 || fr->y1 < fr->y0 ||
+    // a band may be empty (y0 >= y1: a rank with no rows of a short frame) but never reaches past the image
+    if (fr->width <= 0 || fr->height <= 0 || fr->y_step <= 0 || fr->y0 < 0 || fr->y1 < 0 || fr->y1 > fr->height ||
         (fr->out_pitch != 0 && fr->out_pitch < fr->width))
         return fail(ctx, ORE_ERR_INVALID, "ore_render: bad frame geometry");
     if (!ctx->tex[0] || !ctx->sky[0]) return fail(ctx, ORE_ERR_INVALID, "ore_render: texture and sky must be set first");
@@ -662,7 +714,12 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
     prm.pixels = out_device ? out_device : ctx->pixels;
     for (int i = 0; i < ctx->n_lights; i++) prm.lights[i] = ctx->lights[i];
 
-    ORE_CUDA(ctx, cudaEventRecord(ctx->ev[0], stream));
+    const bool timing = !(fr->flags & ORE_FLAG_NO_KERNEL_TIMING);
+    if (!out_device) {
+        // the context's own framebuffer may still be the source of a pipelined device->host copy
+        ORE_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->ev_copied[0], 0));
+    }
+    if (timing) ORE_CUDA(ctx, cudaEventRecord(ctx->ev[0], stream));
     {
         int m = W > n_rows ? W : n_rows;
         if (ctx->n_spheres_pad > m) m = ctx->n_spheres_pad;
@@ -672,7 +729,7 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
         ORE_CUDA(ctx, cudaGetLastError());
         ctx->last_launches++;
     }
-    ORE_CUDA(ctx, cudaEventRecord(ctx->ev[1], stream));
+    if (timing) ORE_CUDA(ctx, cudaEventRecord(ctx->ev[1], stream));
     const bool exh = (fr->flags & ORE_FLAG_EXHAUSTIVE) != 0;
     const bool warp_cull = !(fr->flags & (ORE_FLAG_NO_WARP_CULL | ORE_FLAG_PER_RAY_SHADOW));
     const bool fast_libm = (fr->flags & ORE_FLAG_FAST_LIBM) != 0;  // default-path kernels only
@@ -707,7 +764,7 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
         ORE_CUDA(ctx, cudaGetLastError());
         ctx->last_launches++;
     }
-    ORE_CUDA(ctx, cudaEventRecord(ctx->ev[2], stream));
+    if (timing) ORE_CUDA(ctx, cudaEventRecord(ctx->ev[2], stream));
     {
         int grid = 0;
         const int nl = ctx->n_lights >= 3 ? 3 : (ctx->n_lights == 2 ? 2 : 1);
@@ -831,7 +888,7 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
         ORE_CUDA(ctx, cudaGetLastError());
         ctx->last_launches++;
     }
-    ORE_CUDA(ctx, cudaEventRecord(ctx->ev[3], stream));
+    if (timing) ORE_CUDA(ctx, cudaEventRecord(ctx->ev[3], stream));
     // hint for the next frame of this context (see hits_hint): 8 bytes, no synchronisation
     ORE_CUDA(ctx, cudaMemcpyAsync(ctx->hits_hint, ctx->counters + CNT_HITS, sizeof(unsigned long long),
                                   cudaMemcpyDeviceToHost, stream));
@@ -842,8 +899,10 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
         ctx->last_launches++;
         ctx->ran_count = true;
     }
-    ORE_CUDA(ctx, cudaEventRecord(ctx->ev[4], stream));
-    ctx->ev_valid = true;
+    if (timing) ORE_CUDA(ctx, cudaEventRecord(ctx->ev[4], stream));
+    ctx->ev_valid = timing;
+    ORE_CUDA(ctx, cudaEventRecord(ctx->ev_done, stream));
+    ctx->ev_done_set = true;
     return ORE_OK;
 }
 
@@ -868,12 +927,129 @@ extern "C" int ore_render(ore_context* ctx, const ore_camera* cam, const ore_fra
     return ORE_OK;
 }
 
-extern "C" int ore_render_async(ore_context* ctx, const ore_camera* cam, const ore_frame* frame, uint32_t* out_host) {
+// ---- stream-ordered 32-bit flags (cuStreamWriteValue32 / cuStreamWaitValue32, no SM involved) ----------------
+// The driver entry points are resolved at run time (the library links against cudart only).
+typedef int (*ore_cu_memop32)(cudaStream_t, unsigned long long /*CUdeviceptr*/, unsigned int, unsigned int);
+static ore_cu_memop32 cu_write32 = nullptr, cu_wait32 = nullptr;
+static bool memops_resolved = false;
+static void resolve_memops() {
+    if (memops_resolved) return;
+    memops_resolved = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+        cu_write32 = (ore_cu_memop32)f;
+    f = nullptr;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+        cu_wait32 = (ore_cu_memop32)f;
+    (void)cudaGetLastError();
+}
+
+// fallbacks on an SM: one thread.  The wait kernel is only ever used when the driver offers no stream wait; it
+// polls a flag that ANOTHER GPU (or the host) writes, never another launch on this GPU.
+__global__ void flag_write_kernel(uint32_t* flag, uint32_t value) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+}
+__global__ void flag_wait_kernel(const uint32_t* flag, uint32_t value) {
+    for (;;) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((int32_t)(v - value) >= 0) break;
+        __nanosleep(200);
+    }
+}
+
+static cudaStream_t pick_stream(ore_context* ctx, void* stream) { return stream ? (cudaStream_t)stream : ctx->stream; }
+
+extern "C" void* ore_get_stream(ore_context* ctx, int which) {
+    if (!ctx) return nullptr;
+    return which == 1 ? (void*)ctx->copy_stream : (void*)ctx->stream;
+}
+
+extern "C" int ore_flag_write(ore_context* ctx, void* stream, uint32_t* flag, uint32_t value) {
+    if (!ctx || !flag) return ORE_ERR_INVALID;
+    ORE_CUDA(ctx, cudaSetDevice(ctx->device));
+    resolve_memops();
+    cudaStream_t st = pick_stream(ctx, stream);
+    // peer-mapped device memory (another GPU's flag, imported with ore_ipc_import) is written by a one-thread
+    // kernel (st.release.sys over NVLink); local device memory and registered host memory by the stream itself
+    cudaPointerAttributes at;
+    bool local = false;
+    if (cudaPointerGetAttributes(&at, flag) == cudaSuccess)
+        local = (at.type == cudaMemoryTypeHost) || (at.type == cudaMemoryTypeDevice && at.device == ctx->device);
+    (void)cudaGetLastError();
+    if (local && cu_write32 && !ctx->no_memops) {
+        void* dptr = flag;
+        if (at.type == cudaMemoryTypeHost) ORE_CUDA(ctx, cudaHostGetDevicePointer(&dptr, flag, 0));
+        if (cu_write32(st, (unsigned long long)(uintptr_t)dptr, value, 0) == 0) return ORE_OK;
+    }
+    flag_write_kernel<<<1, 1, 0, st>>>(flag, value);
+    ORE_CUDA(ctx, cudaGetLastError());
+    return ORE_OK;
+}
+
+// Ordered variant for frames rendered on SEVERAL streams (frames in flight): the flag is written on the context's
+// signal stream once everything enqueued on `stream` so far has completed.  The signal stream is in-order, so flag
+// values written through one context appear in call order even when the frames finish out of order.
+extern "C" int ore_flag_write_after(ore_context* ctx, void* stream, uint32_t* flag, uint32_t value) {
+    if (!ctx || !flag) return ORE_ERR_INVALID;
+    ORE_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->signal_stream) {
+        ORE_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->signal_stream, cudaStreamNonBlocking));
+        for (auto& e : ctx->ev_signal) ORE_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    cudaEvent_t e = ctx->ev_signal[ctx->n_signals++ % 8];
+    ORE_CUDA(ctx, cudaEventRecord(e, pick_stream(ctx, stream)));
+    ORE_CUDA(ctx, cudaStreamWaitEvent(ctx->signal_stream, e, 0));
+    return ore_flag_write(ctx, ctx->signal_stream, flag, value);
+}
+
+extern "C" int ore_flag_wait_geq(ore_context* ctx, void* stream, const uint32_t* flag, uint32_t value) {
+    if (!ctx || !flag) return ORE_ERR_INVALID;
+    ORE_CUDA(ctx, cudaSetDevice(ctx->device));
+    resolve_memops();
+    cudaStream_t st = pick_stream(ctx, stream);
+    cudaPointerAttributes at;
+    void* dptr = (void*)flag;
+    if (cudaPointerGetAttributes(&at, flag) == cudaSuccess && at.type == cudaMemoryTypeHost)
+        ORE_CUDA(ctx, cudaHostGetDevicePointer(&dptr, (void*)flag, 0));
+    (void)cudaGetLastError();
+    if (cu_wait32 && !ctx->no_memops) {
+        if (cu_wait32(st, (unsigned long long)(uintptr_t)dptr, value, 0 /* CU_STREAM_WAIT_VALUE_GEQ */) == 0) return ORE_OK;
+    }
+    flag_wait_kernel<<<1, 1, 0, st>>>((const uint32_t*)dptr, value);
+    ORE_CUDA(ctx, cudaGetLastError());
+    return ORE_OK;
+}
+
+extern "C" int ore_host_register(ore_context* ctx, void* host_ptr, size_t bytes) {
+    if (!ctx || !host_ptr || bytes == 0) return ORE_ERR_INVALID;
+    ORE_CUDA(ctx, cudaSetDevice(ctx->device));
+    ORE_CUDA(ctx, cudaHostRegister(host_ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+    return ORE_OK;
+}
+extern "C" int ore_host_unregister(ore_context* ctx, void* host_ptr) {
+    if (!ctx || !host_ptr) return ORE_ERR_INVALID;
+    ORE_CUDA(ctx, cudaSetDevice(ctx->device));
+    ORE_CUDA(ctx, cudaHostUnregister(host_ptr));
+    return ORE_OK;
+}
+
+// Pipelined presentation.  The band is rendered into one of two device framebuffers and copied to the host on the
+// copy stream while the next frame renders.  frame->out_pitch == 0: rows packed at out_host.  out_pitch == width:
+// out_host is image row y0 of a FULL host frame and every rendered row lands at its image position (a rank of a
+// multi-GPU job copies its own row blocks into the shared host frame over its own PCIe link).
+static int render_async_impl(ore_context* ctx, const ore_camera* cam, const ore_frame* frame, uint32_t* out_host,
+                             uint32_t* done_flag, uint32_t done_value) {
     if (!ctx) return ORE_ERR_INVALID;
     if (!out_host || !frame) return fail(ctx, ORE_ERR_INVALID, "ore_render_async: null output/frame");
+    if (frame->out_pitch != 0 && frame->out_pitch != frame->width)
+        return fail(ctx, ORE_ERR_INVALID, "ore_render_async: out_pitch must be 0 (packed) or the frame width (rows in place)");
     ORE_CUDA(ctx, cudaSetDevice(ctx->device));
     const int n_rows = frame_rows(frame);
-    const size_t n_px = (size_t)(n_rows > 0 ? n_rows : 0) * (size_t)(frame->width > 0 ? frame->width : 0);
+    const size_t W = (size_t)(frame->width > 0 ? frame->width : 0);
+    const size_t n_px = (size_t)(n_rows > 0 ? n_rows : 0) * W;
     const int buf = (int)(ctx->async_frames & 1ull);
     int rc;
     // two device framebuffers: the context's own and a second one
@@ -885,6 +1061,7 @@ extern "C" int ore_render_async(ore_context* ctx, const ore_camera* cam, const o
         // let render_impl size the per-frame buffers first (synchronously, once)
         ORE_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
         ore_frame probe = *frame;
+        probe.out_pitch = 0;
         if ((rc = render_impl(ctx, cam, &probe, nullptr, ctx->stream))) return rc;
         ORE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
@@ -896,12 +1073,37 @@ extern "C" int ore_render_async(ore_context* ctx, const ore_camera* cam, const o
     if ((rc = render_impl(ctx, cam, &fr, target, ctx->stream))) return rc;
     ORE_CUDA(ctx, cudaEventRecord(ctx->ev_rendered[buf], ctx->stream));
     ORE_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rendered[buf], 0));
-    if (ctx->last_px)
-        ORE_CUDA(ctx, cudaMemcpyAsync(out_host, target, ctx->last_px * sizeof(uint32_t), cudaMemcpyDeviceToHost,
-                                      ctx->copy_stream));
+    if (ctx->last_px) {
+        const int yb = frame->y_block > 0 ? frame->y_block : 1;
+        if (frame->out_pitch == 0 || yb >= frame->y_step) {
+            // packed, or a contiguous band: one linear copy
+            ORE_CUDA(ctx, cudaMemcpyAsync(out_host, target, ctx->last_px * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                          ctx->copy_stream));
+        } else {
+            // block-interleaved rows: blocks of yb rows, y_step image rows apart -> one strided copy (+ a ragged tail)
+            const size_t blk_bytes = (size_t)yb * W * sizeof(uint32_t);
+            const size_t full = (size_t)n_rows / yb, rem = (size_t)n_rows % yb;
+            if (full)
+                ORE_CUDA(ctx, cudaMemcpy2DAsync(out_host, (size_t)frame->y_step * W * sizeof(uint32_t), target, blk_bytes,
+                                                blk_bytes, full, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            if (rem)
+                ORE_CUDA(ctx, cudaMemcpyAsync(out_host + full * (size_t)frame->y_step * W, target + full * (size_t)yb * W,
+                                              rem * W * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->copy_stream));
+        }
+    }
     ORE_CUDA(ctx, cudaEventRecord(ctx->ev_copied[buf], ctx->copy_stream));
     ctx->async_frames++;
+    if (done_flag) return ore_flag_write(ctx, ctx->copy_stream, done_flag, done_value);
     return ORE_OK;
+}
+
+extern "C" int ore_render_async(ore_context* ctx, const ore_camera* cam, const ore_frame* frame, uint32_t* out_host) {
+    return render_async_impl(ctx, cam, frame, out_host, nullptr, 0);
+}
+extern "C" int ore_render_async_signal(ore_context* ctx, const ore_camera* cam, const ore_frame* frame, uint32_t* out_host,
+                                       uint32_t* done_flag, uint32_t done_value) {
+    if (!done_flag) return fail(ctx, ORE_ERR_INVALID, "ore_render_async_signal: null flag");
+    return render_async_impl(ctx, cam, frame, out_host, done_flag, done_value);
 }
 
 extern "C" int ore_wait(ore_context* ctx) {

@@ -3,6 +3,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -135,7 +136,16 @@ void procedural(const std::string& spec, int& w, int& h, std::vector<unsigned ch
 sprite::sprite(std::string file) {
     std::vector<unsigned char> rgb;
     int w = 0, h = 0;
-    if (file.rfind("proc:", 0) == 0 || !(load_ppm(file, w, h, rgb) || load_bmp(file, w, h, rgb))) procedural(file, w, h, rgb);
+    if (file.rfind("proc:", 0) == 0) {
+        procedural(file, w, h, rgb);
+    } else if (!(load_ppm(file, w, h, rgb) || load_bmp(file, w, h, rgb))) {
+        // The reference decodes any OpenCV-readable image (Sprite.cpp:30); this shim reads binary PPM (P6) and
+        // 24-bit BMP only.  An unreadable file is an error in the shim's own convention (memManager.cpp:3-11:
+        // message on stderr, exit(99)) - never a silent stand-in texture.
+        fprintf(stderr, "sprite: cannot read '%s' (accepted: binary PPM (P6), 24-bit uncompressed BMP, or a proc: spec)\n",
+                file.c_str());
+        exit(99);
+    }
     width = w;
     height = h;
     std::vector<float> r((size_t)w * h), g((size_t)w * h), b((size_t)w * h);

@@ -18,6 +18,18 @@ Gather (two implementations):
               frame through NVLink (compute fused with its "collective": no separate
               gather kernel, no staging copy).  Ranks render into a strided row view.
 
+Completion (round 2): there is no collective per frame.  Rank r announces "my rows of frame g are in
+place" by storing g+1 into ITS slot of a small flag array owned by the presenter, in stream order behind
+its render kernels (`ore_flag_write`: cuStreamWriteValue32, or a one-thread st.release.sys kernel over
+NVLink for a peer address); the presenter's present stream waits on the slots (`ore_flag_wait_geq`:
+cuStreamWaitValue32) and acknowledges a consumed frame by storing into every rank's `ack` flag, which is
+what lets a rank reuse a ring buffer.  Nobody blocks on anybody else's kernels.
+
+Host-resident frames (the drop-in contract: `setPixelBuff` reads a HOST pointer, window.cpp:130-132):
+`SharedHostFrame` is ONE POSIX shared-memory frame ring mapped and pinned by every rank; each rank copies
+its own row blocks there over its own PCIe link (`ore_render_async_signal`, rows in place) and the
+completion / consumed counters live in the same shared memory.
+
 The band producer is pluggable so the host logic can be tested on CPU with the `gloo`
 backend (tests/test_multigpu_cpu.py) - there the producer is the CPU checker.
 """
@@ -111,9 +123,33 @@ def render_frame_sharded(gatherer: BandGatherer, produce_band):
 
 # ---- CUDA IPC peer mapping (presenter framebuffer visible to every rank) -----------------------
 
+ROW_BLOCK = 8  # rows are dealt to the ranks in blocks of 8 (= the primary kernel's tile height)
+
+
+def block_band(rank: int, world: int, height: int, block: int = ROW_BLOCK) -> dict:
+    """Block-interleaved rows of one rank as ore_frame fields: blocks of `block` rows, rank r owns blocks r, r+P, ...
+    A rank whose first block starts past the image gets an EMPTY band (y0 == y1), not an error."""
+    if world <= 1:
+        return dict(y0=0, y1=height, y_step=1, y_block=1)
+    y0 = min(block * rank, height)
+    return dict(y0=y0, y1=height, y_step=block * world, y_block=block)
+
+
+def block_rows(rank: int, world: int, height: int, block: int = ROW_BLOCK):
+    """image rows of `rank` under block_band (host-side mirror of the C ABI's row rule)"""
+    if world <= 1:
+        return list(range(height))
+    return [y for y in range(height) if (y // block) % world == rank]
+
+
 class PeerFrame:
-    """Rank 0 owns `n_buffers` ping-pong framebuffers (plain cudaMalloc through the C ABI); every
-    rank maps them with CUDA IPC and its render kernels store rows straight into them."""
+    """Rank 0 owns `n_buffers` ring framebuffers (plain cudaMalloc through the C ABI); every rank maps them with
+    CUDA IPC and its render kernels store rows straight into them over NVLink.  Completion and buffer reuse are
+    signalled with stream-ordered flags (module docstring), not with a collective:
+      done[r]  (presenter memory, one slot per rank): frames rank r has finished storing
+      ack      (one flag in EVERY rank's memory, written by the presenter): frames the presenter has consumed"""
+
+    ROW_BLOCK = ROW_BLOCK
 
     def __init__(self, renderer, width: int, height: int, n_buffers: int = 2, group=None):
         import torch.distributed as dist
@@ -126,12 +162,17 @@ class PeerFrame:
         self.nbytes = 4 * width * height
         self.ptrs = []
         self._owned, self._opened = [], []
+        self.n_buffers = n_buffers
+        self.submitted = 0    # frames this rank has submitted
+        self.presented = 0    # frames the presenter has enqueued for presentation (rank 0 only)
         if self.rank == 0:
             for _ in range(n_buffers):
                 p = renderer.dev_alloc(self.nbytes)
                 self._owned.append(p)
                 self.ptrs.append(p)
-            payload = [[renderer.ipc_export(p) for p in self.ptrs]]
+            self.done = renderer.dev_alloc(256 * max(1, self.world))   # one 256-byte line per rank (zeroed)
+            self._owned.append(self.done)
+            payload = [[renderer.ipc_export(p) for p in self.ptrs] + [renderer.ipc_export(self.done)]]
         else:
             payload = [None]
         if self.world > 1:
@@ -140,17 +181,56 @@ class PeerFrame:
             for handle in payload[0]:
                 p = renderer.ipc_import(handle)
                 self._opened.append(p)
-                self.ptrs.append(p)
-
-    ROW_BLOCK = 8  # rows are dealt to the ranks in blocks of 8 (= the primary kernel's tile height)
+            self.ptrs = self._opened[:-1]
+            self.done = self._opened[-1]
+        # every rank's ack flag, mapped by the presenter
+        self.ack = renderer.dev_alloc(256)
+        self._owned.append(self.ack)
+        self.acks = [self.ack]
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, renderer.ipc_export(self.ack), group=group)
+            if self.rank == 0:
+                self.acks = [self.ack]
+                for h in handles[1:]:
+                    p = renderer.ipc_import(h)
+                    self._opened.append(p)
+                    self.acks.append(p)
 
     def band_args(self, buf: int) -> dict:
         """kwargs for Renderer.render_device: this rank's block-interleaved rows of buffer `buf`, stored at
         their image position in the presenter's frame."""
-        b = self.ROW_BLOCK if self.world > 1 else 1
-        y0 = b * self.rank
-        return dict(out_ptr=self.ptrs[buf] + 4 * self.width * y0, y0=y0, y1=self.height,
-                    y_step=b * self.world, y_block=b, out_pitch=self.width)
+        b = block_band(self.rank, self.world, self.height, self.ROW_BLOCK)
+        return dict(out_ptr=self.ptrs[buf] + 4 * self.width * b["y0"], out_pitch=self.width, **b)
+
+    # ---- one frame, flag protocol ----
+    def submit(self, camera, stream: int = 0, flags: int = 0, renderer=None):
+        """Render this rank's rows of the next frame into its ring buffer on `stream` and announce them.  Waits (on
+        the stream, not on the host) until the presenter has consumed the frame that used the buffer before."""
+        rr = renderer or self.r
+        g = self.submitted
+        if g >= self.n_buffers:
+            rr.flag_wait_geq(self.ack, g - self.n_buffers + 1, stream)
+        rr.render_device(camera, self.width, self.height, stream=stream, flags=flags, **self.band_args(g % self.n_buffers))
+        # frames in flight on several streams may finish out of order: the flag goes out on the primary context's
+        # in-order signal stream, behind this frame's kernels
+        self.r.flag_write_after(self.done + 256 * self.rank, g + 1, stream)
+        self.submitted = g + 1
+        return g
+
+    def present(self, stream: int, consume=None):
+        """Presenter only: on `stream`, wait for every rank's rows of the next frame, run `consume(buffer_ptr, g)`
+        (enqueue-only work such as a device->host copy), then acknowledge the frame to every rank."""
+        assert self.rank == 0
+        g = self.presented
+        for r in range(self.world):
+            self.r.flag_wait_geq(self.done + 256 * r, g + 1, stream)
+        if consume is not None:
+            consume(self.ptrs[g % self.n_buffers], g)
+        for a in self.acks:
+            self.r.flag_write(a, g + 1, stream)
+        self.presented = g + 1
+        return g
 
     def close(self):
         for p in self._opened:
@@ -158,6 +238,111 @@ class PeerFrame:
         for p in self._owned:
             self.r.dev_free(p)
         self._opened, self._owned = [], []
+
+
+# ---- one shared, pinned HOST frame ring written by every rank over its own PCIe link ------------------------
+
+class SharedHostFrame:
+    """POSIX shared memory: [header: done[world] and consumed, one 64-byte line each][n_buffers frames].
+    Every rank maps it, pins it (`register(ptr, nbytes)`, e.g. Renderer.host_register) and copies its own row blocks
+    into it; rank 0 is the presenter: the host code that would hand the frame to setPixelBuff.
+      done[r]   = frames whose rows rank r has landed in host memory (written by the GPU's copy stream)
+      consumed  = frames the presenter has consumed (written by the presenter's host thread)"""
+
+    LINE = 64
+    HEADER = 4096
+
+    def __init__(self, width: int, height: int, rank: int, world: int, n_buffers: int = 3, name: str | None = None,
+                 register=None, unregister=None, block: int = ROW_BLOCK):
+        from multiprocessing import shared_memory
+
+        self.width, self.height, self.rank, self.world = width, height, rank, world
+        self.n_buffers, self.block = n_buffers, block
+        self.frame_bytes = 4 * width * height
+        total = self.HEADER + n_buffers * self.frame_bytes
+        assert (world + 1) * self.LINE <= self.HEADER
+        self.owner = name is None
+        if self.owner:
+            self.shm = shared_memory.SharedMemory(create=True, size=total)
+            self.shm.buf[: self.HEADER] = bytes(self.HEADER)
+        else:
+            self.shm = shared_memory.SharedMemory(name=name)
+        self.name = self.shm.name
+        self._flags = np.ndarray((self.HEADER // 4,), dtype=np.uint32, buffer=self.shm.buf)
+        self.frames = [np.ndarray((height, width), dtype=np.uint32, buffer=self.shm.buf,
+                                  offset=self.HEADER + i * self.frame_bytes) for i in range(n_buffers)]
+        self.base = self._flags.ctypes.data
+        self._unregister = unregister
+        self._registered = False
+        if register is not None:
+            register(self.base, total)
+            self._registered = True
+        self.submitted = 0
+        self.presented = 0
+
+    # addresses / views
+    def done_addr(self, r: int) -> int:
+        return self.base + r * self.LINE
+
+    def done(self, r: int) -> int:
+        return int(self._flags[r * self.LINE // 4])
+
+    def set_done(self, r: int, value: int):   # CPU producers (tests); GPU producers write it from the copy stream
+        self._flags[r * self.LINE // 4] = value
+
+    @property
+    def consumed(self) -> int:
+        return int(self._flags[self.world * self.LINE // 4])
+
+    def _set_consumed(self, v: int):
+        self._flags[self.world * self.LINE // 4] = v
+
+    def band(self) -> dict:
+        return block_band(self.rank, self.world, self.height, self.block)
+
+    def row_addr(self, buf: int, y: int) -> int:
+        return self.base + self.HEADER + buf * self.frame_bytes + 4 * self.width * y
+
+    # protocol
+    def can_submit(self) -> bool:
+        """the ring buffer of the next frame is free once the presenter has consumed the frame that used it before"""
+        return self.consumed + self.n_buffers > self.submitted
+
+    def next_slot(self):
+        """(frame number g, buffer index) of this rank's next frame; call can_submit() first"""
+        g = self.submitted
+        self.submitted = g + 1
+        return g, g % self.n_buffers
+
+    def ready(self) -> bool:
+        """presenter: every rank's rows of the next frame to present have landed"""
+        f = self.presented
+        return all(self.done(r) >= f + 1 for r in range(self.world))
+
+    def present(self, consume=None) -> int:
+        """presenter: consume the next frame (call ready() first) and release its buffer"""
+        f = self.presented
+        if consume is not None:
+            consume(self.frames[f % self.n_buffers], f)
+        self.presented = f + 1
+        self._set_consumed(f + 1)
+        return f
+
+    def close(self):
+        if self._registered and self._unregister is not None:
+            self._unregister(self.base)
+        self._registered = False
+        self._flags = None
+        self.frames = []
+        try:
+            self.shm.close()
+        except BufferError:
+            pass
+        if self.owner:
+            try:
+                self.shm.unlink()
+            except FileNotFoundError:
+                pass
 
 
 def numpy_band_from_frame(frame: np.ndarray, rank: int, world: int) -> np.ndarray:

@@ -24,7 +24,7 @@ def test_library_builds_and_exports_all_symbols(pkg):
     lib = ctypes.CDLL(path)
     for name in declared_functions():
         assert hasattr(lib, name), name
-    assert lib.ore_abi_version() == 1
+    assert lib.ore_abi_version() == 2
 
 
 def test_library_carries_only_an_sm100a_image(pkg):
