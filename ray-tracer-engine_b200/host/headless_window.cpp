@@ -2,7 +2,7 @@
 // window.h callbacks and a main() that drives onStart()/update() like wWinMain (window.cpp:57-84) does,
 // with a scripted camera orbit instead of the message pump, and writes the last frame as a PPM.
 //
-//   ore_headless [width height frames spheres out.ppm mesh.obj]
+//   ore_headless [width height frames spheres out.ppm mesh.obj|- pipelined(0|1)]
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -32,12 +32,15 @@ int main(int argc, char** argv) {
     const int frames = argc > 3 ? atoi(argv[3]) : 8;
     const int spheres = argc > 4 ? atoi(argv[4]) : 64;
     const char* out = argc > 5 ? argv[5] : nullptr;
-    if (argc > 6) oreSetMeshFile(argv[6]);
+    if (argc > 6 && strcmp(argv[6], "-") != 0) oreSetMeshFile(argv[6]);
+    const int pipelined = argc > 7 ? atoi(argv[7]) : 0;
+    oreConfigurePresentation(pipelined);
     render.buffmemory.assign((size_t)render.width * render.height, 0u);
 
     oreConfigureScene(spheres, 1u, nullptr, nullptr);
     onStart();
     update();  // warm-up (context buffers, module load)
+    oreFlush();
     const auto t0 = std::chrono::steady_clock::now();
     for (int f = 0; f < frames; f++) {
         // orbit about the cube centre (5,5,5), radius 12, facing the centre (see scene.orbit_camera)
@@ -47,13 +50,14 @@ int main(int argc, char** argv) {
                      (float)yaw, (float)pitch);
         update();
     }
+    oreFlush();  // pipelined mode: the last frame is still in flight
     const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     unsigned long long sum = 0;
     for (unsigned v : render.buffmemory) sum += v;
     printf("{\"width\": %d, \"height\": %d, \"frames\": %d, \"spheres\": %d, \"ms_per_frame\": %.3f, \"mrays_per_s\": %.1f, "
-           "\"checksum\": %llu}\n",
+           "\"checksum\": %llu, \"pipelined\": %d}\n",
            render.width, render.height, frames, spheres, sec / frames * 1e3,
-           (double)render.width * render.height * frames / sec / 1e6, sum);
+           (double)render.width * render.height * frames / sec / 1e6, sum, pipelined);
     if (out) {
         FILE* fp = fopen(out, "wb");
         if (fp) {

@@ -9,6 +9,7 @@
 #include "ore_host.h"
 
 #include <cmath>
+#include <cstdint>
 #include <cstdlib>
 #include <string>
 #include <vector>
@@ -34,8 +35,13 @@ std::string g_sky = "proc:smooth:1024:512:203";
 std::string g_obj;                                                     // loadMesh(file, ...), kernel.cu:1706
 sprite* texture = nullptr;
 sprite* skyTex = nullptr;
-unsigned int* g_pixels = nullptr;  // pinned host frame handed to setPixelBuff
+unsigned int* g_pixels = nullptr;  // pinned host frame(s) handed to setPixelBuff: [2][cap] when pipelined
 size_t g_pixels_cap = 0;
+// pipelined presentation (oreConfigurePresentation(1)): update() enqueues frame f (render + async copy into one of
+// two pinned frames) and hands setPixelBuff frame f-1, whose copy overlapped this frame's kernels
+bool g_pipelined = false;
+volatile uint32_t* g_done = nullptr;   // pinned: number of frames whose copy has landed (written by the copy stream)
+uint32_t g_submitted = 0, g_presented = 0;
 
 unsigned msvc_rand(unsigned& s) {
     s = s * 214013u + 2531011u;
@@ -51,6 +57,8 @@ void oreConfigureScene(int sphere_count, unsigned seed, const char* tex, const c
 }
 
 void oreSetMeshFile(const char* obj_path) { g_obj = obj_path ? obj_path : ""; }
+
+void oreConfigurePresentation(int pipelined) { g_pipelined = pipelined != 0; }
 
 void oreSetCamera(float x, float y, float z, float yaw_deg, float pitch_deg) {
     cam.org[0] = x;
@@ -93,22 +101,52 @@ void onStart() {
     checkOre(ore_set_lights(g_ctx, &lights[0][0], light_size));
 }
 
+static void present_next() {
+    // frame g_presented is complete once the copy stream has stored g_presented + 1 into the pinned counter
+    while ((int32_t)(*g_done - (g_presented + 1)) < 0) {
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    setPixelBuff(g_pixels + (size_t)(g_presented & 1u) * g_pixels_cap);
+    g_presented++;
+}
+
 void update() {
     // checkKey() (kernel.cu:1716-1759) is Win32 key polling; headless callers use oreSetCamera()
     const int width = getScreenWidth(), height = getScreenHeight();
     const size_t n = (size_t)width * height;
     cam.aspect = (float)height / width;  // kernel.cu:1773 (never read by the kernel)
     if (n > g_pixels_cap) {
+        if (g_pipelined) oreFlush();
         if (g_pixels) checkCudaErrors(cudaFreeHost(g_pixels));
-        checkCudaErrors(cudaMallocHost((void**)&g_pixels, n * sizeof(unsigned int)));
+        checkCudaErrors(cudaMallocHost((void**)&g_pixels, 2 * n * sizeof(unsigned int)));
         g_pixels_cap = n;
     }
-    ore_frame fr = {width, height, 0, height, 1, aspect, ORE_FLAG_NONE, 0, 0};
-    checkOre(ore_render(g_ctx, &cam, &fr, g_pixels));  // launch + sync + device->host, like :1783-1788
-    setPixelBuff(g_pixels);
+    if (!g_done) {
+        checkCudaErrors(cudaMallocHost((void**)&g_done, 64));
+        *g_done = 0;
+    }
+    ore_frame fr = {width, height, 0, height, 1, aspect, ORE_FLAG_NO_KERNEL_TIMING, 0, 0};
+    if (!g_pipelined) {
+        checkOre(ore_render(g_ctx, &cam, &fr, g_pixels));  // launch + sync + device->host, like :1783-1788
+        setPixelBuff(g_pixels);
+        return;
+    }
+    // throughput mode: one frame of latency, no host stall on this frame's kernels
+    checkOre(ore_render_async_signal(g_ctx, &cam, &fr, g_pixels + (size_t)(g_submitted & 1u) * g_pixels_cap,
+                                     (uint32_t*)g_done, g_submitted + 1));
+    g_submitted++;
+    if (g_submitted - g_presented >= 2) present_next();
+}
+
+void oreFlush() {
+    while (g_presented < g_submitted) present_next();
 }
 
 void oreShutdown() {
+    if (g_ctx) ore_wait(g_ctx);
+    g_presented = g_submitted;
     if (g_ctx) ore_destroy(g_ctx);
     g_ctx = nullptr;
     delete texture;
@@ -117,4 +155,7 @@ void oreShutdown() {
     if (g_pixels) cudaFreeHost(g_pixels);
     g_pixels = nullptr;
     g_pixels_cap = 0;
+    if (g_done) cudaFreeHost((void*)g_done);
+    g_done = nullptr;
+    g_submitted = g_presented = 0;
 }

@@ -13,5 +13,11 @@ void oreSetCamera(float x, float y, float z, float yaw_deg, float pitch_deg);
 void oreConfigureScene(int sphere_count, unsigned seed, const char* texture, const char* sky);
 // triangle mesh for onStart(): an OBJ file in the reference's dialect (kernel.cu:1706); call before onStart()
 void oreSetMeshFile(const char* obj_path);
+// Presentation mode of update().  0 (default): the reference's synchronous semantics - update() returns after the
+// frame has been handed to setPixelBuff (kernel.cu:1786-1788).  1: pipelined - update() enqueues frame f (kernels +
+// asynchronous copy into one of two pinned host frames) and hands setPixelBuff frame f-1, whose copy overlapped
+// frame f's kernels; oreFlush() presents what is still in flight.  Call before the first update().
+void oreConfigurePresentation(int pipelined);
+void oreFlush();
 // release the render context (the reference never frees its globals)
 void oreShutdown();
