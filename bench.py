@@ -9,14 +9,19 @@
 A "step" is one frame: one pass of the hot path (frame prep -> primary nearest hit -> shadow +
 shade -> packed framebuffer) over one camera of the orbit.  Default workload = BASELINE.json
 configs[3] (7680x4320, 1024 spheres): the configuration the 1/2/4/8-GPU metric is quoted on; it fits
-one GPU, so the SAME workload runs at every N (at N = 1 the line also carries the 4K / 1024-sphere
-figures of configs[2], the scene of the single-GPU roofline target).  With N > 1 the frame is split into interleaved row bands
-(strong scaling) that the ranks store straight into the presenting GPU's framebuffer over
-NVLink (peer-mapped), plus one tiny NCCL all-reduce per frame as the completion signal.
+one GPU, so the SAME workload and the SAME code path run at every N (strong scaling).  With N > 1 the
+frame is split into block-interleaved row bands.
 
-Prints ONE JSON line on rank 0 (contract in the task statement): value = whole-job Mrays/s with
-inputs resident in HBM; e2e = the same through the C ABI with HOST output buffers; roofline =
-FP32 accounting of the dominant kernel; cpu_baseline = the CPU checker timed on a bounded sample.
+value : every rank's kernels store their rows straight into the presenting GPU's frame ring over NVLink
+        (peer-mapped); completion and ring-buffer reuse are signalled with stream-ordered flags
+        (ore_flag_write / ore_flag_wait_geq), not with a collective.  Device-resident, CUDA events, max over ranks.
+e2e   : every rank copies its own rows into ONE shared pinned HOST frame ring (POSIX shared memory registered with
+        CUDA) over its own PCIe link, asynchronously behind its kernels; the presenter (rank 0's host thread) sees
+        the per-rank completion counters in the same shared memory.  The device->host copies are inside the timed
+        region.  Same code at N = 1.
+
+Prints ONE JSON line on rank 0 (contract in the task statement).  `config` is the same object in both arms
+(--impl ours / reference); run details live under `run`.
 """
 from __future__ import annotations
 
@@ -42,7 +47,7 @@ WORKLOADS = {
     "8k1024": (7680, 4320, 1024, 3, "scaled", "configs[3]: 7680x4320, 1024 spheres S(1024,3), row bands"),
     "4k16384": (3840, 2160, 16384, 5, "scaled", "configs[4]: 3840x2160, 16384 spheres S(16384,5)"),
 }
-FLOP_PER_TEST = 18
+FLOP_PER_TEST = 18  # the reference formula after CSE, per ray-sphere test
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
 
 
@@ -54,6 +59,12 @@ def make_workload(pkg, name):
         return pkg.scene.reference_camera() if kind == "reference" else pkg.scene.orbit_camera(sc, frame % 240)
 
     return W, H, sc, camera, desc
+
+
+def base_config(desc, W, H, sc):
+    """the SAME object in both arms (the driver compares it)"""
+    return {"workload": desc, "width": W, "height": H, "n_spheres": sc.n_spheres, "n_lights": int(sc.lights.shape[0]),
+            "rays_per_pixel": 1, "scene": sc.name}
 
 
 class ClockSampler:
@@ -70,7 +81,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -79,12 +90,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.05)
+        time.sleep(0.06)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -92,7 +103,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = self.rows
+        if t_begin is not None:
+            inside = [r for r in rows if t_begin - 0.06 <= r[0] <= t_end + 0.12]
+            rows = inside or rows
+        for _, r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 9:
                 continue
@@ -109,48 +124,22 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def issue_block(workload):
-    """Executed-instruction side of the default path's kernels, from the committed ncu summaries (profiles/): how busy
-    the issue slots and the FMA pipe are.  Static context for the line (ncu never runs inside bench.py); None when the
-    summaries are for another workload or unreadable."""
+def measured_hbm_peak():
     try:
-        if workload != "8k1024":
-            return None
-        out = {"source": "profiles/r01_ncu_{shade_setup,shadow_beam_staged,primary_tile}_8k1024.json (ncu --set full, "
-                         "one launch each, --clock-control none)", "kernels": {}}
-        for key, fn in (("shade_setup_kernel", "r01_ncu_shade_setup_8k1024.json"),
-                        ("shadow_beam_kernel (staged)", "r01_ncu_shadow_beam_staged_8k1024.json"),
-                        ("primary_tile_kernel", "r01_ncu_primary_tile_8k1024.json")):
-            m = json.load(open(os.path.join(ROOT, "profiles", fn)))["metrics"]
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
 
-            def num(name):
-                return float(str(m[name]).split()[0])
 
-            out["kernels"][key] = {
-                "issue_slot_utilisation": num("smsp__issue_active.avg.pct_of_peak_sustained_active") / 100.0,
-                "fma_pipe_utilisation": num("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active") / 100.0,
-                "ncu_ms": num("gpu__time_duration.sum"),
-                "registers": int(num("launch__registers_per_thread")),
-            }
-        return out
+def executed_table(workload):
+    """Executed FP32 work per unit of each kernel: committed ncu op counts (fadd + fmul + 2 ffma, thread level,
+    predicated on) divided by the units the profiled launch processed (profiles/r02_executed_flops.json, written by
+    tools/executed_flops.py from an `ncu --metrics smsp__sass_thread_inst_executed_op_*` capture).  bench.py multiplies
+    them by the LIVE unit counts of the timed frames and divides by the LIVE kernel times."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r02_executed_flops.json"))).get(workload)
     except Exception:
         return None
-
-
-def hbm_block(traffic_bytes, kernel_ms):
-    """DRAM side of the dominant kernel against the measured HBM peak (MEASURED_PEAKS.json, else the recipe's fallback)"""
-    peak, src = 6650.0, "fallback (B200_PROFILING.md)"
-    try:
-        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
-        src = "MEASURED_PEAKS.json"
-    except Exception:
-        pass
-    if not traffic_bytes:
-        return {"peak_gbs": peak, "peak_source": src, "achieved_gbs": None, "frac": None}
-    ach = traffic_bytes / (kernel_ms * 1e-3) / 1e9
-    return {"peak_gbs": peak, "peak_source": src, "achieved_gbs": ach, "frac": ach / peak,
-            "note": "ncu dram bytes of the shadow pass of one frame / its CUDA-event time (the staging buffer between the "
-                    "two shadow kernels is most of it); the pass is instruction-issue bound, not HBM-bound"}
 
 
 def dist_env():
@@ -160,49 +149,57 @@ def dist_env():
     return rank, local, world
 
 
+def host_threads():
+    """threads the CPU arm can really use: the affinity mask, not OMP_NUM_THREADS (torchrun sets that to 1)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 # ---------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the reference's own CPU code (oracle/_ref) or its C restatement
 # ---------------------------------------------------------------------------------------------
-def cpu_sample_plan(orc, sc, cam, W, H, budget_s):
+def cpu_sample_plan(orc, sc, cam, W, H, budget_s, n_threads):
     """pick a row stride so that one sample costs about `budget_s` seconds on the host cores"""
     probe_step = max(1, H // 8)
     t0 = time.perf_counter()
-    orc.render(sc, cam, W, H, y0=probe_step // 2, y_step=probe_step, want_ids=False, want_t=False)
+    orc.render(sc, cam, W, H, y0=probe_step // 2, y_step=probe_step, want_ids=False, want_t=False, n_threads=n_threads)
     dt = time.perf_counter() - t0
     rows_probe = (H - probe_step // 2 + probe_step - 1) // probe_step
     per_row = dt / max(1, rows_probe)
     rows = int(max(1, min(H, budget_s / max(per_row, 1e-9))))
-    step = max(1, H // rows)
-    return step
+    return max(1, H // rows)
 
 
 def run_cpu(args, pkg, what):
-    """times the CPU checker on a bounded sample; returns (mrays, info)"""
+    """times the CPU checker on a bounded sample; returns (mrays, info, seconds per step)"""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oraclelib  # the one place bench.py executes oracle/ (cpu_baseline + --impl reference)
 
     orc = oraclelib.load("best")
     W, H, sc, camera, desc = make_workload(pkg, args.workload)
-    cores = os.cpu_count() or 1
+    n_thr = host_threads()          # passed explicitly: omp_set_num_threads(n) inside the checker
     n_steps = args.steps if what == "reference" else 1
     n_warm = args.warmup if what == "reference" else 0
     budget = min(10.0, 150.0 / max(1, n_steps + n_warm)) if what == "reference" else 12.0
-    step = cpu_sample_plan(orc, sc, camera(0), W, H, budget)
+    step = cpu_sample_plan(orc, sc, camera(0), W, H, budget, n_thr)
     y0 = step // 2
     rows = (H - y0 + step - 1) // step
     times = []
     for i in range(n_warm + n_steps):
         cam = camera(i if what == "reference" else 0)
         t0 = time.perf_counter()
-        orc.render(sc, cam, W, H, y0=y0, y_step=step, want_ids=False, want_t=False)
+        orc.render(sc, cam, W, H, y0=y0, y_step=step, want_ids=False, want_t=False, n_threads=n_thr)
         dt = time.perf_counter() - t0
         if i >= n_warm:
             times.append(dt)
     total = sum(times)
     mrays = rows * W * len(times) / total / 1e6
-    info = {"value": mrays, "unit": "Mrays/s", "cores": cores, "kind": orc.kind,
+    info = {"value": mrays, "unit": "Mrays/s", "cores": n_thr, "kind": orc.kind,
             "sample": f"rows {y0}::{step} of each {W}x{H} frame ({rows} rows, {rows * W} primary rays per step, "
-                      f"{len(times)} step(s), {total:.1f} s), all {cores} host threads (OpenMP)"}
+                      f"{len(times)} step(s), {total:.1f} s), {n_thr} OpenMP threads requested explicitly "
+                      f"(OMP_NUM_THREADS in the environment: {os.environ.get('OMP_NUM_THREADS', 'unset')})"}
     return mrays, info, total / len(times)
 
 
@@ -213,9 +210,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="8k1024", choices=sorted(WORKLOADS))
-    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the N = 1 side measurements (4K, primary-only, fast libm, reference kernel)")
     ap.add_argument("--in-flight", type=int, default=4, help="frames in flight per GPU (contexts/streams used round-robin)")
+    ap.add_argument("--host-buffers", type=int, default=3, help="frames in the shared host ring of the e2e path")
+    ap.add_argument("--emulate-world", type=int, default=0,
+                    help="tool, single process only: render just the rows rank --emulate-rank of this many ranks would "
+                         "render (isolates per-rank effects of short frames from NVLink effects); the line says so")
+    ap.add_argument("--emulate-rank", type=int, default=0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank, local, world = dist_env()
@@ -223,8 +225,7 @@ def main():
     import rte_b200
     pkg = rte_b200.pkg
     W, H, sc, camera, desc = make_workload(pkg, args.workload)
-    config = {"workload": desc, "width": W, "height": H, "n_spheres": sc.n_spheres, "n_lights": int(sc.lights.shape[0]),
-              "rays_per_pixel": 1, "scene": sc.name}
+    config = base_config(desc, W, H, sc)
 
     if args.impl == "reference":
         if rank != 0:
@@ -246,370 +247,382 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the render path has no CPU fallback")
     torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on stdout; rank 0's stdout is ONE JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=dev)
+    emulate = args.emulate_world if (world == 1 and args.emulate_world > 1) else 0
+    mg = pkg.multigpu
+    F = pkg.capi
     pkg.build.build_library()
-    r = pkg.Renderer(local)
-    r.set_scene(sc)
-    stream = torch.cuda.Stream(device=local)
-    # a second context + stream: consecutive frames alternate between the two, so frame f+1's kernels fill the
-    # SMs that frame f's persistent CTAs vacate at the end of a kernel (double-buffered rendering; every frame
-    # still completes inside the timed region)
-    ctxs = [(r, stream)]
-    for _ in range(max(1, args.in_flight) - 1):
+    NF = max(1, args.in_flight)
+    ctxs = []
+    for _ in range(NF):
         rx = pkg.Renderer(local)
         rx.set_scene(sc)
         ctxs.append((rx, torch.cuda.Stream(device=local)))
-    NF = len(ctxs)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")  # > 126 MB L2
-    sync_t = torch.zeros(1, dtype=torch.int32, device=f"cuda:{local}")
-
-    peer = None
-    gatherer = None
-    gather_mode = args.gather
-    if not (world > 1 and gather_mode == "nccl"):
-        err = None
-        try:
-            peer = pkg.multigpu.PeerFrame(r, W, H, n_buffers=max(2, args.in_flight))
-        except Exception as e:  # CUDA IPC refused (e.g. separate IPC namespaces): decided collectively below
-            err = e
-        if world > 1:
-            bad = torch.tensor([1 if err is not None else 0], dtype=torch.int32, device=f"cuda:{local}")
-            dist.all_reduce(bad, op=dist.ReduceOp.MAX)
-            if int(bad.item()):
-                if rank == 0:
-                    print(f"bench.py: peer-mapped framebuffer unavailable ({err}); using the NCCL band gather", file=sys.stderr)
-                if peer is not None:
-                    peer.close()
-                peer, gather_mode = None, "nccl"
-        elif err is not None:
-            raise err
-    if peer is None:
-        gatherer = pkg.multigpu.BandGatherer(W, H, torch.device("cuda", local))
+    r, stream = ctxs[0]
+    present_stream = torch.cuda.Stream(device=local)
+    # frame ring on the presenter + completion / ack flags
+    peer = mg.PeerFrame(r, W, H, n_buffers=NF, band_of=(args.emulate_rank, emulate) if emulate else None)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def render_step(f, which=0):
-        """device-resident step: this rank's rows of frame f into the presenter's framebuffer"""
-        cam = camera(f)
-        rr, st = ctxs[which]
-        with torch.cuda.stream(st):
-            if peer is not None:
-                rr.render_device(cam, W, H, stream=st.cuda_stream, **peer.band_args(f % len(peer.ptrs)))
-                if world > 1:
-                    dist.all_reduce(sync_t)  # completion signal: every rank's rows of frame f have landed
-            else:
-                plan = gatherer.plan
-                rr.render_device(cam, W, H, out_ptr=gatherer.band.data_ptr(), stream=st.cuda_stream,
-                                 y0=plan.y0, y1=H, y_step=plan.y_step)
-                gatherer.gather()
+    def render_step(f, flags=F.ORE_FLAG_NO_KERNEL_TIMING):
+        """device-resident step: this rank's rows of frame f into the presenter's ring, announced by a flag"""
+        rr, st = ctxs[peer.submitted % NF]
+        peer.submit(camera(f), stream=st.cuda_stream, flags=flags, renderer=rr)
+        if rank == 0:
+            # presenter: on the present stream, wait for every rank's rows of the frame, then acknowledge it to all
+            peer.present(present_stream.cuda_stream)
 
-    def flush_l2():
-        with torch.cuda.stream(stream):
-            flush.fill_(1)
+    def join_streams(ev_list=None):
+        """make `stream` wait for everything enqueued on the other streams of this rank"""
+        sig = r.stream_handle(2)
+        others = [st for _, st in ctxs[1:]] + [present_stream] + ([torch.cuda.ExternalStream(sig, device=dev)] if sig else [])
+        for st in others:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            stream.wait_event(ev)
 
-    overlap = (gatherer is None)   # the NCCL-gather variant reuses one band buffer: no frame overlap there
     frame_bytes = W * H * 4
-    l2_note = ("not flushed: every step writes a fresh framebuffer plus per-pixel hit records "
-               f"({3 * frame_bytes / 1e6:.0f} MB per step, L2 is 126 MB) and reads 64 KB of scene records that the kernels "
-               "keep in shared memory by design; nothing a step touches can be served from the previous step's L2")
-    small_frame = 3 * frame_bytes / max(1, world) < (160 << 20)
-    if small_frame:
-        l2_note = "flushed before every step (256 MiB fill on the step's stream, inside the timed region)"
+    n_rows_mine = pkg.Renderer.rows(H, **mg.block_band(peer.band_rank, peer.band_world, H))
 
-    # warm-up (both contexts)
-    for f in range(max(args.warmup, 2) * (NF if overlap else 1)):
-        render_step(f, f % NF if overlap else 0)
+    # warm-up (every context)
+    for f in range(max(args.warmup, 2) * NF):
+        render_step(f)
     barrier()
+    # hit pixels of this rank's band (for the working-set note and the roofline units)
+    warm_hits = r.counters()["hit_pixels"]
 
     sampler = ClockSampler(local)
     sampler.start()
-    kernel_ms = []
+    time.sleep(0.15)
     ev_start = torch.cuda.Event(enable_timing=True)
     ev_end = torch.cuda.Event(enable_timing=True)
     barrier()
+    t_begin = time.perf_counter()
     ev_start.record(stream)
     for _, st in ctxs[1:]:
         st.wait_event(ev_start)
+    present_stream.wait_event(ev_start)
+    t_host0 = time.perf_counter()
     for i in range(args.steps):
-        which = i % NF if overlap else 0
-        if small_frame:
-            with torch.cuda.stream(ctxs[which][1]):
-                flush.fill_(1)
-        render_step(args.warmup + i, which)   # no host sync inside the timed region
-    for _, st in ctxs[1:]:
-        ev_other = torch.cuda.Event()
-        ev_other.record(st)
-        stream.wait_event(ev_other)
+        render_step(args.warmup + i)   # no host sync, no collective inside the timed region
+    t_host1 = time.perf_counter()
+    join_streams()
     ev_end.record(stream)
     barrier()
-    clocks = sampler.stop()
-    # per-kernel device times (CUDA events inside the library, on the launching stream): separate untimed pass,
-    # one frame at a time
-    for i in range(min(args.steps, 8)):
-        render_step(args.warmup + i, 0)
-        stream.synchronize()
-        kernel_ms.append(r.kernel_ms())
-    launches_per_frame = int(r.counters()["kernel_launches"])   # counted by the library per render call
-    barrier()
-    total_ms = torch.tensor([ev_start.elapsed_time(ev_end)], dtype=torch.float64, device=f"cuda:{local}")
+    t_end = time.perf_counter()
+    clocks = sampler.stop(t_begin, t_end)
+    total_ms = torch.tensor([ev_start.elapsed_time(ev_end)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
     value = W * H * args.steps / (total_ms * 1e-3) / 1e6
+    host_issue_ms = (t_host1 - t_host0) * 1e3 / args.steps
 
-    # ---- e2e: through the C ABI with HOST output, device->host copy inside the timed region ----
-    # N = 1: ore_render_async into two pinned host framebuffers (frame f copies out while f+1 renders; all K
-    #        frames are on the host before the clock stops) and, for reference, the synchronous ore_render.
-    # N > 1: every rank renders its rows into the presenter's frame (peer stores), completion all-reduce, then the
-    #        presenter copies the frame to pinned host memory.
-    host = [r.host_alloc((H, W)) for _ in range(2)] if rank == 0 else None
-    frame_check = None
-
-    def e2e_sync_step(f):
-        cam = camera(f)
-        if world == 1:
-            r.render(cam, W, H, out=host[f % 2])     # ore_render: kernels + D2H of the frame, synchronous
-        else:
-            render_step(f)
-            stream.synchronize()
-            if rank == 0:
-                if peer is not None:
-                    r.copy_to_host(host[f % 2], peer.ptrs[f % len(peer.ptrs)])
-                else:
-                    host[f % 2][:] = gatherer.frame.cpu().numpy().view(np.uint32)
-
-    def timed_e2e(step_fn, finish_fn=None):
-        for f in range(2):
-            step_fn(f)
-        if finish_fn:
-            finish_fn()
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(args.steps):
-            step_fn(args.warmup + i)
-        if finish_fn:
-            finish_fn()
-        if world > 1:
-            dist.barrier()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{local}")
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        return W * H * args.steps / float(tt.item()) / 1e6
-
-    e2e_sync_value = timed_e2e(e2e_sync_step)
-    if world == 1:
-        e2e_value = timed_e2e(lambda f: r.render_async(camera(f), W, H, out=host[f % 2]), r.wait)
-        e2e_mode = "pipelined: ore_render_async x K + ore_wait, two pinned host framebuffers"
-    else:
-        e2e_value = e2e_sync_value
-        e2e_mode = "peer-written frame, completion all-reduce, presenter D2H to pinned host memory, per frame"
-        # correctness of the sharded frame: the presenter re-renders the last frame alone and compares
-        if rank == 0:
-            last = args.warmup + args.steps - 1
-            alone = r.render(camera(last), W, H)
-            frame_check = "identical" if np.array_equal(alone, host[last % 2]) else "MISMATCH"
+    # ---- per-kernel device times (CUDA events inside the library, on the launching stream): separate untimed
+    # ---- pass, one frame at a time
+    kernel_ms = []
+    for i in range(min(args.steps, 8)):
+        render_step(args.warmup + i, flags=0)
+        torch.cuda.synchronize()
+        kernel_ms.append(ctxs[(peer.submitted - 1) % NF][0].kernel_ms())
+    launches_per_frame = int(ctxs[(peer.submitted - 1) % NF][0].counters()["kernel_launches"])
     barrier()
 
-    # ---- roofline accounting (untimed): reference-order test counts of the SAME frames ----
-    own = {"primary": 0.0, "shadow": 0.0, "sky": 0.0, "hits": 0.0}
-    if peer is not None:
-        band_kw = peer.band_args(0)
-    else:
-        band_kw = dict(out_ptr=gatherer.band.data_ptr(), y0=gatherer.plan.y0, y1=H, y_step=gatherer.plan.y_step)
-    count_out = peer.ptrs[0] if peer is not None else gatherer.band.data_ptr()
+    # ---- e2e: ONE shared pinned host frame ring, every rank copies its own rows over its own PCIe link ----------
+    NHB = max(2, args.host_buffers)
+    name = [None]
+    shared = None
+    if rank == 0:
+        shared = mg.SharedHostFrame(W, H, peer.band_rank, peer.band_world, n_buffers=NHB,
+                                    register=r.host_register, unregister=r.host_unregister)
+        name = [shared.name]
+    if world > 1:
+        dist.broadcast_object_list(name, src=0)
+        if rank != 0:
+            shared = mg.SharedHostFrame(W, H, rank, world, n_buffers=NHB, name=name[0], register=r.host_register,
+                                        unregister=r.host_unregister)
+    band = shared.band()
+    e2e_ranks = [shared.rank] if emulate else list(range(world))
+
+    def e2e_ready():
+        f = shared.presented
+        return all(shared.done(q) >= f + 1 for q in e2e_ranks)
+
+    def e2e_drain(upto, block):
+        while rank == 0 and shared.presented < upto:
+            if e2e_ready():
+                shared.present()
+            elif not block:
+                return
+    e2e_events = []
+
+    def e2e_run(n_frames, first_cam, timed):
+        """n_frames through ore_render_async_signal into the shared host ring"""
+        copy_stream = torch.cuda.ExternalStream(r.stream_handle(1), device=dev)
+        render_stream = torch.cuda.ExternalStream(r.stream_handle(0), device=dev)
+        target = shared.submitted + n_frames
+        if timed:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e0.record(render_stream)
+        for i in range(n_frames):
+            while not shared.can_submit():       # ring full: wait for the presenter (rank 0 keeps presenting meanwhile)
+                e2e_drain(target, False)
+            g, buf = shared.next_slot()
+            r.render_async(camera(first_cam + i), W, H, out=shared.row_addr(buf, band["y0"]), in_place=True,
+                           done_flag=shared.done_addr(shared.rank), done_value=g + 1,
+                           flags=F.ORE_FLAG_NO_KERNEL_TIMING, **band)
+            e2e_drain(target, False)
+        if timed:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record(copy_stream)               # behind the last frame's copy and its completion flag
+            e2e_events.append((e0, e1))
+        e2e_drain(target, True)                  # presenter: every rank's rows of every frame have landed
+        r.wait()
+
+    e2e_run(max(2, NHB), 0, False)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_run(args.steps, args.warmup, True)
+    if world > 1:
+        dist.barrier()
+    wall = time.perf_counter() - t0
+    e0, e1 = e2e_events[-1]
+    tt = torch.tensor([e0.elapsed_time(e1), wall * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    e2e_ms, e2e_wall_ms = [float(v) for v in tt.tolist()]
+    e2e_value = W * H * args.steps / (e2e_ms * 1e-3) / 1e6
+    e2e_wall_value = W * H * args.steps / (e2e_wall_ms * 1e-3) / 1e6
+    frame_check = None
+    if rank == 0:
+        last_g = shared.submitted - 1
+        got = shared.frames[last_g % NHB]
+        alone = r.render(camera(args.warmup + args.steps - 1), W, H)
+        if emulate:
+            rows = mg.block_rows(peer.band_rank, peer.band_world, H)
+            frame_check = "identical" if np.array_equal(alone[rows], got[rows]) else "MISMATCH"
+        else:
+            frame_check = "identical" if np.array_equal(alone, got) else "MISMATCH"
+    # synchronous update() semantics at N = 1, for reference: launch + sync + copy per call
+    e2e_sync_value = None
+    if world == 1 and not emulate:
+        hostbuf = r.host_alloc((H, W))
+        for f in range(2):
+            r.render(camera(f), W, H, out=hostbuf)
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            r.render(camera(args.warmup + i), W, H, out=hostbuf, flags=F.ORE_FLAG_NO_KERNEL_TIMING)
+        e2e_sync_value = W * H * args.steps / (time.perf_counter() - t0) / 1e6
+        r.host_free(hostbuf)
+    barrier()
+
+    # ---- accounting (untimed): live unit counts of the timed frames + reference-order test counts ----
+    own = {"primary": 0.0, "shadow": 0.0, "sky": 0.0, "hits": 0.0, "pixels": 0.0, "exact_p": 0.0, "exact_s": 0.0,
+           "l1": 0.0, "l2": 0.0}
+    band_kw = peer.band_args(0)
     for i in range(args.steps):
-        r.render_device(camera(args.warmup + i), W, H, flags=pkg.capi.ORE_FLAG_COUNT_REFERENCE_TESTS, **band_kw)
+        r.render_device(camera(args.warmup + i), W, H, flags=F.ORE_FLAG_COUNT_REFERENCE_TESTS, **band_kw)
         c = r.counters()
         own["primary"] += c["primary_tests"]
         own["shadow"] += c["shadow_tests_ref"]
         own["sky"] += c["sky_tests"]
         own["hits"] += c["hit_pixels"]
-    counts = torch.tensor([own["primary"], own["shadow"], own["sky"], own["hits"]], dtype=torch.float64,
-                          device=f"cuda:{local}")
+        own["pixels"] += c["pixels"]
+        own["exact_p"] += c["exact_primary"]
+        own["exact_s"] += c["exact_shadow"]
+        own["l1"] += c["beam_l1"]
+        own["l2"] += c["beam_l2"]
+    keys = list(own)
+    counts = torch.tensor([own[k] for k in keys], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(counts)
-    tests_primary, tests_shadow, tests_sky, hits = [float(v) for v in counts.tolist()]
-    # the same accounting for the per-ray shadow kernel (every sample ray x every sphere; the kernel the
-    # FP32-pipe utilisation in profiles/ is quoted on), 3 untimed frames
-    per_ray = None
-    if world == 1:
-        pr_ms, pr_tests = [], 0.0
-        for i in range(3):
-            r.render_device(camera(args.warmup + i), W, H, out_ptr=count_out,
-                            flags=pkg.capi.ORE_FLAG_PER_RAY_SHADOW | pkg.capi.ORE_FLAG_COUNT_REFERENCE_TESTS)
-            pr_ms.append(r.kernel_ms()[2])
-            pr_tests += r.counters()["shadow_tests_ref"]
-        per_ray = {"kernel": "shadow_kernel<3> (ORE_FLAG_PER_RAY_SHADOW)", "kernel_ms": statistics.mean(pr_ms),
-                   "achieved": FLOP_PER_TEST * pr_tests / 3 / (statistics.mean(pr_ms) * 1e-3) / 1e12, "unit": "TFLOP/s"}
+    tot = dict(zip(keys, [float(v) for v in counts.tolist()]))
     peak_tf, nominal_mhz = r.measure_fp32_peak()
-    # dominant kernel = shadow kernel; roofline of rank 0's own launches against rank 0's own tests
     k_shadow_ms = statistics.mean(m[2] for m in kernel_ms)
     k_primary_ms = statistics.mean(m[1] for m in kernel_ms)
     k_prep_ms = statistics.mean(m[0] for m in kernel_ms)
-    own_shadow = own["shadow"]
-    shadow_flop_per_launch = FLOP_PER_TEST * own_shadow / args.steps
-    achieved_tf = shadow_flop_per_launch / (k_shadow_ms * 1e-3) / 1e12
-    step_flop = FLOP_PER_TEST * (tests_primary + tests_shadow + tests_sky) / args.steps
-    step_tf = step_flop / (total_ms / args.steps * 1e-3) / 1e12
+    # (1) algorithmic rate: what a literal implementation of the reference's loops would have to execute
+    alg_tf_shadow = FLOP_PER_TEST * own["shadow"] / args.steps / (k_shadow_ms * 1e-3) / 1e12
+    alg_tf_step = FLOP_PER_TEST * (tot["primary"] + tot["shadow"] + tot["sky"]) / args.steps / (total_ms / args.steps * 1e-3) / 1e12
+    # (2) executed rate: FP32 operations the kernels really execute = committed ncu op counts per unit x LIVE units
+    ex = executed_table(args.workload)
+    executed = None
+    frac = None
+    achieved_tf = None
+    if ex:
+        hits_f, px_f = own["hits"] / args.steps, own["pixels"] / args.steps
+        fl_shadow = ex["shadow_pass"]["flop_per_hit_pixel"] * hits_f
+        fl_primary = ex["primary"]["flop_per_pixel"] * px_f
+        achieved_tf = fl_shadow / (k_shadow_ms * 1e-3) / 1e12
+        frac = achieved_tf / peak_tf if peak_tf else None
+        executed = {
+            "source": ex.get("source"),
+            "shadow_pass": {"flop_per_hit_pixel": ex["shadow_pass"]["flop_per_hit_pixel"], "hit_pixels_per_launch": hits_f,
+                            "flop_per_launch": fl_shadow, "kernel_ms": k_shadow_ms, "achieved_tflops": achieved_tf,
+                            "frac_of_measured_peak": frac},
+            "primary": {"flop_per_pixel": ex["primary"]["flop_per_pixel"], "pixels_per_launch": px_f,
+                        "flop_per_launch": fl_primary, "kernel_ms": k_primary_ms,
+                        "achieved_tflops": fl_primary / (k_primary_ms * 1e-3) / 1e12,
+                        "frac_of_measured_peak": (fl_primary / (k_primary_ms * 1e-3) / 1e12 / peak_tf) if peak_tf else None},
+            "issue_slot_utilisation": ex.get("issue_slot_utilisation"),
+            "live_cross_check": {
+                "what": "device counters of the timed frames against the profiled frame's (same units => same work)",
+                "exact_shadow_tests_per_hit_pixel": own["exact_s"] / max(1.0, own["hits"]),
+                "profiled_exact_shadow_tests_per_hit_pixel": ex.get("exact_shadow_per_hit_pixel"),
+                "cone_tests_per_hit_pixel": own["l2"] / max(1.0, own["hits"]),
+                "profiled_cone_tests_per_hit_pixel": ex.get("cone_tests_per_hit_pixel")},
+        }
+    hbm_peak, hbm_src = measured_hbm_peak()
+    traffic = (ex or {}).get("shadow_pass", {}).get("dram_bytes_per_hit_pixel")
+    traffic_launch = traffic * own["hits"] / args.steps if traffic else None
 
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.isfile(tpath):
-        try:
-            traffic = json.load(open(tpath)).get(args.workload, {}).get("shadow_kernel_dram_bytes_per_launch")
-        except Exception:
-            traffic = None
-
-    if traffic and world > 1:
-        traffic = traffic / world   # the ncu capture is a whole frame on one GPU; a rank sweeps 1/world of the hit pixels
-    also_4k = None
-    if world == 1 and args.workload == "8k1024":
-        # configs[2] (4K / 1024 spheres, the single-GPU roofline scene): same scene, quarter of the pixels
-        W4, H4 = 3840, 2160
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ms4, kms4 = [], []
-        for i in range(args.warmup + 10):
-            flush_l2()
+    # ---- N = 1 side measurements ----------------------------------------------------------------
+    extras = {}
+    count_out = peer.ptrs[0]
+    if world == 1 and not emulate and not args.no_extras:
+        def timed_frames(n, w, h, flags=0, cam0=args.warmup):
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for i in range(3):
+                r.render_device(camera(i), w, h, out_ptr=count_out, stream=stream.cuda_stream, flags=flags | F.ORE_FLAG_NO_KERNEL_TIMING)
+            stream.synchronize()
             ev0.record(stream)
-            with torch.cuda.stream(stream):
-                r.render_device(camera(i), W4, H4, out_ptr=count_out, stream=stream.cuda_stream)
+            for i in range(n):
+                r.render_device(camera(cam0 + i), w, h, out_ptr=count_out, stream=stream.cuda_stream, flags=flags | F.ORE_FLAG_NO_KERNEL_TIMING)
             ev1.record(stream)
             ev1.synchronize()
-            if i >= args.warmup:
-                ms4.append(ev0.elapsed_time(ev1))
+            return ev0.elapsed_time(ev1) / n
+
+        if args.workload == "8k1024":
+            ms4 = timed_frames(10, 3840, 2160)
+            kms4 = []
+            for i in range(4):
+                r.render_device(camera(args.warmup + i), 3840, 2160, out_ptr=count_out, stream=stream.cuda_stream)
+                stream.synchronize()
                 kms4.append(r.kernel_ms())
-        also_4k = {"workload": WORKLOADS["4k1024"][5], "value": W4 * H4 / statistics.mean(ms4) / 1e3, "unit": "Mrays/s",
-                   "ms_per_step": statistics.mean(ms4), "steps": 10,
-                   "kernel_ms": {"prep": statistics.mean(m[0] for m in kms4), "primary": statistics.mean(m[1] for m in kms4),
-                                 "shadow": statistics.mean(m[2] for m in kms4)}}
-    primary_only = None
-    if world == 1:
-        # SURVEY.md 8(d): the primary-only fraction (light_size = 0 is a legal reference configuration: the light
-        # loop runs zero times, kernel.cu:1665): tests = W*H*N exactly
+            extras["also_configs2_4k1024"] = {
+                "workload": WORKLOADS["4k1024"][5], "value": 3840 * 2160 / ms4 / 1e3, "unit": "Mrays/s", "ms_per_step": ms4,
+                "steps": 10, "kernel_ms": {"prep": statistics.mean(m[0] for m in kms4), "primary": statistics.mean(m[1] for m in kms4),
+                                           "shadow": statistics.mean(m[2] for m in kms4)}}
         r.set_lights(sc.lights[:0])
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        for i in range(3):
-            r.render_device(camera(i), W, H, out_ptr=count_out, stream=stream.cuda_stream)
-        stream.synchronize()
-        ev0.record(stream)
-        for i in range(10):
-            r.render_device(camera(args.warmup + i), W, H, out_ptr=count_out, stream=stream.cuda_stream)
-        ev1.record(stream)
-        ev1.synchronize()
-        po_ms = ev0.elapsed_time(ev1) / 10
+        po_ms = timed_frames(10, W, H)
         r.set_lights(sc.lights)
         po_tf = FLOP_PER_TEST * W * H * sc.n_spheres / (po_ms * 1e-3) / 1e12
-        primary_only = {"what": "n_lights = 0: primary nearest hit + sky only; tests = W*H*N", "ms_per_step": po_ms,
-                        "value": W * H / po_ms / 1e3, "unit": "Mrays/s", "achieved": po_tf, "achieved_unit": "TFLOP/s"}
-    fast_libm = None
-    if world == 1:
-        # the same frames with ORE_FLAG_FAST_LIBM (CUDA's libm: within 1 LSB instead of bit-identical)
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        for i in range(3):
-            r.render_device(camera(i), W, H, out_ptr=count_out, stream=stream.cuda_stream, flags=pkg.capi.ORE_FLAG_FAST_LIBM)
-        stream.synchronize()
-        ev0.record(stream)
-        for i in range(10):
-            r.render_device(camera(args.warmup + i), W, H, out_ptr=count_out, stream=stream.cuda_stream,
-                            flags=pkg.capi.ORE_FLAG_FAST_LIBM)
-        ev1.record(stream)
-        ev1.synchronize()
-        fl_ms = ev0.elapsed_time(ev1) / 10
-        fast_libm = {"flag": "ORE_FLAG_FAST_LIBM", "value": W * H / fl_ms / 1e3, "unit": "Mrays/s", "ms_per_step": fl_ms, "steps": 10,
-                     "note": "CUDA's cosf/sinf/acosf/atan2f instead of the glibc-bit-compatible device functions; ids/t unchanged, "
-                             "pixels within 1 LSB on >= 99.9 % instead of bit-identical"}
-    ref_gpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        # the reference's OWN CUDA kernel built for sm_100 (oracle/_ref/libref_sm100*.so), same scene, 3 frames:
-        # reported alongside, never on our path
-        try:
-            sys.path.insert(0, os.path.join(ROOT, "tests"))
-            import oraclelib
-            ref_gpu = {}
-            cams = [camera(args.warmup + i) for i in range(3)]
-            for fast in (False, True):
-                if oraclelib.have_ref_gpu(fast):
-                    _, ms_up, ms_k = oraclelib.RefGpu(fast=fast).render(sc, cams, W, H)
-                    ref_gpu["use_fast_math" if fast else "default_flags"] = {
-                        "ms_per_update": ms_up, "ms_per_kernel": ms_k,
-                        "mrays_per_s_update": W * H / ms_up / 1e3, "mrays_per_s_kernel": W * H / ms_k / 1e3}
-            ref_gpu["what"] = ("the reference's rayTrace kernel / update() compiled unmodified in arithmetic for sm_100 "
-                               "(oracle/ref_build/make_ref_gpu.py), run headless on this GPU in this run")
-        except Exception as e:  # measurement extra only
-            ref_gpu = {"unavailable": str(e)[:200]}
+        extras["primary_only"] = {"what": "n_lights = 0: primary nearest hit + sky only; reference tests = W*H*N", "ms_per_step": po_ms,
+                                  "value": W * H / po_ms / 1e3, "unit": "Mrays/s",
+                                  "algorithmic_tflops": po_tf, "algorithmic_speedup_vs_literal": po_tf / peak_tf if peak_tf else None}
+        fl_ms = timed_frames(10, W, H, flags=F.ORE_FLAG_FAST_LIBM)
+        extras["fast_libm"] = {"flag": "ORE_FLAG_FAST_LIBM", "value": W * H / fl_ms / 1e3, "unit": "Mrays/s", "ms_per_step": fl_ms, "steps": 10,
+                               "note": "CUDA's cosf/sinf/acosf/atan2f instead of the glibc-bit-compatible device functions; ids/t "
+                                       "unchanged, pixels within 1 LSB on >= 99.9 % instead of bit-identical"}
+        if not args.no_cpu_baseline:
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "tests"))
+                import oraclelib
+                ref_gpu = {}
+                cams = [camera(args.warmup + i) for i in range(3)]
+                for fast in (False, True):
+                    if oraclelib.have_ref_gpu(fast):
+                        _, ms_up, ms_k = oraclelib.RefGpu(fast=fast).render(sc, cams, W, H)
+                        ref_gpu["use_fast_math" if fast else "default_flags"] = {
+                            "ms_per_update": ms_up, "ms_per_kernel": ms_k,
+                            "mrays_per_s_update": W * H / ms_up / 1e3, "mrays_per_s_kernel": W * H / ms_k / 1e3}
+                ref_gpu["what"] = ("the reference's rayTrace kernel / update() compiled unmodified in arithmetic for sm_100 "
+                                   "(oracle/ref_build/make_ref_gpu.py), run headless on this GPU in this run")
+                extras["reference_kernel_on_b200"] = ref_gpu
+            except Exception as e:  # measurement extra only
+                extras["reference_kernel_on_b200"] = {"unavailable": str(e)[:200]}
+    mem_used = None
+    try:
+        free_b, total_b = torch.cuda.mem_get_info(local)
+        mem_used = (total_b - free_b) / 1e9
+    except Exception:
+        pass
+
     if rank == 0:
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not emulate and not args.no_cpu_baseline:
             _, cpu, _ = run_cpu(args, pkg, "cpu_baseline")
+        hits_rank = own["hits"] / args.steps
+        ws_mb = (n_rows_mine * W * 4 * 3 + hits_rank * (4 + 4 * (6 + 31 * int(sc.lights.shape[0])))) / 1e6
         line = {
             "metric": "Mrays/s (primary rays)", "value": value, "unit": "Mrays/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": dict(config, l2=l2_note,
-                           frame_overlap=(f"{NF} frames in flight per GPU (contexts/streams used round-robin)"
-                                          if overlap and NF > 1 else "none"),
-                           parallelism=(f"row-bands x{world} (8-row blocks dealt round-robin), presenter = rank 0, gather = {gather_mode}"
-                                        if world > 1 else "1 GPU"),
-                           hit_pixel_fraction=hits / (W * H * args.steps),
-                           tests_per_pixel={"primary": tests_primary / (W * H * args.steps),
-                                            "shadow_reference_order": tests_shadow / (W * H * args.steps)}),
+            "config": config,
+            "run": {
+                "l2": (f"not flushed at any N (one policy): the inputs a step reads are the 64 KB of scene records the kernels keep "
+                       f"in shared memory by design; what it WRITES and re-reads is larger than L2 - per rank and step "
+                       f"{ws_mb:.0f} MB of framebuffer rows, hit records and shadow staging, x {NF} frames in flight, L2 126 MB"),
+                "frame_overlap": f"{NF} frames in flight per GPU (contexts/streams used round-robin), ring of {NF} presenter frames",
+                "parallelism": (f"row-bands x{world} (8-row blocks dealt round-robin), presenter = rank 0; rows stored over NVLink into "
+                                f"the presenter's ring; completion = per-rank flags (no collective in the timed region)"
+                                if world > 1 else "1 GPU (same code path: frame ring + flags)"),
+                "emulated": (f"rows of rank {peer.band_rank} of {emulate} only, on ONE GPU: value counts the WHOLE frame's pixels, i.e. it is "
+                             f"the rate {emulate} such ranks would reach together if NVLink cost nothing - a tool output, not a bench line"
+                             if emulate else None),
+                "hit_pixel_fraction": tot["hits"] / max(1.0, tot["pixels"]),
+                "host_issue_ms_per_step": host_issue_ms,
+                "device_memory_used_gb": mem_used,
+                "tests_per_pixel": {"primary": tot["primary"] / max(1.0, tot["pixels"]),
+                                    "shadow_reference_order": tot["shadow"] / max(1.0, tot["pixels"])},
+            },
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 36 + 32,
-                    "d2h_bytes_per_step": W * H * 4, "mode": e2e_mode,
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 36 + 36,
+                    "d2h_bytes_per_step": W * H * 4 + 4 * world,
+                    "mode": (f"ore_render_async_signal: every rank copies its own row blocks into ONE shared pinned host frame ring "
+                             f"({NHB} frames, POSIX shm registered with CUDA) over its own PCIe link, copy of frame f behind the kernels "
+                             f"of f+1; per-rank completion counters in the same shared memory; the presenter's host thread consumes "
+                             f"frames in order. Timed with CUDA events (first render -> last copy + flag landed), max over ranks"),
+                    "wall_clock_value": e2e_wall_value,
                     "synchronous_value": e2e_sync_value,
-                    "note": "inputs per step are the 36-byte camera and the 32-byte frame descriptor (kernel arguments); "
-                            "output per step is the whole framebuffer read back to pinned host memory; "
-                            "synchronous_value = ore_render (launch + sync + copy per call, the reference update() semantics)",
+                    "note": "inputs per step are the 36-byte camera and the 36-byte frame descriptor (kernel arguments); output per "
+                            "step is the whole framebuffer in pinned host memory plus a 4-byte counter per rank; "
+                            "synchronous_value = ore_render (launch + sync + copy per call, the reference update() semantics, N = 1)",
                     "sharded_frame_check": frame_check},
             "gpu_launches": launches_per_frame * args.steps,
-            "gpu_launches_per_frame": {"count": launches_per_frame,
-                                       "kernels": "prep_frame, primary_tile, one catch-all fused shadow_beam (normally empty), then per "
-                                                  "hit-list chunk shade_setup + shadow_beam (as many chunks as the previous "
-                                                  "frame's hit count suggests); one fused shadow_beam only when the sphere "
-                                                  "records exceed shared memory"},
+            "gpu_launches_per_frame": {"count": launches_per_frame, "kernels": "see DESIGN.md section 4"},
             "roofline": {
-                "bound": "fp32", "kernel": "shadow pass = shade_setup_kernel + shadow_beam_kernel (soft-shadow any-hit + shading; default path)",
-                "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None,
-                "traffic": traffic,
+                "bound": "fp32",
+                "kernel": "shadow pass (soft-shadow any-hit + shading; the dominant kernels of the step)",
+                "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": frac,
+                "traffic": traffic_launch,
                 "peak_source": "measured: FFMA burn on this GPU in this run (MEASURED_PEAKS.json carries HBM and bf16 only); "
                                f"nominal 148 SM x 128 lanes x 2 x 1.965 GHz = {NOMINAL_FP32_TFLOPS:.2f}",
-                "flop_per_test": FLOP_PER_TEST,
-                "tests_per_launch": own_shadow / args.steps,
-                "kernel_ms": k_shadow_ms,
-                "definition": "achieved = 18 FLOP x reference-order sphere tests of the launch / CUDA-event kernel time "
-                              "(SURVEY.md 8d). The kernel reaches the reference's results with far fewer executed FLOP "
-                              "(shared L/C per pixel, 3-FMA filter, per-light cone and per-warp beam tests ahead of the "
-                              "per-ray tests), so frac is an ALGORITHMIC-work rate and exceeds 1; executed-instruction "
-                              "utilisation of the kernels (ncu, profiles/) is under `executed`, the FP32-pipe-bound "
-                              "kernel generation under per_ray_kernel.",
-                "per_ray_kernel": (dict(per_ray, frac=per_ray["achieved"] / peak_tf) if per_ray and peak_tf else per_ray),
-                "whole_step": {"achieved": step_tf, "frac": step_tf / peak_tf if peak_tf else None,
-                               "frac_of_nominal": step_tf / NOMINAL_FP32_TFLOPS},
+                "definition": "achieved = EXECUTED FP32 FLOP of the launch (fadd + fmul + 2 ffma, thread level: committed ncu op "
+                              "counts per hit pixel x the hit pixels of the timed frames, counted on the device) / CUDA-event "
+                              "kernel time; frac = achieved / measured FFMA peak. The kernels are bound by instruction issue, "
+                              "not by the FP32 pipe (see `executed`); the algorithmic rate of SURVEY.md 8(d) is reported "
+                              "separately as algorithmic_speedup_vs_literal.",
+                "executed": executed,
+                "algorithmic": {
+                    "flop_per_test": FLOP_PER_TEST, "reference_order_shadow_tests_per_launch": own["shadow"] / args.steps,
+                    "shadow_pass_tflops": alg_tf_shadow, "whole_step_tflops": alg_tf_step,
+                    "algorithmic_speedup_vs_literal": alg_tf_shadow / peak_tf if peak_tf else None,
+                    "whole_step_speedup_vs_literal": alg_tf_step / peak_tf if peak_tf else None,
+                    "definition": "18 FLOP x sphere tests the REFERENCE's loop order makes (counted exactly on the device by "
+                                  "the literal loop, untimed) / time / FFMA peak: how many times faster than a perfect literal "
+                                  "implementation of kernel.cu:332-336 the pass runs. Not a hardware utilisation."},
                 "kernel_ms_all": {"prep": k_prep_ms, "primary": k_primary_ms, "shadow": k_shadow_ms},
-                "dram_write_gbs_framebuffer": W * H * 4 / world / ((k_primary_ms + k_shadow_ms) * 1e-3) / 1e9,
-                "hbm": hbm_block(traffic, k_shadow_ms),
-                "executed": issue_block(args.workload),
+                "dram_write_gbs_framebuffer": n_rows_mine * W * 4 / ((k_primary_ms + k_shadow_ms) * 1e-3) / 1e9,
+                "hbm": {"peak_gbs": hbm_peak, "peak_source": hbm_src,
+                        "achieved_gbs": (traffic_launch / (k_shadow_ms * 1e-3) / 1e9) if traffic_launch else None,
+                        "frac": (traffic_launch / (k_shadow_ms * 1e-3) / 1e9 / hbm_peak) if traffic_launch else None},
             },
             "cpu_baseline": cpu,
-            "reference_kernel_on_b200": ref_gpu,
-            "also_configs2_4k1024": also_4k,
-            "fast_libm": fast_libm,
-            "primary_only": (dict(primary_only, frac=primary_only["achieved"] / peak_tf) if primary_only and peak_tf else primary_only),
         }
+        line.update(extras)
         print(json.dumps(line))
-    if host:
-        for h_ in host:
-            r.host_free(h_)
-    if peer is not None:
-        peer.close()
+    shared.close()
+    peer.close()
     for rx, _ in ctxs[1:]:
         rx.close()
     r.close()

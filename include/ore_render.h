@@ -221,7 +221,7 @@ int ore_flag_wait_geq(ore_context* ctx, void* stream, const uint32_t* flag, uint
  * `stream` so far is complete: flags written through one context appear in CALL order even when frames rendered on
  * different streams (several frames in flight) finish out of order. */
 int ore_flag_write_after(ore_context* ctx, void* stream, uint32_t* flag, uint32_t value);
-void* ore_get_stream(ore_context* ctx, int which); /* 0: render stream, 1: copy stream (cudaStream_t) */
+void* ore_get_stream(ore_context* ctx, int which); /* 0: render stream, 1: copy stream, 2: signal stream (cudaStream_t) */
 /* device -> host copy on the context's stream, synchronous (the setPixelBuff copy) */
 int ore_copy_to_host(ore_context* ctx, void* host_dst, const void* dev_src, size_t bytes);
 

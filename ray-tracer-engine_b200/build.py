@@ -56,8 +56,10 @@ def _env():
     return env
 
 
-def build_library(force: bool = False, verbose: bool = False, extra_flags=()) -> str:
-    if not force and not extra_flags and not is_stale():
+def build_library(force: bool = False, verbose: bool = False, extra_flags=(), out: str | None = None) -> str:
+    """out: path of a VARIANT library (tuning experiments built with extra -D flags, selected with ORE_LIB=...)"""
+    target = out or LIB_PATH
+    if not force and not extra_flags and not out and not is_stale():
         return LIB_PATH
     nvcc = find_nvcc()
     os.makedirs(OBJ_DIR, exist_ok=True)
@@ -79,11 +81,11 @@ def build_library(force: bool = False, verbose: bool = False, extra_flags=()) ->
 
     with ThreadPoolExecutor(max_workers=len(jobs)) as ex:
         objs = list(ex.map(compile_one, jobs))
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", *objs, "-o", LIB_PATH]
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", *objs, "-o", target]
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd, env=_env())
-    return LIB_PATH
+    return target
 
 
 if __name__ == "__main__":

@@ -94,7 +94,10 @@ struct ore_context {
     size_t stage_cap = 0;    // floats
     size_t stage_blocks_override = 0;  // test hook (env ORE_STAGE_BLOCKS at ore_create): staging capacity in 32-item blocks
     bool stage_always = false;         // test hook (env ORE_STAGE_ALWAYS=1): two-stage pass also for non-resident scenes
-    bool no_memops = false;            // test hook (env ORE_NO_STREAM_MEMOPS=1): flags through the one-thread kernels
+    bool no_memops = false;
+    std::string dbg_cycles_path;       // tools hook (env ORE_DEBUG_BLOCK_CYCLES=file): per-block SM clocks of the shadow pass
+    uint32_t* dbg_cycles = nullptr;
+    size_t dbg_cap = 0;            // test hook (env ORE_NO_STREAM_MEMOPS=1): flags through the one-thread kernels
     // hit count of this context's previous frame, copied to pinned memory at the end of every frame and read
     // WITHOUT synchronisation by the next one: only a hint for how many staged chunk pairs to launch - whatever
     // lies beyond them is swept by one catch-all fused launch, so any value (stale, zero, mid-copy) is safe
@@ -201,6 +204,7 @@ extern "C" int ore_create(ore_context** out, int device) {
     *ctx->hits_hint = 0;
     if (const char* e = getenv("ORE_STAGE_ALWAYS")) ctx->stage_always = atoi(e) != 0;
     if (const char* e = getenv("ORE_NO_STREAM_MEMOPS")) ctx->no_memops = atoi(e) != 0;
+    if (const char* e = getenv("ORE_DEBUG_BLOCK_CYCLES")) ctx->dbg_cycles_path = e;
     if (const char* e = getenv("ORE_STAGE_BLOCKS")) {
         const long v = atol(e);
         if (v > 0) ctx->stage_blocks_override = (size_t)v;
@@ -234,6 +238,20 @@ extern "C" int ore_destroy(ore_context* ctx) {
     if (!ctx) return ORE_ERR_INVALID;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->dbg_cycles) {
+        // tools hook: [2][dbg_cap] uint32 of the LAST frame, preceded by dbg_cap as one uint64
+        cudaDeviceSynchronize();
+        std::vector<uint32_t> h(2 * ctx->dbg_cap);
+        if (cudaMemcpy(h.data(), ctx->dbg_cycles, h.size() * 4, cudaMemcpyDeviceToHost) == cudaSuccess) {
+            if (FILE* f = fopen(ctx->dbg_cycles_path.c_str(), "wb")) {
+                const unsigned long long cap = ctx->dbg_cap;
+                fwrite(&cap, 8, 1, f);
+                fwrite(h.data(), 4, h.size(), f);
+                fclose(f);
+            }
+        }
+        cudaFree(ctx->dbg_cycles);
+    }
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     for (int i = 0; i < 2; i++) {
         if (ctx->ev_rendered[i]) cudaEventDestroy(ctx->ev_rendered[i]);
@@ -712,6 +730,17 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
     prm.hit_list = ctx->hit_list;
     prm.counters = ctx->counters;
     prm.pixels = out_device ? out_device : ctx->pixels;
+    if (!ctx->dbg_cycles_path.empty()) {
+        const size_t nb = (n_px + 31) / 32;
+        if (nb > ctx->dbg_cap) {
+            if (ctx->dbg_cycles) ORE_CUDA(ctx, cudaFree(ctx->dbg_cycles));
+            ORE_CUDA(ctx, cudaMalloc((void**)&ctx->dbg_cycles, 2 * nb * sizeof(uint32_t)));
+            ctx->dbg_cap = nb;
+        }
+        ORE_CUDA(ctx, cudaMemsetAsync(ctx->dbg_cycles, 0, 2 * ctx->dbg_cap * sizeof(uint32_t), stream));
+        prm.dbg_cycles = ctx->dbg_cycles;
+        prm.dbg_cap = (uint32_t)ctx->dbg_cap;
+    }
     for (int i = 0; i < ctx->n_lights; i++) prm.lights[i] = ctx->lights[i];
 
     const bool timing = !(fr->flags & ORE_FLAG_NO_KERNEL_TIMING);
@@ -812,11 +841,11 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
                 if (fast_libm) {
                     ORE_CUDA(ctx, (cudaError_t)ore_fast_shadow_beam(&prm, &st, 0, ctx->sm_count, bsmem, exh ? 1 : 0, stream));
                 } else if (exh) {
-                    if ((rc = grid_for(ctx, shadow_beam_kernel<true, false>, bsmem, &grid))) return rc;
-                    shadow_beam_kernel<true, false><<<grid, CTA_THREADS, bsmem, stream>>>(prm, st);
+                    if ((rc = grid_for(ctx, shadow_beam_kernel<true, false>, bsmem, &grid, BEAM_THREADS))) return rc;
+                    shadow_beam_kernel<true, false><<<grid, BEAM_THREADS, bsmem, stream>>>(prm, st);
                 } else {
-                    if ((rc = grid_for(ctx, shadow_beam_kernel<false, false>, bsmem, &grid))) return rc;
-                    shadow_beam_kernel<false, false><<<grid, CTA_THREADS, bsmem, stream>>>(prm, st);
+                    if ((rc = grid_for(ctx, shadow_beam_kernel<false, false>, bsmem, &grid, BEAM_THREADS))) return rc;
+                    shadow_beam_kernel<false, false><<<grid, BEAM_THREADS, bsmem, stream>>>(prm, st);
                 }
             } else {
                 st.buf = ctx->stage;
@@ -832,9 +861,9 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
                 }
                 int grid_a = 0, grid_b = 0;
                 if (!fast_libm) {
-                    if ((rc = grid_for(ctx, shade_setup_kernel, 0, &grid_a))) return rc;
-                    if (exh) rc = grid_for(ctx, shadow_beam_kernel<true, true>, bsmem, &grid_b);
-                    else rc = grid_for(ctx, shadow_beam_kernel<false, true>, bsmem, &grid_b);
+                    if ((rc = grid_for(ctx, shade_setup_kernel, 0, &grid_a, STAGE_A_THREADS))) return rc;
+                    if (exh) rc = grid_for(ctx, shadow_beam_kernel<true, true>, bsmem, &grid_b, BEAM_THREADS);
+                    else rc = grid_for(ctx, shadow_beam_kernel<false, true>, bsmem, &grid_b, BEAM_THREADS);
                     if (rc) return rc;
                 }
                 if (n_chunks < n_chunks_max) {
@@ -845,11 +874,11 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
                     if (fast_libm) {
                         ORE_CUDA(ctx, (cudaError_t)ore_fast_shadow_beam(&prm, &rest, 0, ctx->sm_count, bsmem, exh ? 1 : 0, stream));
                     } else if (exh) {
-                        if ((rc = grid_for(ctx, shadow_beam_kernel<true, false>, bsmem, &grid))) return rc;
-                        shadow_beam_kernel<true, false><<<grid, CTA_THREADS, bsmem, stream>>>(prm, rest);
+                        if ((rc = grid_for(ctx, shadow_beam_kernel<true, false>, bsmem, &grid, BEAM_THREADS))) return rc;
+                        shadow_beam_kernel<true, false><<<grid, BEAM_THREADS, bsmem, stream>>>(prm, rest);
                     } else {
-                        if ((rc = grid_for(ctx, shadow_beam_kernel<false, false>, bsmem, &grid))) return rc;
-                        shadow_beam_kernel<false, false><<<grid, CTA_THREADS, bsmem, stream>>>(prm, rest);
+                        if ((rc = grid_for(ctx, shadow_beam_kernel<false, false>, bsmem, &grid, BEAM_THREADS))) return rc;
+                        shadow_beam_kernel<false, false><<<grid, BEAM_THREADS, bsmem, stream>>>(prm, rest);
                     }
                     ORE_CUDA(ctx, cudaGetLastError());
                     ctx->last_launches++;
@@ -861,9 +890,9 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
                         ORE_CUDA(ctx, (cudaError_t)ore_fast_shade_setup(&prm, &st, ctx->sm_count, stream));
                         ORE_CUDA(ctx, (cudaError_t)ore_fast_shadow_beam(&prm, &st, 1, ctx->sm_count, bsmem, exh ? 1 : 0, stream));
                     } else {
-                        shade_setup_kernel<<<grid_a, CTA_THREADS, 0, stream>>>(prm, st);
-                        if (exh) shadow_beam_kernel<true, true><<<grid_b, CTA_THREADS, bsmem, stream>>>(prm, st);
-                        else shadow_beam_kernel<false, true><<<grid_b, CTA_THREADS, bsmem, stream>>>(prm, st);
+                        shade_setup_kernel<<<grid_a, STAGE_A_THREADS, 0, stream>>>(prm, st);
+                        if (exh) shadow_beam_kernel<true, true><<<grid_b, BEAM_THREADS, bsmem, stream>>>(prm, st);
+                        else shadow_beam_kernel<false, true><<<grid_b, BEAM_THREADS, bsmem, stream>>>(prm, st);
                     }
                     ORE_CUDA(ctx, cudaGetLastError());
                     ctx->last_launches += (c + 1 < n_chunks) ? 2 : 1;  // the common tail below counts one
@@ -964,6 +993,7 @@ static cudaStream_t pick_stream(ore_context* ctx, void* stream) { return stream 
 
 extern "C" void* ore_get_stream(ore_context* ctx, int which) {
     if (!ctx) return nullptr;
+    if (which == 2) return (void*)ctx->signal_stream;  // null until the first ore_flag_write_after
     return which == 1 ? (void*)ctx->copy_stream : (void*)ctx->stream;
 }
 

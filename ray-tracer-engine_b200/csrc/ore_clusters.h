@@ -97,5 +97,58 @@ inline void build_clusters(const Rec4* ex, const Rec4* sh, int n, std::vector<Re
     }
 }
 
+// Bounding ball of the member balls sorted[p0, p1): centre = the better of (mean of the centres, centre of the box
+// around the member balls), radius = max |c_i - centre| + R'_i, rounded up.  +inf ("always open") when a member
+// cannot be bounded by the float tests.
+inline Rec4 bounding_ball(const std::vector<Rec4>& sorted, size_t p0, size_t p1) {
+    if (p1 <= p0) return Rec4{0.f, 0.f, 0.f, 0.f};
+    double mean[3] = {0, 0, 0}, lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    bool tame = true;
+    for (size_t p = p0; p < p1; p++) {
+        const Rec4& s = sorted[p];
+        tame = tame && tame_value(s.x) && tame_value(s.y) && tame_value(s.z) && tame_value(s.w);
+        const double c[3] = {s.x, s.y, s.z};
+        for (int k = 0; k < 3; k++) {
+            mean[k] += c[k];
+            lo[k] = std::min(lo[k], c[k] - std::fabs((double)s.w));
+            hi[k] = std::max(hi[k], c[k] + std::fabs((double)s.w));
+        }
+    }
+    if (!tame) return Rec4{(float)0, (float)0, (float)0, INFINITY};
+    const double m = (double)(p1 - p0);
+    Rec4 best{0.f, 0.f, 0.f, INFINITY};
+    for (int cand = 0; cand < 2; cand++) {
+        const float f[3] = {(float)(cand ? 0.5 * (lo[0] + hi[0]) : mean[0] / m), (float)(cand ? 0.5 * (lo[1] + hi[1]) : mean[1] / m),
+                            (float)(cand ? 0.5 * (lo[2] + hi[2]) : mean[2] / m)};
+        double rad = 0;
+        for (size_t p = p0; p < p1; p++) {
+            const Rec4& s = sorted[p];
+            const double dx = (double)s.x - f[0], dy = (double)s.y - f[1], dz = (double)s.z - f[2];
+            rad = std::max(rad, std::sqrt(dx * dx + dy * dy + dz * dz) + std::fabs((double)s.w));
+        }
+        if (std::isfinite(rad) && rad < 1e15) {
+            const float fr = std::nextafter((float)(rad * (1.0 + 1e-6) + 1e-30), INFINITY);
+            if (fr < best.w) best = Rec4{f[0], f[1], f[2], fr};
+        }
+    }
+    return best;
+}
+
+// Two more levels over the same Morton order (round 2, shadow_sweep_kernel): LEAVES of 8 consecutive spheres and
+// SUPER-clusters of 32 consecutive leaves (256 spheres), one bounding ball each.  leaves: ceil(n/8) entries rounded up
+// to a multiple of 32 (padding = radius -1: never touched); supers: ceil(n/256) entries rounded up to a multiple of 4.
+constexpr int LEAF_SPHERES = 8;
+constexpr int SUPER_LEAVES = 32;
+inline void build_hierarchy(const std::vector<Rec4>& sorted_shadow, int n, std::vector<Rec4>& leaves, std::vector<Rec4>& supers) {
+    const size_t n_leaf = ((size_t)std::max(n, 0) + LEAF_SPHERES - 1) / LEAF_SPHERES;
+    const size_t n_sup = (n_leaf + SUPER_LEAVES - 1) / SUPER_LEAVES;
+    leaves.assign((n_leaf + 31) & ~(size_t)31, Rec4{0.f, 0.f, 0.f, -1.f});
+    supers.assign((n_sup + 3) & ~(size_t)3, Rec4{0.f, 0.f, 0.f, -1.f});
+    for (size_t j = 0; j < n_leaf; j++)
+        leaves[j] = bounding_ball(sorted_shadow, j * LEAF_SPHERES, std::min((j + 1) * LEAF_SPHERES, (size_t)n));
+    const size_t per = (size_t)LEAF_SPHERES * SUPER_LEAVES;
+    for (size_t k = 0; k < n_sup; k++) supers[k] = bounding_ball(sorted_shadow, k * per, std::min((k + 1) * per, (size_t)n));
+}
+
 }  // namespace ore_host
 #endif

@@ -18,17 +18,38 @@ extern "C" ORE_HIDDEN int ore_fast_set_tables(const float* cphi, const float* sp
     return 0;
 }
 
+// occupancy per (kernel, dynamic shared memory, block size) is looked up once (single host thread per context)
+struct LaunchEntry {
+    const void* fn;
+    size_t smem;
+    int threads, occ, device;
+};
+static LaunchEntry g_launch_cache[32];
+static int g_launch_cached = 0;
+
 template <typename K, typename... A>
-static cudaError_t launch(K kernel, int sm_count, size_t smem, long long max_grid, cudaStream_t stream, A... args) {
-    int occ = 0;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, ore_fast::CTA_THREADS, smem);
-    if (e != cudaSuccess) return e;
-    if (occ < 1) return cudaErrorLaunchOutOfResources;
+static cudaError_t launch(K kernel, int threads, int sm_count, size_t smem, long long max_grid, cudaStream_t stream, A... args) {
+    const void* fn = reinterpret_cast<const void*>(kernel);
+    int occ = 0, device = 0;
+    cudaGetDevice(&device);  // the opt-in shared-memory limit is a per-device attribute
+    size_t limit = smem;
+    for (int i = 0; i < g_launch_cached; i++) {
+        const LaunchEntry& e = g_launch_cache[i];
+        if (e.fn != fn || e.device != device) continue;
+        if (e.smem == smem && e.threads == threads) occ = e.occ;
+        if (e.smem > limit) limit = e.smem;
+    }
+    if (!occ) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem);
+        if (e != cudaSuccess) return e;
+        if (occ < 1) return cudaErrorLaunchOutOfResources;
+        if (g_launch_cached < 32) g_launch_cache[g_launch_cached++] = LaunchEntry{fn, smem, threads, occ, device};
+    }
     long long grid = (long long)occ * sm_count;
     if (max_grid > 0 && grid > max_grid) grid = max_grid;
-    kernel<<<(int)grid, ore_fast::CTA_THREADS, smem, stream>>>(args...);
+    kernel<<<(int)grid, threads, smem, stream>>>(args...);
     return cudaGetLastError();
 }
 
@@ -36,21 +57,21 @@ static cudaError_t launch(K kernel, int sm_count, size_t smem, long long max_gri
 extern "C" ORE_HIDDEN int ore_fast_primary_tile(const void* prm, int sm_count, size_t smem, long long n_batches, int exh,
                                                cudaStream_t stream) {
     const ore_fast::FrameParams& p = *static_cast<const ore_fast::FrameParams*>(prm);
-    return (int)(exh ? launch(ore_fast::primary_tile_kernel<ore_fast::TILE_P, true>, sm_count, smem, n_batches, stream, p)
-                     : launch(ore_fast::primary_tile_kernel<ore_fast::TILE_P, false>, sm_count, smem, n_batches, stream, p));
+    return (int)(exh ? launch(ore_fast::primary_tile_kernel<ore_fast::TILE_P, true>, ore_fast::CTA_THREADS, sm_count, smem, n_batches, stream, p)
+                     : launch(ore_fast::primary_tile_kernel<ore_fast::TILE_P, false>, ore_fast::CTA_THREADS, sm_count, smem, n_batches, stream, p));
 }
 extern "C" ORE_HIDDEN int ore_fast_shadow_beam(const void* prm, const void* stage, int staged, int sm_count, size_t smem,
                                               int exh, cudaStream_t stream) {
     const ore_fast::FrameParams& p = *static_cast<const ore_fast::FrameParams*>(prm);
     const ore_fast::StageArgs& st = *static_cast<const ore_fast::StageArgs*>(stage);
     if (!staged)
-        return (int)(exh ? launch(ore_fast::shadow_beam_kernel<true, false>, sm_count, smem, 0, stream, p, st)
-                         : launch(ore_fast::shadow_beam_kernel<false, false>, sm_count, smem, 0, stream, p, st));
-    return (int)(exh ? launch(ore_fast::shadow_beam_kernel<true, true>, sm_count, smem, 0, stream, p, st)
-                     : launch(ore_fast::shadow_beam_kernel<false, true>, sm_count, smem, 0, stream, p, st));
+        return (int)(exh ? launch(ore_fast::shadow_beam_kernel<true, false>, ore_fast::BEAM_THREADS, sm_count, smem, 0, stream, p, st)
+                         : launch(ore_fast::shadow_beam_kernel<false, false>, ore_fast::BEAM_THREADS, sm_count, smem, 0, stream, p, st));
+    return (int)(exh ? launch(ore_fast::shadow_beam_kernel<true, true>, ore_fast::BEAM_THREADS, sm_count, smem, 0, stream, p, st)
+                     : launch(ore_fast::shadow_beam_kernel<false, true>, ore_fast::BEAM_THREADS, sm_count, smem, 0, stream, p, st));
 }
 extern "C" ORE_HIDDEN int ore_fast_shade_setup(const void* prm, const void* stage, int sm_count, cudaStream_t stream) {
     const ore_fast::FrameParams& p = *static_cast<const ore_fast::FrameParams*>(prm);
     const ore_fast::StageArgs& st = *static_cast<const ore_fast::StageArgs*>(stage);
-    return (int)launch(ore_fast::shade_setup_kernel, sm_count, 0, 0, stream, p, st);
+    return (int)launch(ore_fast::shade_setup_kernel, ore_fast::STAGE_A_THREADS, sm_count, 0, 0, stream, p, st);
 }

@@ -29,13 +29,24 @@ constexpr int MAX_STAGES = 4;
 #ifndef ORE_SHADOW_MIN_CTAS
 #define ORE_SHADOW_MIN_CTAS 2
 #endif
+// The shadow-pass kernels are warp-independent persistent kernels: a CTA's registers and shared memory stay
+// allocated until its LAST warp has run out of work, so small CTAs hand an SM back to the next kernel (the next
+// frame's, or the other stage's) almost warp by warp at the tail of a launch.
+#ifndef ORE_BEAM_THREADS
+#define ORE_BEAM_THREADS 256
+#endif
 #ifndef ORE_BEAM_MIN_CTAS
-#define ORE_BEAM_MIN_CTAS 3  // shadow_beam_kernel: 80 registers, 3 x 256 threads per SM
+#define ORE_BEAM_MIN_CTAS (768 / ORE_BEAM_THREADS)  // shadow_beam_kernel: 80 registers, 768 threads per SM
+#endif
+#ifndef ORE_STAGE_A_THREADS
+#define ORE_STAGE_A_THREADS 256
 #endif
 #ifndef ORE_SHADOW_SG
 #define ORE_SHADOW_SG 4
 #endif
 constexpr int SHADOW_THREADS = ORE_SHADOW_THREADS;
+constexpr int BEAM_THREADS = ORE_BEAM_THREADS;
+constexpr int STAGE_A_THREADS = ORE_STAGE_A_THREADS;
 // primary tile kernel: rows per 32-wide pixel tile and CTAs/SM it is bounded for
 #ifndef ORE_TILE_P
 #define ORE_TILE_P 8
@@ -132,6 +143,10 @@ struct FrameParams {
     const int* box_offsets;
     const int* box_indices;
     int n_tris, n_boxes, mesh_has_normals;
+    // tools only (env ORE_DEBUG_BLOCK_CYCLES at ore_create): SM clocks spent on every hit-list block, [2][dbg_cap]
+    // (0: shade_setup_kernel, 1: staged shadow_beam_kernel); null on every product path
+    uint32_t* dbg_cycles;
+    uint32_t dbg_cap;
     LightP lights[MAX_LIGHTS];
 };
 
@@ -1540,9 +1555,9 @@ __device__ __forceinline__ void shade_point(const FrameParams& prm, uint32_t ite
 // Warps run independently: each fetches blocks of 32 consecutive hit-list items.
 // ------------------------------------------------------------------------------------
 #ifndef ORE_STAGE_A_MIN_CTAS
-#define ORE_STAGE_A_MIN_CTAS 4
+#define ORE_STAGE_A_MIN_CTAS (1024 / ORE_STAGE_A_THREADS)
 #endif
-__global__ void __launch_bounds__(CTA_THREADS, ORE_STAGE_A_MIN_CTAS) shade_setup_kernel(const FrameParams prm, const StageArgs st) {
+__global__ void __launch_bounds__(STAGE_A_THREADS, ORE_STAGE_A_MIN_CTAS) shade_setup_kernel(const FrameParams prm, const StageArgs st) {
     const int lane = threadIdx.x & 31;
     const uint32_t n_items = (uint32_t)prm.counters[CNT_HITS];
     const v3 O0 = mk(prm.Ox, prm.Oy, prm.Oz);
@@ -1555,6 +1570,7 @@ __global__ void __launch_bounds__(CTA_THREADS, ORE_STAGE_A_MIN_CTAS) shade_setup
         if ((unsigned long long)blk * 32ull >= n_items) break;
         const uint32_t item = blk * 32u + lane;
         const bool valid = item < n_items;
+        const long long dbg_t0 = prm.dbg_cycles ? clock64() : 0;
         size_t o_out = 0;
         int my_id = -1;
         v3 start = mk(1e9f, 1e9f, 1e9f), normal = mk(0.f, 0.f, 0.f);
@@ -1592,6 +1608,7 @@ __global__ void __launch_bounds__(CTA_THREADS, ORE_STAGE_A_MIN_CTAS) shade_setup
             }
             q[30 * 32] = a;
         }
+        if (prm.dbg_cycles && lane == 0 && blk < prm.dbg_cap) prm.dbg_cycles[blk] = (uint32_t)(clock64() - dbg_t0);
     }
 }
 
@@ -1631,7 +1648,7 @@ __device__ __forceinline__ bool beam_may_touch(const float4 q, float bx, float b
 // offset <= rho_perp + t sin(a), which is exactly what level 1 bounds.
 // ------------------------------------------------------------------------------------
 template <bool EXH, bool STAGED>
-__global__ void __launch_bounds__(CTA_THREADS, ORE_BEAM_MIN_CTAS) shadow_beam_kernel(const FrameParams prm, const StageArgs st) {
+__global__ void __launch_bounds__(BEAM_THREADS, ORE_BEAM_MIN_CTAS) shadow_beam_kernel(const FrameParams prm, const StageArgs st) {
     constexpr int NL = 3;        // lights per pass
     constexpr int NR = 10 * NL;
     constexpr uint32_t ALL = (1u << NR) - 1u;
@@ -1682,6 +1699,7 @@ __global__ void __launch_bounds__(CTA_THREADS, ORE_BEAM_MIN_CTAS) shadow_beam_ke
         if ((unsigned long long)blk * 32ull >= n_items) break;
         const uint32_t item = blk * 32u + lane;
         const bool valid = item < n_items;
+        const long long dbg_t0 = prm.dbg_cycles ? clock64() : 0;
         // not near the end of the list / chunk, where a reserved block would wait behind this one while other
         // warps run dry
         const bool ahead = (unsigned long long)(blk + 8192u) * 32ull < n_items && (!STAGED || wb + 8192u < st.cap_blocks);
@@ -2033,6 +2051,8 @@ __global__ void __launch_bounds__(CTA_THREADS, ORE_BEAM_MIN_CTAS) shadow_beam_ke
             }
         }
         if (valid) prm.pixels[o_out] = ref_rgb_to_int((int)(fr * 254.f), (int)(fg * 254.f), (int)(fb * 254.f));
+        if (STAGED && prm.dbg_cycles && lane == 0 && blk < prm.dbg_cap)
+            prm.dbg_cycles[prm.dbg_cap + blk] = (uint32_t)(clock64() - dbg_t0);
         if (!ahead) {
             if (lane == 0) wb_next = (uint32_t)atomicAdd(cursor, 1ull);
             wb_next = __shfl_sync(0xffffffffu, wb_next, 0);

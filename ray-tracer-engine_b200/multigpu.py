@@ -151,13 +151,16 @@ class PeerFrame:
 
     ROW_BLOCK = ROW_BLOCK
 
-    def __init__(self, renderer, width: int, height: int, n_buffers: int = 2, group=None):
+    def __init__(self, renderer, width: int, height: int, n_buffers: int = 2, group=None, band_of=None):
+        """band_of = (rank, world): render the rows THAT rank of THAT many ranks would own while the flags stay those
+        of this process (single-process tools that look at one rank's share of a frame)"""
         import torch.distributed as dist
 
         self.r = renderer
         multi = dist.is_available() and dist.is_initialized()
         self.rank = dist.get_rank(group) if multi else 0
         self.world = dist.get_world_size(group) if multi else 1
+        self.band_rank, self.band_world = band_of if band_of else (self.rank, self.world)
         self.width, self.height = width, height
         self.nbytes = 4 * width * height
         self.ptrs = []
@@ -200,7 +203,7 @@ class PeerFrame:
     def band_args(self, buf: int) -> dict:
         """kwargs for Renderer.render_device: this rank's block-interleaved rows of buffer `buf`, stored at
         their image position in the presenter's frame."""
-        b = block_band(self.rank, self.world, self.height, self.ROW_BLOCK)
+        b = block_band(self.band_rank, self.band_world, self.height, self.ROW_BLOCK)
         return dict(out_ptr=self.ptrs[buf] + 4 * self.width * b["y0"], out_pitch=self.width, **b)
 
     # ---- one frame, flag protocol ----
