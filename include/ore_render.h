@@ -41,24 +41,17 @@ enum ore_flags {
      * by the parity tests to prove the filter never drops a hit. */
     ORE_FLAG_EXHAUSTIVE = 1,
     /* Also count, per frame, the sphere::intersect calls the REFERENCE's loop order
-     * would make in castLightRay (first blocker index + 1, or N) - the roofline's
-     * "tests" (SURVEY.md 8d).  Costs one extra kernel; off on the timed path. */
+     * would make in castLightRay (first blocker index + 1, or N) - the "tests" of the
+     * algorithmic rate.  Costs one extra kernel; off on the timed path. */
     ORE_FLAG_COUNT_REFERENCE_TESTS = 2,
-    /* Shadow phase without the per-light cone test: every sample ray is tested against
-     * every sphere (30 filter tests per pixel and sphere).  Same results; this is the
-     * kernel the FP32-pipe roofline figures in profiles/ are quoted on. */
-    ORE_FLAG_PER_RAY_SHADOW = 4,
-    /* No warp-cooperative culling: the primary kernel applies the per-pixel filter to every
-     * sphere and the shadow kernel the per-pixel cone test to every sphere (the previous
-     * generation of both kernels).  Same results. */
-    ORE_FLAG_NO_WARP_CULL = 8,
     /* Use CUDA's own cosf/sinf/acosf/atan2f instead of the glibc-bit-compatible device functions of the default
      * path (csrc/ore_libm.cuh).  ~20 % faster; ids and t unchanged; pixels within 1 LSB of the default on
      * >= 99.9 % (measured 99.999 %) instead of bit-identical to the host-compiled reference. */
     ORE_FLAG_FAST_LIBM = 16,
-    /* Default shadow pass as ONE kernel (shading set-up + light directions + sweep fused) instead of the two-stage
-     * pass through a staging buffer.  Same results; slower (its hot code does not fit the SM instruction cache) but
-     * needs no staging memory.  Also used automatically when the staging buffer cannot be allocated. */
+    /* Shadow pass as ONE kernel (shading set-up + light directions + sweep in one warp program) instead of the
+     * two-stage pass through a staging buffer.  Same results; slower (its hot code does not fit the SM instruction
+     * cache) but needs no staging memory.  Also what the catch-all launch runs and what a failed staging allocation
+     * falls back to. */
     ORE_FLAG_FUSED_SHADOW = 32,
     /* Do not record the per-kernel CUDA events behind ore_get_kernel_ms for this call (five event records per
      * frame; throughput loops set this, ore_get_kernel_ms then reports zeros). */
@@ -109,8 +102,10 @@ typedef struct ore_counters {
     uint64_t exact_primary;   /* exact re-adjudications executed, primary phase           */
     uint64_t exact_shadow;    /* exact re-adjudications executed, shadow phase            */
     uint64_t kernel_launches; /* kernels launched by the call                             */
-    uint64_t beam_l1;         /* spheres passing the warp-level beam test (sum over warps) */
-    uint64_t beam_l2;         /* (pixel, sphere) pairs passing the per-pixel cone test     */
+    uint64_t beam_l1;         /* spheres passing the warp-level beam test (sum over warps, lights, groups) */
+    uint64_t beam_l2;         /* (pixel, sphere, light) triples passing the per-pixel cone test */
+    uint64_t primary_steps;   /* warp steps of the primary sweep: 32 tile-cone tests each (super / leaf / sphere) */
+    uint64_t sweep_steps;     /* warp steps of the shadow sweep: 32 beam tests each                */
 } ore_counters;
 
 /* ---- lifetime ---------------------------------------------------------------------
@@ -227,7 +222,8 @@ int ore_copy_to_host(ore_context* ctx, void* host_dst, const void* dev_src, size
 
 /* ---- introspection of the LAST render (parity tests, roofline accounting) ---------
  * hit_id: nearest primitive or -1 (castRay, kernel.cu:1330-1372; spheres, then cubes, then planes); hit_t: nearest t,
- * +inf on miss.  Packed like the pixels.  Either pointer may be NULL. */
+ * +inf on miss.  Packed like the pixels.  Either pointer may be NULL.  The render path itself keeps one compact
+ * (pixel, id, t) record per HIT pixel; the per-pixel maps are expanded from them inside this call. */
 int ore_get_hits(ore_context* ctx, int32_t* hit_id_host, float* hit_t_host);
 int ore_get_counters(ore_context* ctx, ore_counters* out);
 /* average device time (ms) of each kernel of the last render, measured with CUDA events

@@ -15,8 +15,6 @@ from . import build as _build
 
 ORE_FLAG_EXHAUSTIVE = 1
 ORE_FLAG_COUNT_REFERENCE_TESTS = 2
-ORE_FLAG_PER_RAY_SHADOW = 4
-ORE_FLAG_NO_WARP_CULL = 8
 ORE_FLAG_FAST_LIBM = 16
 ORE_FLAG_FUSED_SHADOW = 32
 ORE_FLAG_NO_KERNEL_TIMING = 64
@@ -46,7 +44,7 @@ class OreFrame(C.Structure):
 class OreCounters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "pixels", "hit_pixels", "primary_tests", "shadow_tests_ref", "sky_tests",
-        "exact_primary", "exact_shadow", "kernel_launches", "beam_l1", "beam_l2")]
+        "exact_primary", "exact_shadow", "kernel_launches", "beam_l1", "beam_l2", "primary_steps", "sweep_steps")]
 
 
 class OreError(RuntimeError):

@@ -26,9 +26,9 @@ using namespace ore;
 extern "C" int ore_fast_set_tables(const float* cphi, const float* sphi, const float* bk);
 extern "C" int ore_fast_primary_tile(const void* prm, int sm_count, size_t smem, long long n_batches, int exh,
                                      cudaStream_t stream);
-// stage: a StageArgs of identical layout; staged = 0 selects the fused kernel (only first_block is used then)
-extern "C" int ore_fast_shadow_beam(const void* prm, const void* stage, int staged, int sm_count, size_t smem, int exh,
-                                    cudaStream_t stream);
+// stage: a StageArgs of identical layout; staged = 0 selects the fused form (only first_block is used then)
+extern "C" int ore_fast_shadow_sweep(const void* prm, const void* stage, int staged, int sm_count, size_t smem, int exh,
+                                     cudaStream_t stream);
 extern "C" int ore_fast_shade_setup(const void* prm, const void* stage, int sm_count, cudaStream_t stream);
 
 struct ore_context {
@@ -50,12 +50,21 @@ struct ore_context {
     size_t pinned_cap = 0;
 
     // scene (structure of arrays on the device)
-    int n_spheres = 0, n_spheres_pad = 0;
-    float4* sph_exact = nullptr;
-    float4* sph_prim = nullptr;
-    float4* sph_cone = nullptr;
-    float4* sph_shad = nullptr;
-    size_t sph_cap = 0;
+    int n_spheres = 0;
+    float4* sph_exact = nullptr;   // cx,cy,cz,radius member in ORIGINAL order (hit attributes by hit id)
+    // the spheres in Morton order with two levels of bounding balls over them (ore_clusters.h)
+    float4* sph_xsort = nullptr;   // exact records, sorted
+    float4* sph_sort = nullptr;    // shadow records cx,cy,cz,R', sorted
+    int* sort_index = nullptr;     // sorted position -> original index
+    float4* leaf_sph = nullptr;    // ball of spheres [8j, 8j+8)
+    float4* super_sph = nullptr;   // ball of leaves [32k, 32k+32)
+    // per-frame (camera-space) records of the primary kernel
+    float4* prim_sorted = nullptr;
+    float4* cone_sorted = nullptr;
+    float4* leaf_cone = nullptr;
+    float4* super_cone = nullptr;
+    int n_sort = 0, n_leaves = 0, n_leaves_pad = 0, n_supers = 0, n_supers_pad = 0;
+    size_t sph_cap = 0, sort_cap = 0, leaf_cap = 0, super_cap = 0;
     int n_lights = 0;
     LightP lights[MAX_LIGHTS];
     float* tex[3] = {nullptr, nullptr, nullptr};
@@ -79,30 +88,29 @@ struct ore_context {
     size_t dx_cap = 0;
     float* dy_tab = nullptr;
     size_t dy_cap = 0;
-    int32_t* hit_id = nullptr;
-    float* hit_t = nullptr;
-    uint32_t* hit_list = nullptr;
+    uint32_t* hit_list = nullptr;  // compact hit records (pixel, id, t), one per hit pixel
+    int32_t* hit_ids = nullptr;
+    float* hit_ts = nullptr;
     uint32_t* pixels = nullptr;
     size_t px_cap = 0;
+    int32_t* hit_id_map = nullptr;  // per-pixel id / t maps: only built by ore_get_hits
+    float* hit_t_map = nullptr;
+    size_t map_cap = 0;
     unsigned long long* counters = nullptr;
-    float4* sph_sort = nullptr;   // shadow records in Morton order, clusters of 32 (beam kernel sweep)
-    float4* sph_xsort = nullptr;  // exact records in the same order
-    float4* clu_sph = nullptr;    // bounding sphere per cluster
-    size_t sort_cap = 0, clu_cap = 0;
-    int n_clusters = 0;
     float* stage = nullptr;  // staging buffer between the two kernels of the default shadow pass
     size_t stage_cap = 0;    // floats
     size_t stage_blocks_override = 0;  // test hook (env ORE_STAGE_BLOCKS at ore_create): staging capacity in 32-item blocks
-    bool stage_always = false;         // test hook (env ORE_STAGE_ALWAYS=1): two-stage pass also for non-resident scenes
-    bool no_memops = false;
+    bool no_memops = false;            // test hook (env ORE_NO_STREAM_MEMOPS=1): flags through the one-thread kernels
     std::string dbg_cycles_path;       // tools hook (env ORE_DEBUG_BLOCK_CYCLES=file): per-block SM clocks of the shadow pass
     uint32_t* dbg_cycles = nullptr;
-    size_t dbg_cap = 0;            // test hook (env ORE_NO_STREAM_MEMOPS=1): flags through the one-thread kernels
+    size_t dbg_cap = 0;
     // hit count of this context's previous frame, copied to pinned memory at the end of every frame and read
     // WITHOUT synchronisation by the next one: only a hint for how many staged chunk pairs to launch - whatever
     // lies beyond them is swept by one catch-all fused launch, so any value (stale, zero, mid-copy) is safe
     unsigned long long* hits_hint = nullptr;
     bool hits_hint_set = false;
+    FrameParams last_prm;              // the last frame's parameters (ore_get_hits expands its hit records)
+    bool last_prm_valid = false;
 
     // occupancy-sized grids, computed once per (kernel, dynamic shared memory, block size)
     struct GridEntry {
@@ -202,7 +210,6 @@ extern "C" int ore_create(ore_context** out, int device) {
     ORE_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming));
     ORE_CUDA(ctx, cudaMallocHost((void**)&ctx->hits_hint, sizeof(unsigned long long)));
     *ctx->hits_hint = 0;
-    if (const char* e = getenv("ORE_STAGE_ALWAYS")) ctx->stage_always = atoi(e) != 0;
     if (const char* e = getenv("ORE_NO_STREAM_MEMOPS")) ctx->no_memops = atoi(e) != 0;
     if (const char* e = getenv("ORE_DEBUG_BLOCK_CYCLES")) ctx->dbg_cycles_path = e;
     if (const char* e = getenv("ORE_STAGE_BLOCKS")) {
@@ -266,10 +273,11 @@ extern "C" int ore_destroy(ore_context* ctx) {
         cudaStreamDestroy(ctx->signal_stream);
     }
     if (ctx->pixels_b) cudaFree(ctx->pixels_b);
-    void* dev[] = {ctx->stage, ctx->sph_sort, ctx->sph_xsort, ctx->clu_sph, ctx->sph_exact, ctx->sph_prim, ctx->sph_cone, ctx->sph_shad, ctx->tex[0], ctx->tex[1], ctx->tex[2],
-                   ctx->sky[0],    ctx->sky[1],   ctx->sky[2],   ctx->dx_tab, ctx->dy_tab, ctx->hit_id,
-                   ctx->hit_t,     ctx->hit_list, ctx->pixels,   ctx->counters, ctx->cubes,   ctx->planes,   ctx->tris,
-                   ctx->boxes,     ctx->box_offsets, ctx->box_indices, ctx->box_sph, ctx->box_cone};
+    void* dev[] = {ctx->stage, ctx->sph_exact, ctx->sph_xsort, ctx->sph_sort, ctx->sort_index, ctx->leaf_sph, ctx->super_sph,
+                   ctx->prim_sorted, ctx->cone_sorted, ctx->leaf_cone, ctx->super_cone, ctx->tex[0], ctx->tex[1], ctx->tex[2],
+                   ctx->sky[0], ctx->sky[1], ctx->sky[2], ctx->dx_tab, ctx->dy_tab, ctx->hit_list, ctx->hit_ids, ctx->hit_ts,
+                   ctx->hit_id_map, ctx->hit_t_map, ctx->pixels, ctx->counters, ctx->cubes, ctx->planes, ctx->tris, ctx->boxes,
+                   ctx->box_offsets, ctx->box_indices, ctx->box_sph, ctx->box_cone};
     for (void* p : dev)
         if (p) cudaFree(p);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -283,72 +291,86 @@ extern "C" int ore_destroy(ore_context* ctx) {
 
 // ---- scene upload -----------------------------------------------------------------------
 
-// Shadow-sweep clusters: the spheres in Morton order of their centres, 32 per cluster, one bounding sphere per
-// cluster.  The any-hit result does not depend on the order spheres are visited in, so the beam kernel walks clusters
-// first (one per lane) and only opens the ones its beams can touch.  ex/sh: the records just uploaded (pinned staging).
-static int upload_clusters(ore_context* ctx, const float4* ex, const float4* sh, int n) {
-    const int n_clu = (n + 31) / 32;
-    ctx->n_clusters = n_clu;
-    if (n_clu == 0) return ORE_OK;
-    const size_t n_sort = (size_t)n_clu * 32, n_clu_pad = ((size_t)n_clu + 3) & ~(size_t)3;
-    int rc;
-    size_t c1 = ctx->sort_cap, c2 = ctx->sort_cap;
-    if ((rc = ensure_dev(ctx, &ctx->sph_sort, &c1, n_sort))) return rc;
-    if ((rc = ensure_dev(ctx, &ctx->sph_xsort, &c2, n_sort))) return rc;
-    ctx->sort_cap = c1 < c2 ? c1 : c2;
-    if ((rc = ensure_dev(ctx, &ctx->clu_sph, &ctx->clu_cap, n_clu_pad))) return rc;
-
-    // host-only builder (csrc/ore_clusters.h, unit-tested on the CPU by tests/test_clusters_cpu.py)
-    std::vector<ore_host::Rec4> ss, xs, cl;
-    ore_host::build_clusters(reinterpret_cast<const ore_host::Rec4*>(ex), reinterpret_cast<const ore_host::Rec4*>(sh), n, ss, xs, cl);
-    static_assert(sizeof(ore_host::Rec4) == sizeof(float4), "Rec4 must have float4's layout");
-    if (ss.size() != n_sort || cl.size() != n_clu_pad) return fail(ctx, ORE_ERR_INVALID, "cluster builder size mismatch");
-    ORE_CUDA(ctx, cudaMemcpy(ctx->sph_sort, ss.data(), n_sort * sizeof(float4), cudaMemcpyHostToDevice));
-    ORE_CUDA(ctx, cudaMemcpy(ctx->sph_xsort, xs.data(), n_sort * sizeof(float4), cudaMemcpyHostToDevice));
-    ORE_CUDA(ctx, cudaMemcpy(ctx->clu_sph, cl.data(), n_clu_pad * sizeof(float4), cudaMemcpyHostToDevice));
-    return ORE_OK;
-}
-
+// Replaces object::sphereAllocMem: the n records go to the device twice - in their original order (hit attributes are
+// looked up by hit id) and in the Morton order of their centres, with a bounding ball per leaf of 8 and per
+// super-cluster of 32 leaves (csrc/ore_clusters.h, unit-tested on the CPU by tests/test_clusters_cpu.py).  Both
+// the primary kernel (tile cones) and the shadow sweep (beams) descend that hierarchy; neither result depends on
+// the order spheres are visited in (nearest hit: candidates are adjudicated by (t, original index)).
 static int upload_spheres(ore_context* ctx, const float* src, size_t stride_floats, size_t first, int32_t n) {
     if (!ctx || n < 0 || (n > 0 && !src)) return fail(ctx, ORE_ERR_INVALID, "ore_set_spheres: bad arguments");
     ORE_CUDA(ctx, cudaSetDevice(ctx->device));
     if (int rcw = wait_last_render(ctx)) return rcw;
-    const int n_pad = ((n + SPHERE_PAD - 1) / SPHERE_PAD) * SPHERE_PAD + SPHERE_PAD;  // >= 1 pad block
-    size_t cap_e = ctx->sph_cap, cap_p = ctx->sph_cap, cap_s = ctx->sph_cap, cap_c = ctx->sph_cap;
-    int rc;
-    if ((rc = ensure_dev(ctx, &ctx->sph_exact, &cap_e, (size_t)n_pad))) return rc;
-    if ((rc = ensure_dev(ctx, &ctx->sph_prim, &cap_p, (size_t)n_pad))) return rc;
-    if ((rc = ensure_dev(ctx, &ctx->sph_cone, &cap_c, (size_t)n_pad))) return rc;
-    if ((rc = ensure_dev(ctx, &ctx->sph_shad, &cap_s, (size_t)n_pad))) return rc;
-    ctx->sph_cap = std::min(std::min(cap_e, cap_p), std::min(cap_s, cap_c));
-    if ((rc = ensure_pinned(ctx, 2 * (size_t)n_pad * sizeof(float4)))) return rc;
-    float4* ex = (float4*)ctx->pinned;
-    float4* sh = ex + n_pad;
-    for (int i = 0; i < n_pad; i++) {
-        if (i < n) {
-            const float* s = src + (size_t)i * stride_floats + first;
-            ex[i] = make_float4(s[0], s[1], s[2], s[3]);
-            const float r4 = s[3] * s[3];  // the test squares the stored member, kernel.cu:334
-            // R' = effective radius, rounded up so that R'^2 >= (1+k) r4 in float
-            float rp = (float)sqrt((double)r4 * (1.0 + (double)ORE_KAPPA_SHADOW));
-            rp = nextafterf(rp, INFINITY);
-            while (rp * rp < (float)((double)r4 * (1.0 + (double)ORE_KAPPA_SHADOW))) rp = nextafterf(rp, INFINITY);
-            sh[i] = make_float4(s[0], s[1], s[2], rp);
-        } else if (n > 0) {
-            // padding = copies of the last sphere: any-hit is idempotent and the exact path skips idx >= n
-            ex[i] = ex[n - 1];
-            sh[i] = sh[n - 1];
-        } else {
-            ex[i] = make_float4(3e18f, -1e18f, 2e17f, 0.f);
-            sh[i] = make_float4(3e18f, -1e18f, 2e17f, 0.f);
-        }
+    std::vector<ore_host::Rec4> ex((size_t)std::max(n, 1)), sh((size_t)std::max(n, 1));
+    for (int i = 0; i < n; i++) {
+        const float* s = src + (size_t)i * stride_floats + first;
+        ex[i] = ore_host::Rec4{s[0], s[1], s[2], s[3]};
+        const float r4 = s[3] * s[3];  // the test squares the stored member, kernel.cu:334
+        // R' = effective radius, rounded up so that R'^2 >= (1+k) r4 in float
+        float rp = (float)sqrt((double)r4 * (1.0 + (double)ORE_KAPPA_SHADOW));
+        rp = nextafterf(rp, INFINITY);
+        while (rp * rp < (float)((double)r4 * (1.0 + (double)ORE_KAPPA_SHADOW))) rp = nextafterf(rp, INFINITY);
+        sh[i] = ore_host::Rec4{s[0], s[1], s[2], rp};
     }
-    ORE_CUDA(ctx, cudaMemcpyAsync(ctx->sph_exact, ex, (size_t)n_pad * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
-    ORE_CUDA(ctx, cudaMemcpyAsync(ctx->sph_shad, sh, (size_t)n_pad * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<ore_host::Rec4> ss, xs, cl32, leaves, supers;
+    std::vector<int> order;
+    ore_host::build_clusters(ex.data(), sh.data(), n, ss, xs, cl32, &order);
+    ore_host::build_hierarchy(ss, n, leaves, supers);
+    static_assert(sizeof(ore_host::Rec4) == sizeof(float4), "Rec4 must have float4's layout");
+    if (ss.empty()) {   // empty scene: one block of padding records (never read: every loop is bounded by n = 0)
+        ss.assign(32, ore_host::Rec4{3e18f, -1e18f, 2e17f, 0.f});
+        xs = ss;
+        order.assign(32, 0);
+    }
+    const size_t n_sort = ss.size(), n_leaf_pad = leaves.size(), n_sup_pad = supers.size();
+    int rc;
+    size_t c0 = ctx->sph_cap;
+    if ((rc = ensure_dev(ctx, &ctx->sph_exact, &c0, (size_t)std::max(n, 1)))) return rc;
+    ctx->sph_cap = c0;
+    size_t c1 = ctx->sort_cap, c2 = c1, c3 = c1, c4 = c1, c5 = c1;
+    if ((rc = ensure_dev(ctx, &ctx->sph_xsort, &c1, n_sort))) return rc;
+    if ((rc = ensure_dev(ctx, &ctx->sph_sort, &c2, n_sort))) return rc;
+    if ((rc = ensure_dev(ctx, &ctx->sort_index, &c3, n_sort))) return rc;
+    if ((rc = ensure_dev(ctx, &ctx->prim_sorted, &c4, n_sort))) return rc;
+    if ((rc = ensure_dev(ctx, &ctx->cone_sorted, &c5, n_sort))) return rc;
+    ctx->sort_cap = std::min(std::min(c1, c2), std::min(std::min(c3, c4), c5));
+    size_t l1 = ctx->leaf_cap, l2 = l1;
+    if ((rc = ensure_dev(ctx, &ctx->leaf_sph, &l1, n_leaf_pad))) return rc;
+    if ((rc = ensure_dev(ctx, &ctx->leaf_cone, &l2, n_leaf_pad))) return rc;
+    ctx->leaf_cap = std::min(l1, l2);
+    size_t s1 = ctx->super_cap, s2 = s1;
+    if ((rc = ensure_dev(ctx, &ctx->super_sph, &s1, n_sup_pad))) return rc;
+    if ((rc = ensure_dev(ctx, &ctx->super_cone, &s2, n_sup_pad))) return rc;
+    ctx->super_cap = std::min(s1, s2);
+    // pinned staging: the five arrays back to back (16-byte records first), one H2D copy each
+    const size_t b_ex = (size_t)std::max(n, 1) * 16, b_sort = n_sort * 16, b_leaf = n_leaf_pad * 16, b_sup = n_sup_pad * 16;
+    if ((rc = ensure_pinned(ctx, b_ex + 2 * b_sort + b_leaf + b_sup + n_sort * sizeof(int)))) return rc;
+    char* h = (char*)ctx->pinned;
+    char* h_ex = h;
+    char* h_xs = h_ex + b_ex;
+    char* h_ss = h_xs + b_sort;
+    char* h_lv = h_ss + b_sort;
+    char* h_sp = h_lv + b_leaf;
+    char* h_ix = h_sp + b_sup;
+    memcpy(h_ex, ex.data(), b_ex);
+    memcpy(h_xs, xs.data(), b_sort);
+    memcpy(h_ss, ss.data(), b_sort);
+    memcpy(h_lv, leaves.data(), b_leaf);
+    memcpy(h_sp, supers.data(), b_sup);
+    memcpy(h_ix, order.data(), n_sort * sizeof(int));
+    ORE_CUDA(ctx, cudaMemcpyAsync(ctx->sph_exact, h_ex, b_ex, cudaMemcpyHostToDevice, ctx->stream));
+    ORE_CUDA(ctx, cudaMemcpyAsync(ctx->sph_xsort, h_xs, b_sort, cudaMemcpyHostToDevice, ctx->stream));
+    ORE_CUDA(ctx, cudaMemcpyAsync(ctx->sph_sort, h_ss, b_sort, cudaMemcpyHostToDevice, ctx->stream));
+    ORE_CUDA(ctx, cudaMemcpyAsync(ctx->leaf_sph, h_lv, b_leaf, cudaMemcpyHostToDevice, ctx->stream));
+    ORE_CUDA(ctx, cudaMemcpyAsync(ctx->super_sph, h_sp, b_sup, cudaMemcpyHostToDevice, ctx->stream));
+    ORE_CUDA(ctx, cudaMemcpyAsync(ctx->sort_index, h_ix, n_sort * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     ORE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->n_spheres = n;
-    ctx->n_spheres_pad = n_pad;
-    return upload_clusters(ctx, ex, sh, n);
+    ctx->n_sort = (int)n_sort;
+    ctx->n_leaves = (n + ore_host::LEAF_SPHERES - 1) / ore_host::LEAF_SPHERES;
+    ctx->n_leaves_pad = (int)n_leaf_pad;
+    ctx->n_supers = (ctx->n_leaves + ore_host::SUPER_LEAVES - 1) / ore_host::SUPER_LEAVES;
+    ctx->n_supers_pad = (int)n_sup_pad;
+    return ORE_OK;
 }
 
 extern "C" int ore_set_spheres(ore_context* ctx, const float* xyz_radius, int32_t n) {
@@ -546,11 +568,10 @@ extern "C" int ore_set_sky(ore_context* ctx, const float* r, const float* g, con
 
 // ---- render -------------------------------------------------------------------------------
 
-static constexpr int PRIMARY_P = 8;        // pixels per thread of the strip kernel (NO_WARP_CULL generation)
-static constexpr int TILE_ROWS = TILE_P;   // rows per tile of the default primary kernel
-static constexpr size_t RESIDENT_BYTES = 96 * 1024;
-static constexpr int STREAM_CHUNK = 2048;
-static constexpr int STREAM_STAGES = 3;
+static constexpr int TILE_ROWS = TILE_P;   // rows per tile of the primary kernel
+// shared memory of the primary kernel: the leaf / super-cluster cone records always, the sphere-level records when
+// everything stays within this budget (6 CTAs of 128 threads per SM)
+static constexpr size_t PRIMARY_RESIDENT_BYTES = 36 * 1024;
 
 template <typename K>
 static int grid_for(ore_context* ctx, K kernel, size_t smem, int* grid, int threads = CTA_THREADS) {
@@ -583,6 +604,30 @@ static int frame_rows(const ore_frame* fr) {
     return full * yb + (rem < yb ? rem : yb);
 }
 
+// one launch of the sweep kernel (stage B / fused / catch-all)
+static int launch_sweep(ore_context* ctx, const FrameParams& prm, const StageArgs& st, bool staged, bool exh, bool fast_libm,
+                        cudaStream_t stream) {
+    int rc, grid = 0;
+    const size_t smem = SWEEP_SMEM_BYTES;
+    if (fast_libm) {
+        ORE_CUDA(ctx, (cudaError_t)ore_fast_shadow_sweep(&prm, &st, staged ? 1 : 0, ctx->sm_count, smem, exh ? 1 : 0, stream));
+        return ORE_OK;
+    }
+#define ORE_SWEEP(E, S)                                                                                  \
+    do {                                                                                                 \
+        if ((rc = grid_for(ctx, shadow_sweep_kernel<E, S>, smem, &grid, SWEEP_THREADS))) return rc;      \
+        shadow_sweep_kernel<E, S><<<grid, SWEEP_THREADS, smem, stream>>>(prm, st);                       \
+    } while (0)
+    if (staged) {
+        if (exh) ORE_SWEEP(true, true); else ORE_SWEEP(false, true);
+    } else {
+        if (exh) ORE_SWEEP(true, false); else ORE_SWEEP(false, false);
+    }
+#undef ORE_SWEEP
+    ORE_CUDA(ctx, cudaGetLastError());
+    return ORE_OK;
+}
+
 static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame* fr, uint32_t* out_device,
                        cudaStream_t stream) {
     if (!ctx) return ORE_ERR_INVALID;
@@ -591,6 +636,9 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
     if (fr->width <= 0 || fr->height <= 0 || fr->y_step <= 0 || fr->y0 < 0 || fr->y1 < 0 || fr->y1 > fr->height ||
         (fr->out_pitch != 0 && fr->out_pitch < fr->width))
         return fail(ctx, ORE_ERR_INVALID, "ore_render: bad frame geometry");
+    if (fr->flags & ~(uint32_t)(ORE_FLAG_EXHAUSTIVE | ORE_FLAG_COUNT_REFERENCE_TESTS | ORE_FLAG_FAST_LIBM | ORE_FLAG_FUSED_SHADOW |
+                                ORE_FLAG_NO_KERNEL_TIMING))
+        return fail(ctx, ORE_ERR_INVALID, "ore_render: unknown flag");
     if (!ctx->tex[0] || !ctx->sky[0]) return fail(ctx, ORE_ERR_INVALID, "ore_render: texture and sky must be set first");
     if (!ctx->sph_exact) {
         int rc = upload_spheres(ctx, nullptr, 4, 0, 0);
@@ -608,23 +656,26 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
     ctx->last_launches = 0;
     ctx->ev_valid = false;
     ctx->ran_count = false;
+    ctx->last_prm_valid = false;
     if (n_px == 0) return ORE_OK;
 
     int rc;
-    if ((rc = ensure_dev(ctx, &ctx->dx_tab, &ctx->dx_cap, (size_t)W))) return rc;
+    const int W_pad = (W + 31) & ~31;
+    if ((rc = ensure_dev(ctx, &ctx->dx_tab, &ctx->dx_cap, (size_t)W_pad))) return rc;
     if ((rc = ensure_dev(ctx, &ctx->dy_tab, &ctx->dy_cap, (size_t)n_rows))) return rc;
-    if (n_px > ctx->px_cap || !ctx->hit_id) {
-        size_t c1 = ctx->hit_id ? ctx->px_cap : 0, c2 = c1, c3 = c1, c4 = c1;
-        if ((rc = ensure_dev(ctx, &ctx->hit_id, &c1, n_px))) return rc;
-        if ((rc = ensure_dev(ctx, &ctx->hit_t, &c2, n_px))) return rc;
-        if ((rc = ensure_dev(ctx, &ctx->hit_list, &c3, n_px))) return rc;
+    if (n_px > ctx->px_cap || !ctx->hit_list) {
+        size_t c1 = ctx->hit_list ? ctx->px_cap : 0, c2 = c1, c3 = c1, c4 = c1;
+        if ((rc = ensure_dev(ctx, &ctx->hit_list, &c1, n_px))) return rc;
+        if ((rc = ensure_dev(ctx, &ctx->hit_ids, &c2, n_px))) return rc;
+        if ((rc = ensure_dev(ctx, &ctx->hit_ts, &c3, n_px))) return rc;
         if ((rc = ensure_dev(ctx, &ctx->pixels, &c4, n_px))) return rc;
-        ctx->px_cap = c1;
+        ctx->px_cap = std::min(std::min(c1, c2), std::min(c3, c4));
     }
 
     FrameParams prm;
     memset(&prm, 0, sizeof prm);
     prm.W = W;
+    prm.W_pad = W_pad;
     prm.H = fr->height;
     prm.y0 = fr->y0;
     prm.y_step = (yb >= fr->y_step) ? 1 : fr->y_step;
@@ -633,7 +684,6 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
     prm.out_global = (out_device && fr->out_pitch > 0) ? 1 : 0;
     prm.pitch = prm.out_global ? fr->out_pitch : W;
     prm.n_spheres = ctx->n_spheres;
-    prm.n_spheres_pad = ctx->n_spheres_pad;
     prm.n_lights = ctx->n_lights;
     prm.flags = fr->flags;
     prm.aspect = fr->aspect;
@@ -677,30 +727,28 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
             prm.tile_sa = (float)(sin(a) * (1.0 + 1e-6) + 1e-6);
         }
     }
-    if ((size_t)ctx->n_spheres_pad * sizeof(float4) <= RESIDENT_BYTES) {
-        prm.resident = 1;
-        prm.chunk = ctx->n_spheres_pad;
-        prm.stages = 1;
-        prm.n_chunks = 1;
-    } else {
-        prm.resident = 0;
-        prm.chunk = STREAM_CHUNK;
-        prm.stages = STREAM_STAGES;
-        prm.n_chunks = (ctx->n_spheres_pad + STREAM_CHUNK - 1) / STREAM_CHUNK;
-    }
-    const size_t smem = (size_t)prm.stages * prm.chunk * sizeof(float4);
     prm.dx_tab = ctx->dx_tab;
     prm.dy_tab = ctx->dy_tab;
     prm.sph_exact = ctx->sph_exact;
-    prm.sph_prim = ctx->sph_prim;
-    prm.sph_cone = ctx->sph_cone;
-    prm.sph_shad = ctx->sph_shad;
-    prm.sph_sort = ctx->sph_sort;
     prm.sph_xsort = ctx->sph_xsort;
-    prm.clu_sph = ctx->clu_sph;
-    prm.n_clusters = ctx->n_clusters;
-    const size_t beam_bytes = ((size_t)ctx->n_clusters * 32 + (((size_t)ctx->n_clusters + 3) & ~(size_t)3)) * sizeof(float4);
-    prm.beam_resident = (ctx->n_clusters > 0 && beam_bytes <= RESIDENT_BYTES) ? 1 : 0;
+    prm.sph_sort = ctx->sph_sort;
+    prm.sort_index = ctx->sort_index;
+    prm.leaf_sph = ctx->leaf_sph;
+    prm.super_sph = ctx->super_sph;
+    prm.n_sort = ctx->n_sort;
+    prm.n_leaves = ctx->n_leaves;
+    prm.n_leaves_pad = ctx->n_leaves_pad;
+    prm.n_supers = ctx->n_supers;
+    prm.n_supers_pad = ctx->n_supers_pad;
+    prm.prim_sorted = ctx->prim_sorted;
+    prm.cone_sorted = ctx->cone_sorted;
+    prm.leaf_cone = ctx->leaf_cone;
+    prm.super_cone = ctx->super_cone;
+    const size_t tree_bytes = ((size_t)ctx->n_supers_pad + (size_t)ctx->n_leaves_pad) * sizeof(float4);
+    const size_t all_bytes = tree_bytes + (size_t)ctx->n_sort * sizeof(float4);
+    prm.cone_resident = all_bytes <= PRIMARY_RESIDENT_BYTES ? 1 : 0;
+    const size_t psmem = prm.cone_resident ? all_bytes : tree_bytes;
+    if (psmem > 200 * 1024) return fail(ctx, ORE_ERR_INVALID, "ore_render: more than ~100 000 spheres are not supported");
     prm.tex_r = ctx->tex[0];
     prm.tex_g = ctx->tex[1];
     prm.tex_b = ctx->tex[2];
@@ -725,9 +773,9 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
     prm.n_tris = ctx->n_tris;
     prm.n_boxes = ctx->n_boxes;
     prm.mesh_has_normals = ctx->mesh_has_normals;
-    prm.hit_id = ctx->hit_id;
-    prm.hit_t = ctx->hit_t;
     prm.hit_list = ctx->hit_list;
+    prm.hit_ids = ctx->hit_ids;
+    prm.hit_ts = ctx->hit_ts;
     prm.counters = ctx->counters;
     prm.pixels = out_device ? out_device : ctx->pixels;
     if (!ctx->dbg_cycles_path.empty()) {
@@ -750,172 +798,104 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
     }
     if (timing) ORE_CUDA(ctx, cudaEventRecord(ctx->ev[0], stream));
     {
-        int m = W > n_rows ? W : n_rows;
-        if (ctx->n_spheres_pad > m) m = ctx->n_spheres_pad;
-        if (ctx->n_boxes > m) m = ctx->n_boxes;
-        if (m < CNT_SLOTS) m = CNT_SLOTS;
+        int m = W_pad > n_rows ? W_pad : n_rows;
+        m = std::max(m, std::max(ctx->n_sort, std::max(ctx->n_leaves_pad, ctx->n_supers_pad)));
+        m = std::max(m, std::max(ctx->n_boxes, (int)CNT_SLOTS));
         prep_frame_kernel<<<(m + 255) / 256, 256, 0, stream>>>(prm);
         ORE_CUDA(ctx, cudaGetLastError());
         ctx->last_launches++;
     }
     if (timing) ORE_CUDA(ctx, cudaEventRecord(ctx->ev[1], stream));
     const bool exh = (fr->flags & ORE_FLAG_EXHAUSTIVE) != 0;
-    const bool warp_cull = !(fr->flags & (ORE_FLAG_NO_WARP_CULL | ORE_FLAG_PER_RAY_SHADOW));
-    const bool fast_libm = (fr->flags & ORE_FLAG_FAST_LIBM) != 0;  // default-path kernels only
-    if (!warp_cull && (ctx->n_cubes || ctx->n_planes || ctx->n_boxes))
-        return fail(ctx, ORE_ERR_INVALID,
-                    "cubes/planes/meshes are supported by the default kernels only (drop NO_WARP_CULL / PER_RAY_SHADOW)");
+    const bool fast_libm = (fr->flags & ORE_FLAG_FAST_LIBM) != 0;
     {
         int grid = 0;
-        if (warp_cull && fast_libm) {
-            const long long tiles = (long long)((W + 31) / 32) * ((n_rows + TILE_ROWS - 1) / TILE_ROWS);
-            const long long n_batches = (tiles + CTA_WARPS - 1) / CTA_WARPS;
-            ORE_CUDA(ctx, (cudaError_t)ore_fast_primary_tile(&prm, ctx->sm_count, smem, n_batches, exh ? 1 : 0, stream));
-        } else if (warp_cull) {
-            const long long tiles = (long long)((W + 31) / 32) * ((n_rows + TILE_ROWS - 1) / TILE_ROWS);
-            const long long n_batches = (tiles + CTA_WARPS - 1) / CTA_WARPS;
-            if (exh) {
-                if ((rc = grid_for(ctx, primary_tile_kernel<TILE_ROWS, true>, smem, &grid))) return rc;
-                if (grid > n_batches) grid = (int)n_batches;
-                primary_tile_kernel<TILE_ROWS, true><<<grid, CTA_THREADS, smem, stream>>>(prm);
-            } else {
-                if ((rc = grid_for(ctx, primary_tile_kernel<TILE_ROWS, false>, smem, &grid))) return rc;
-                if (grid > n_batches) grid = (int)n_batches;
-                primary_tile_kernel<TILE_ROWS, false><<<grid, CTA_THREADS, smem, stream>>>(prm);
-            }
-        } else {
-            if ((rc = grid_for(ctx, primary_kernel<PRIMARY_P>, smem, &grid))) return rc;
-            const int strips_per_row = (W + 32 * PRIMARY_P - 1) / (32 * PRIMARY_P);
-            const long long n_batches = ((long long)n_rows * strips_per_row + CTA_WARPS - 1) / CTA_WARPS;
+        const long long tiles = (long long)((W + 31) / 32) * ((n_rows + TILE_ROWS - 1) / TILE_ROWS);
+        const long long n_batches = (tiles + PRIMARY_WARPS - 1) / PRIMARY_WARPS;
+        if (fast_libm) {
+            ORE_CUDA(ctx, (cudaError_t)ore_fast_primary_tile(&prm, ctx->sm_count, psmem, n_batches, exh ? 1 : 0, stream));
+        } else if (exh) {
+            if ((rc = grid_for(ctx, primary_tile_kernel<TILE_ROWS, true>, psmem, &grid, PRIMARY_THREADS))) return rc;
             if (grid > n_batches) grid = (int)n_batches;
-            primary_kernel<PRIMARY_P><<<grid, CTA_THREADS, smem, stream>>>(prm);
+            primary_tile_kernel<TILE_ROWS, true><<<grid, PRIMARY_THREADS, psmem, stream>>>(prm);
+        } else {
+            if ((rc = grid_for(ctx, primary_tile_kernel<TILE_ROWS, false>, psmem, &grid, PRIMARY_THREADS))) return rc;
+            if (grid > n_batches) grid = (int)n_batches;
+            primary_tile_kernel<TILE_ROWS, false><<<grid, PRIMARY_THREADS, psmem, stream>>>(prm);
         }
         ORE_CUDA(ctx, cudaGetLastError());
         ctx->last_launches++;
     }
     if (timing) ORE_CUDA(ctx, cudaEventRecord(ctx->ev[2], stream));
     {
-        int grid = 0;
-        const int nl = ctx->n_lights >= 3 ? 3 : (ctx->n_lights == 2 ? 2 : 1);
-#define ORE_LAUNCH_SHADOW(NL, EXH)                                                        \
-    do {                                                                                  \
-        if ((rc = grid_for(ctx, shadow_kernel<NL, EXH>, smem, &grid, SHADOW_THREADS))) return rc; \
-        shadow_kernel<NL, EXH><<<grid, SHADOW_THREADS, smem, stream>>>(prm);              \
-    } while (0)
-        if (warp_cull) {
-            // the beam kernel stages the whole record array (resident) or reads it through L1/L2: no ring
-            const size_t bsmem = prm.beam_resident ? beam_bytes : 0;
-            // Two-stage pass (default): shade_setup_kernel -> staging buffer -> staged shadow_beam_kernel, in chunks
-            // of the hit list that fit the staging buffer.  The host does not know the hit count (no sync), so the
-            // chunk count comes from the pixel count; kernels of chunks past the end of the hit list exit at once.
-            StageArgs st{};
-            st.nv = 6 + 31 * ctx->n_lights;
-            const size_t n_blocks_px = (n_px + 31) / 32;
-            size_t cap_blocks = 0;
-            // Scenes whose sphere records do not fit in shared memory sweep them through L1; that sweep is bound
-            // by L1 bandwidth and the fused kernel hides the set-up arithmetic under it, so it stays the better
-            // choice there (4K / 16384 spheres: 8.1 ms fused, 10.3 ms two-stage; 8K / 1024: 4.5 vs 3.7 ms).
-            bool staged = !(fr->flags & ORE_FLAG_FUSED_SHADOW) && (prm.beam_resident || ctx->stage_always);
-            if (staged) {
-                size_t want_items = n_px / 4 > ((size_t)1 << 20) ? n_px / 4 : ((size_t)1 << 20);
-                if (want_items > ((size_t)16 << 20)) want_items = (size_t)16 << 20;
-                if (want_items > n_px) want_items = n_px;
-                cap_blocks = (want_items + 31) / 32;
-                if (ctx->stage_blocks_override) cap_blocks = ctx->stage_blocks_override;
-                while ((n_blocks_px + cap_blocks - 1) / cap_blocks > (size_t)MAX_STAGE_CHUNKS) cap_blocks *= 2;
-                const size_t need = cap_blocks * 32 * (size_t)st.nv;
-                if (need > ctx->stage_cap || !ctx->stage) {
-                    if (ctx->stage) ORE_CUDA(ctx, cudaFree(ctx->stage));
-                    ctx->stage = nullptr;
-                    ctx->stage_cap = 0;
-                    if (cudaMalloc((void**)&ctx->stage, need * sizeof(float)) == cudaSuccess) {
-                        ctx->stage_cap = need;
-                    } else {
-                        (void)cudaGetLastError();  // no room for the staging buffer: the fused kernel needs none
-                        ctx->stage = nullptr;
-                        staged = false;
-                    }
-                }
-            }
-            if (!staged) {
-                if (fast_libm) {
-                    ORE_CUDA(ctx, (cudaError_t)ore_fast_shadow_beam(&prm, &st, 0, ctx->sm_count, bsmem, exh ? 1 : 0, stream));
-                } else if (exh) {
-                    if ((rc = grid_for(ctx, shadow_beam_kernel<true, false>, bsmem, &grid, BEAM_THREADS))) return rc;
-                    shadow_beam_kernel<true, false><<<grid, BEAM_THREADS, bsmem, stream>>>(prm, st);
+        // Two-stage pass (default): shade_setup_kernel -> staging buffer -> staged shadow_sweep_kernel, in chunks of the
+        // hit list that fit the staging buffer.  The host does not know the hit count (no sync): the first frame of a
+        // context sizes the chunk count from the pixel count, later frames from the previous frame's hit count (a hint
+        // read without synchronisation), and one catch-all launch of the fused sweep takes whatever lies beyond.
+        StageArgs st{};
+        st.nv = STAGE_HEADER + STAGE_PER_LIGHT * ctx->n_lights;
+        const size_t n_blocks_px = (n_px + 31) / 32;
+        size_t cap_blocks = 0;
+        bool staged = !(fr->flags & ORE_FLAG_FUSED_SHADOW);
+        if (staged) {
+            size_t want_items = n_px / 4 > ((size_t)1 << 20) ? n_px / 4 : ((size_t)1 << 20);
+            if (want_items > ((size_t)16 << 20)) want_items = (size_t)16 << 20;
+            if (want_items > n_px) want_items = n_px;
+            cap_blocks = (want_items + 31) / 32;
+            if (ctx->stage_blocks_override) cap_blocks = ctx->stage_blocks_override;
+            while ((n_blocks_px + cap_blocks - 1) / cap_blocks > (size_t)MAX_STAGE_CHUNKS) cap_blocks *= 2;
+            const size_t need = cap_blocks * 32 * (size_t)st.nv;
+            if (need > ctx->stage_cap || !ctx->stage) {
+                if (ctx->stage) ORE_CUDA(ctx, cudaFree(ctx->stage));
+                ctx->stage = nullptr;
+                ctx->stage_cap = 0;
+                if (cudaMalloc((void**)&ctx->stage, need * sizeof(float)) == cudaSuccess) {
+                    ctx->stage_cap = need;
                 } else {
-                    if ((rc = grid_for(ctx, shadow_beam_kernel<false, false>, bsmem, &grid, BEAM_THREADS))) return rc;
-                    shadow_beam_kernel<false, false><<<grid, BEAM_THREADS, bsmem, stream>>>(prm, st);
-                }
-            } else {
-                st.buf = ctx->stage;
-                st.cap_blocks = (uint32_t)cap_blocks;
-                const int n_chunks_max = (int)((n_blocks_px + cap_blocks - 1) / cap_blocks);
-                int n_chunks = n_chunks_max;
-                if (ctx->hits_hint_set) {
-                    // previous frame's hit count + 25 % + 64 K items; the catch-all below covers a wrong guess
-                    const unsigned long long h = *(volatile unsigned long long*)ctx->hits_hint;
-                    const unsigned long long est_blocks = (h + h / 4 + 65536ull + 31ull) / 32ull;
-                    const unsigned long long want = (est_blocks + cap_blocks - 1) / cap_blocks;
-                    if (want < (unsigned long long)n_chunks_max) n_chunks = want < 1 ? 1 : (int)want;
-                }
-                int grid_a = 0, grid_b = 0;
-                if (!fast_libm) {
-                    if ((rc = grid_for(ctx, shade_setup_kernel, 0, &grid_a, STAGE_A_THREADS))) return rc;
-                    if (exh) rc = grid_for(ctx, shadow_beam_kernel<true, true>, bsmem, &grid_b, BEAM_THREADS);
-                    else rc = grid_for(ctx, shadow_beam_kernel<false, true>, bsmem, &grid_b, BEAM_THREADS);
-                    if (rc) return rc;
-                }
-                if (n_chunks < n_chunks_max) {
-                    // catch-all: hit-list blocks beyond the staged chunks (normally none: exits at once), one fused launch
-                    StageArgs rest{};
-                    rest.first_block = (uint32_t)((size_t)n_chunks * cap_blocks);
-                    rest.nv = st.nv;
-                    if (fast_libm) {
-                        ORE_CUDA(ctx, (cudaError_t)ore_fast_shadow_beam(&prm, &rest, 0, ctx->sm_count, bsmem, exh ? 1 : 0, stream));
-                    } else if (exh) {
-                        if ((rc = grid_for(ctx, shadow_beam_kernel<true, false>, bsmem, &grid, BEAM_THREADS))) return rc;
-                        shadow_beam_kernel<true, false><<<grid, BEAM_THREADS, bsmem, stream>>>(prm, rest);
-                    } else {
-                        if ((rc = grid_for(ctx, shadow_beam_kernel<false, false>, bsmem, &grid, BEAM_THREADS))) return rc;
-                        shadow_beam_kernel<false, false><<<grid, BEAM_THREADS, bsmem, stream>>>(prm, rest);
-                    }
-                    ORE_CUDA(ctx, cudaGetLastError());
-                    ctx->last_launches++;
-                }
-                for (int c = 0; c < n_chunks; c++) {
-                    st.chunk = c;
-                    st.first_block = (uint32_t)((size_t)c * cap_blocks);
-                    if (fast_libm) {
-                        ORE_CUDA(ctx, (cudaError_t)ore_fast_shade_setup(&prm, &st, ctx->sm_count, stream));
-                        ORE_CUDA(ctx, (cudaError_t)ore_fast_shadow_beam(&prm, &st, 1, ctx->sm_count, bsmem, exh ? 1 : 0, stream));
-                    } else {
-                        shade_setup_kernel<<<grid_a, STAGE_A_THREADS, 0, stream>>>(prm, st);
-                        if (exh) shadow_beam_kernel<true, true><<<grid_b, BEAM_THREADS, bsmem, stream>>>(prm, st);
-                        else shadow_beam_kernel<false, true><<<grid_b, BEAM_THREADS, bsmem, stream>>>(prm, st);
-                    }
-                    ORE_CUDA(ctx, cudaGetLastError());
-                    ctx->last_launches += (c + 1 < n_chunks) ? 2 : 1;  // the common tail below counts one
+                    (void)cudaGetLastError();  // no room for the staging buffer: the fused sweep needs none
+                    ctx->stage = nullptr;
+                    staged = false;
                 }
             }
-        } else if (!(fr->flags & ORE_FLAG_PER_RAY_SHADOW)) {
-            if (exh) {
-                if ((rc = grid_for(ctx, shadow_cone_kernel<true>, smem, &grid))) return rc;
-                shadow_cone_kernel<true><<<grid, CTA_THREADS, smem, stream>>>(prm);
-            } else {
-                if ((rc = grid_for(ctx, shadow_cone_kernel<false>, smem, &grid))) return rc;
-                shadow_cone_kernel<false><<<grid, CTA_THREADS, smem, stream>>>(prm);
-            }
-        } else if (nl == 3) {
-            if (exh) ORE_LAUNCH_SHADOW(3, true); else ORE_LAUNCH_SHADOW(3, false);
-        } else if (nl == 2) {
-            if (exh) ORE_LAUNCH_SHADOW(2, true); else ORE_LAUNCH_SHADOW(2, false);
-        } else {
-            if (exh) ORE_LAUNCH_SHADOW(1, true); else ORE_LAUNCH_SHADOW(1, false);
         }
-#undef ORE_LAUNCH_SHADOW
-        ORE_CUDA(ctx, cudaGetLastError());
-        ctx->last_launches++;
+        if (!staged) {
+            if ((rc = launch_sweep(ctx, prm, st, false, exh, fast_libm, stream))) return rc;
+            ctx->last_launches++;
+        } else {
+            st.buf = ctx->stage;
+            st.cap_blocks = (uint32_t)cap_blocks;
+            const int n_chunks_max = (int)((n_blocks_px + cap_blocks - 1) / cap_blocks);
+            int n_chunks = n_chunks_max;
+            if (ctx->hits_hint_set) {
+                // previous frame's hit count + 25 % + 64 K items; the catch-all below covers a wrong guess
+                const unsigned long long h = *(volatile unsigned long long*)ctx->hits_hint;
+                const unsigned long long est_blocks = (h + h / 4 + 65536ull + 31ull) / 32ull;
+                const unsigned long long want = (est_blocks + cap_blocks - 1) / cap_blocks;
+                if (want < (unsigned long long)n_chunks_max) n_chunks = want < 1 ? 1 : (int)want;
+            }
+            int grid_a = 0;
+            if (!fast_libm && (rc = grid_for(ctx, shade_setup_kernel, 0, &grid_a, STAGE_A_THREADS))) return rc;
+            if (n_chunks < n_chunks_max) {
+                // catch-all: hit-list blocks beyond the staged chunks (normally none: exits at once), one fused launch
+                StageArgs rest{};
+                rest.first_block = (uint32_t)((size_t)n_chunks * cap_blocks);
+                rest.nv = st.nv;
+                if ((rc = launch_sweep(ctx, prm, rest, false, exh, fast_libm, stream))) return rc;
+                ctx->last_launches++;
+            }
+            for (int c = 0; c < n_chunks; c++) {
+                st.chunk = c;
+                st.first_block = (uint32_t)((size_t)c * cap_blocks);
+                if (fast_libm) {
+                    ORE_CUDA(ctx, (cudaError_t)ore_fast_shade_setup(&prm, &st, ctx->sm_count, stream));
+                } else {
+                    shade_setup_kernel<<<grid_a, STAGE_A_THREADS, 0, stream>>>(prm, st);
+                    ORE_CUDA(ctx, cudaGetLastError());
+                }
+                if ((rc = launch_sweep(ctx, prm, st, true, exh, fast_libm, stream))) return rc;
+                ctx->last_launches += 2;
+            }
+        }
     }
     if (timing) ORE_CUDA(ctx, cudaEventRecord(ctx->ev[3], stream));
     // hint for the next frame of this context (see hits_hint): 8 bytes, no synchronisation
@@ -932,6 +912,8 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
     ctx->ev_valid = timing;
     ORE_CUDA(ctx, cudaEventRecord(ctx->ev_done, stream));
     ctx->ev_done_set = true;
+    ctx->last_prm = prm;
+    ctx->last_prm_valid = true;
     return ORE_OK;
 }
 
@@ -1213,10 +1195,21 @@ extern "C" int ore_get_hits(ore_context* ctx, int32_t* hit_id_host, float* hit_t
     ORE_CUDA(ctx, cudaSetDevice(ctx->device));
     ORE_CUDA(ctx, cudaDeviceSynchronize());
     if (ctx->last_px == 0) return ORE_OK;
+    if (!ctx->last_prm_valid) return fail(ctx, ORE_ERR_INVALID, "ore_get_hits: no frame rendered");
+    // the render path keeps compact hit records only; the per-pixel maps are built here, on demand
+    int rc;
+    size_t c1 = ctx->map_cap, c2 = c1;
+    if ((rc = ensure_dev(ctx, &ctx->hit_id_map, &c1, ctx->last_px))) return rc;
+    if ((rc = ensure_dev(ctx, &ctx->hit_t_map, &c2, ctx->last_px))) return rc;
+    ctx->map_cap = std::min(c1, c2);
+    fill_hits_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(ctx->hit_id_map, ctx->hit_t_map, ctx->last_px);
+    expand_hits_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(ctx->last_prm, ctx->hit_id_map, ctx->hit_t_map);
+    ORE_CUDA(ctx, cudaGetLastError());
+    ORE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (hit_id_host)
-        ORE_CUDA(ctx, cudaMemcpy(hit_id_host, ctx->hit_id, ctx->last_px * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        ORE_CUDA(ctx, cudaMemcpy(hit_id_host, ctx->hit_id_map, ctx->last_px * sizeof(int32_t), cudaMemcpyDeviceToHost));
     if (hit_t_host)
-        ORE_CUDA(ctx, cudaMemcpy(hit_t_host, ctx->hit_t, ctx->last_px * sizeof(float), cudaMemcpyDeviceToHost));
+        ORE_CUDA(ctx, cudaMemcpy(hit_t_host, ctx->hit_t_map, ctx->last_px * sizeof(float), cudaMemcpyDeviceToHost));
     return ORE_OK;
 }
 
@@ -1237,6 +1230,8 @@ extern "C" int ore_get_counters(ore_context* ctx, ore_counters* out) {
     out->kernel_launches = ctx->last_launches;
     out->beam_l1 = c[CNT_BEAM_L1];
     out->beam_l2 = c[CNT_BEAM_L2];
+    out->primary_steps = c[CNT_PRIMARY_STEPS];
+    out->sweep_steps = c[CNT_SWEEP_STEPS];
     return ORE_OK;
 }
 

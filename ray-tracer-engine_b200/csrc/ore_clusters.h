@@ -24,14 +24,16 @@ inline bool tame_value(float v) { return std::isfinite(v) && std::fabs(v) < 1e15
 
 // ex / sh: n exact records (cx,cy,cz,radius member) and n shadow records (cx,cy,cz,R').  Outputs: sorted_shadow and
 // sorted_exact with ceil(n/32)*32 entries (the tail repeats the last sphere; the kernels never read index >= n),
-// bounds with ceil(n/32) rounded up to a multiple of 4 entries (centre, radius; padding = zeros).
+// bounds with ceil(n/32) rounded up to a multiple of 4 entries (centre, radius; padding = zeros) - the 32-sphere
+// clusters of round 1, kept for the containment test - and, optionally, the permutation itself.
 inline void build_clusters(const Rec4* ex, const Rec4* sh, int n, std::vector<Rec4>& sorted_shadow,
-                           std::vector<Rec4>& sorted_exact, std::vector<Rec4>& bounds) {
+                           std::vector<Rec4>& sorted_exact, std::vector<Rec4>& bounds, std::vector<int>* sort_index = nullptr) {
     const int n_clu = (n + 31) / 32;
     const size_t n_sort = (size_t)n_clu * 32, n_clu_pad = ((size_t)n_clu + 3) & ~(size_t)3;
     sorted_shadow.assign(n_sort, Rec4{0.f, 0.f, 0.f, 0.f});
     sorted_exact.assign(n_sort, Rec4{0.f, 0.f, 0.f, 0.f});
     bounds.assign(n_clu_pad, Rec4{0.f, 0.f, 0.f, 0.f});
+    if (sort_index) sort_index->assign(n_sort, 0);
     if (n <= 0) return;
 
     // Morton keys (10 bits per axis) over the bounding box of the tame centres
@@ -71,6 +73,7 @@ inline void build_clusters(const Rec4* ex, const Rec4* sh, int n, std::vector<Re
         const int i = order[p < (size_t)n ? p : (size_t)n - 1].second;
         sorted_shadow[p] = sh[i];
         sorted_exact[p] = ex[i];
+        if (sort_index) (*sort_index)[p] = i;   // original index of the sphere at sorted position p
     }
     for (size_t j = 0; j < (size_t)n_clu; j++) {
         const size_t p0 = j * 32, p1 = std::min(p0 + 32, (size_t)n);

@@ -57,18 +57,18 @@ static cudaError_t launch(K kernel, int threads, int sm_count, size_t smem, long
 extern "C" ORE_HIDDEN int ore_fast_primary_tile(const void* prm, int sm_count, size_t smem, long long n_batches, int exh,
                                                cudaStream_t stream) {
     const ore_fast::FrameParams& p = *static_cast<const ore_fast::FrameParams*>(prm);
-    return (int)(exh ? launch(ore_fast::primary_tile_kernel<ore_fast::TILE_P, true>, ore_fast::CTA_THREADS, sm_count, smem, n_batches, stream, p)
-                     : launch(ore_fast::primary_tile_kernel<ore_fast::TILE_P, false>, ore_fast::CTA_THREADS, sm_count, smem, n_batches, stream, p));
+    return (int)(exh ? launch(ore_fast::primary_tile_kernel<ore_fast::TILE_P, true>, ore_fast::PRIMARY_THREADS, sm_count, smem, n_batches, stream, p)
+                     : launch(ore_fast::primary_tile_kernel<ore_fast::TILE_P, false>, ore_fast::PRIMARY_THREADS, sm_count, smem, n_batches, stream, p));
 }
-extern "C" ORE_HIDDEN int ore_fast_shadow_beam(const void* prm, const void* stage, int staged, int sm_count, size_t smem,
-                                              int exh, cudaStream_t stream) {
+extern "C" ORE_HIDDEN int ore_fast_shadow_sweep(const void* prm, const void* stage, int staged, int sm_count, size_t smem,
+                                               int exh, cudaStream_t stream) {
     const ore_fast::FrameParams& p = *static_cast<const ore_fast::FrameParams*>(prm);
     const ore_fast::StageArgs& st = *static_cast<const ore_fast::StageArgs*>(stage);
     if (!staged)
-        return (int)(exh ? launch(ore_fast::shadow_beam_kernel<true, false>, ore_fast::BEAM_THREADS, sm_count, smem, 0, stream, p, st)
-                         : launch(ore_fast::shadow_beam_kernel<false, false>, ore_fast::BEAM_THREADS, sm_count, smem, 0, stream, p, st));
-    return (int)(exh ? launch(ore_fast::shadow_beam_kernel<true, true>, ore_fast::BEAM_THREADS, sm_count, smem, 0, stream, p, st)
-                     : launch(ore_fast::shadow_beam_kernel<false, true>, ore_fast::BEAM_THREADS, sm_count, smem, 0, stream, p, st));
+        return (int)(exh ? launch(ore_fast::shadow_sweep_kernel<true, false>, ore_fast::SWEEP_THREADS, sm_count, smem, 0, stream, p, st)
+                         : launch(ore_fast::shadow_sweep_kernel<false, false>, ore_fast::SWEEP_THREADS, sm_count, smem, 0, stream, p, st));
+    return (int)(exh ? launch(ore_fast::shadow_sweep_kernel<true, true>, ore_fast::SWEEP_THREADS, sm_count, smem, 0, stream, p, st)
+                     : launch(ore_fast::shadow_sweep_kernel<false, true>, ore_fast::SWEEP_THREADS, sm_count, smem, 0, stream, p, st));
 }
 extern "C" ORE_HIDDEN int ore_fast_shade_setup(const void* prm, const void* stage, int sm_count, cudaStream_t stream) {
     const ore_fast::FrameParams& p = *static_cast<const ore_fast::FrameParams*>(prm);

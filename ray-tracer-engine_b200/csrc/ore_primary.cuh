@@ -29,8 +29,8 @@ namespace ore {
 #endif
 constexpr int PRIMARY_THREADS = ORE_PRIMARY_THREADS;
 constexpr int PRIMARY_WARPS = PRIMARY_THREADS / 32;
-constexpr int LEAF_SPHERES = 8;    // ore_clusters.h: LEAF_SPHERES
-constexpr int SUPER_LEAVES = 32;   // ore_clusters.h: SUPER_LEAVES
+constexpr int LEAF_SPHERES = 8;    // = ore_host::LEAF_SPHERES (ore_clusters.h)
+constexpr int SUPER_LEAVES = 32;   // = ore_host::SUPER_LEAVES
 
 // Tile-cone record of a ball (centre c, radius R) seen from the eye O: a pixel tile whose directions
 // lie within `a` of its axis A can only contain a hit if  A.M + cos(a) sv - sin(a) sqrt(LL - sv^2) <= 0  with

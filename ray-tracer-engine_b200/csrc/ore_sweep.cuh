@@ -40,18 +40,6 @@ constexpr int SWEEP_SLOT_FLOATS = 30 * 32;                    // one light's dir
 constexpr int SWEEP_SLOT_BYTES = SWEEP_SLOT_FLOATS * 4;       // 3840
 constexpr size_t SWEEP_SMEM_BYTES = (size_t)SWEEP_WARPS * 2 * SWEEP_SLOT_BYTES + (size_t)SWEEP_WARPS * 2 * 8;
 
-// staging layout (value-major inside a block of 32 items: value v of lane i at (block * nv + v) * 32 + i):
-//   0-2 start, 3-5 texel r,g,b, then per light: 0-2 cone axis, 3 cone min-dot (-1: degenerate), 4 a = N.toL,
-//   5-34 the 30 direction components
-constexpr int STAGE_HEADER = 6;
-constexpr int STAGE_PER_LIGHT = 35;
-constexpr int STAGE_DIRS_AT = 5;
-
-// direction r of a bundle stored with `stride` floats between components (1: contiguous [10][3]; 32: a shared-memory slot)
-__device__ __forceinline__ v3 dir_at(const float* __restrict__ d, int stride, int r) {
-    return mk(d[(3 * r) * stride], d[(3 * r + 1) * stride], d[(3 * r + 2) * stride]);
-}
-
 // one light's warp beam against the ball q = (centre, radius).  Radius >= 1e18 or NaN: always.
 struct Beam {
     float bx, by, bz;   // centroid of the group's origins

@@ -109,3 +109,74 @@ def test_degenerate_layouts(probe):
                np.stack([np.linspace(0, 9, 70), np.zeros(70), np.zeros(70), np.zeros(70)], axis=1).astype(np.float32)):
         ss, xs, cl, n_clu = probe(ex, ex.copy())
         check(ex, ex.copy(), ss, xs, cl, n_clu)
+
+
+# ---- round 2: leaves of 8 spheres and super-clusters of 32 leaves over the same Morton order -----------------------
+
+@pytest.fixture(scope="module")
+def hierarchy(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("clu2") / "libcluster_probe2.so")
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CXX", None)
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", CSRC,
+                           os.path.join(ROOT, "tests", "cluster_probe.cpp"), "-o", out], env=env)
+    lib = C.CDLL(out)
+    fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int)
+    lib.ore_probe_build_hierarchy.argtypes = [fp, fp, C.c_int, fp, ip, fp, fp, C.c_int, C.c_int, C.c_int]
+    lib.ore_probe_build_hierarchy.restype = C.c_int
+
+    def build(ex, sh):
+        n = len(ex)
+        n_sort = max(1, (n + 31) // 32) * 32
+        n_leaf = (n + 7) // 8
+        ss = np.zeros((n_sort, 4), dtype=np.float32)
+        order = np.zeros(n_sort, dtype=np.int32)
+        lv = np.zeros((max(32, (n_leaf + 31) // 32 * 32), 4), dtype=np.float32)
+        sp = np.zeros((max(4, ((n_leaf + 31) // 32 + 3) // 4 * 4), 4), dtype=np.float32)
+        exc = np.ascontiguousarray(ex, dtype=np.float32).reshape(-1, 4) if n else np.zeros((1, 4), dtype=np.float32)
+        shc = np.ascontiguousarray(sh, dtype=np.float32).reshape(-1, 4) if n else np.zeros((1, 4), dtype=np.float32)
+        got = lib.ore_probe_build_hierarchy(exc.ctypes.data_as(fp), shc.ctypes.data_as(fp), n, ss.ctypes.data_as(fp),
+                                            order.ctypes.data_as(ip), lv.ctypes.data_as(fp), sp.ctypes.data_as(fp),
+                                            len(ss), len(lv), len(sp))
+        assert got == n_leaf
+        return ss, order, lv, sp, n_leaf
+
+    return build
+
+
+def contained(members, ball):
+    mem = members.astype(np.float64)
+    tame = np.all(np.isfinite(mem) & (np.abs(mem) < 1e15))
+    c, r = ball[:3].astype(np.float64), float(ball[3])
+    if not tame:
+        return r == np.inf
+    d = np.sqrt(((mem[:, :3] - c) ** 2).sum(axis=1)) + np.abs(mem[:, 3])
+    return bool(np.isfinite(r) and np.all(d <= r))
+
+
+@pytest.mark.parametrize("n", [1, 7, 8, 9, 255, 256, 257, 1024, 5000, 16384])
+def test_leaves_and_super_clusters_contain_their_members(hierarchy, n):
+    rng = np.random.default_rng(n + 1)
+    ex, sh = make(rng, n)
+    if n >= 255:   # a few untame members
+        for k in (3, n // 2, n - 2):
+            sh[k, 0] = ex[k, 0] = np.float32(1e17 if k % 2 else np.inf)
+    ss, order, lv, sp, n_leaf = hierarchy(ex, sh)
+    # the permutation: sorted position p holds original sphere order[p], every sphere exactly once
+    assert sorted(order[:n].tolist()) == list(range(n))
+    assert np.array_equal(ss[:n].view(np.uint32), sh[order[:n]].view(np.uint32))
+    for j in range(n_leaf):
+        assert contained(ss[8 * j:min(8 * j + 8, n)], lv[j]), ("leaf", j)
+    n_sup = (n_leaf + 31) // 32
+    for k in range(n_sup):
+        assert contained(ss[256 * k:min(256 * k + 256, n)], sp[k]), ("super", k)
+    assert np.all(lv[n_leaf:, 3] == -1) and np.all(sp[n_sup:, 3] == -1)   # padding: never touched
+
+
+def test_leaves_are_much_tighter_than_the_round1_clusters(hierarchy, probe):
+    rng = np.random.default_rng(5)
+    ex, sh = make(rng, 1024, extent=25.0)
+    ss, order, lv, sp, n_leaf = hierarchy(ex, sh)
+    _, _, cl, n_clu = probe(ex, sh)
+    assert np.mean(lv[:n_leaf, 3]) < 0.72 * np.mean(cl[:n_clu, 3])

@@ -52,8 +52,7 @@ def test_default_equals_exhaustive_on_random_scenes(seed, renderer, pkg):
     F = pkg.capi
     a = renderer.render(cam, W, H)
     ia, ta = renderer.hits(H, W)
-    for flags in (F.ORE_FLAG_EXHAUSTIVE, F.ORE_FLAG_NO_WARP_CULL, F.ORE_FLAG_PER_RAY_SHADOW,
-                  F.ORE_FLAG_PER_RAY_SHADOW | F.ORE_FLAG_EXHAUSTIVE, F.ORE_FLAG_FUSED_SHADOW):
+    for flags in (F.ORE_FLAG_EXHAUSTIVE, F.ORE_FLAG_FUSED_SHADOW, F.ORE_FLAG_FUSED_SHADOW | F.ORE_FLAG_EXHAUSTIVE):
         b = renderer.render(cam, W, H, flags=flags)
         ib, tb = renderer.hits(H, W)
         assert np.array_equal(ia, ib), (seed, flags)

@@ -13,7 +13,7 @@ for n, seed, W, H in ((64, 2, 161, 91), (1024, 3, 96, 54), (7000, 7, 48, 27), (0
     sc = pkg.scene.scaled_scene(n, seed) if n else pkg.scene.reference_scene(0, 1)
     cam = pkg.scene.orbit_camera(sc, 11) if n else pkg.scene.reference_camera()
     r.set_scene(sc)
-    for flags in (0, F.ORE_FLAG_NO_WARP_CULL, F.ORE_FLAG_PER_RAY_SHADOW, F.ORE_FLAG_COUNT_REFERENCE_TESTS):
+    for flags in (0, F.ORE_FLAG_FUSED_SHADOW, F.ORE_FLAG_EXHAUSTIVE, F.ORE_FLAG_COUNT_REFERENCE_TESTS):
         px = r.render(cam, W, H, flags=flags)
         r.render(cam, W, H, y0=3, y1=H, y_step=4, flags=flags)
     print(n, W, H, int(px.sum()), flush=True)
