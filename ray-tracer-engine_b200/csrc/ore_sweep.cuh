@@ -138,25 +138,11 @@ __global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_CTAS) shadow_sweep_ke
         }
         float fr = 0.f, fg = 0.f, fb = 0.f;
 
-        // lanes are processed in groups that hit the SAME primitive (the hit list is grouped that way, so a warp normally
-        // is one group; a warp straddling a silhouette is two or three): origins on one sphere give a narrow beam.
-        // At most 4 groups; the last one takes every lane that is left.
-        uint32_t gmask[4] = {0u, 0u, 0u, 0u};
-        int n_groups = 0;
-        {
-            uint32_t pending = __ballot_sync(0xffffffffu, valid);
-#pragma unroll
-            for (int g = 0; g < 4; g++) {
-                if (pending) {
-                    const int leader = __ffs(pending) - 1;
-                    const int gid = __shfl_sync(0xffffffffu, my_id, leader);
-                    const bool ing = ((pending >> lane) & 1u) && (g == 3 || my_id == gid);
-                    gmask[g] = __ballot_sync(0xffffffffu, ing);
-                    pending &= ~gmask[g];
-                    n_groups = g + 1;
-                }
-            }
-        }
+        // Lanes are processed in groups that hit the SAME primitive (the hit list is grouped that way, so a warp normally
+        // is one group; a warp straddling a silhouette is two or three): origins on one sphere give a narrow beam.  There
+        // is no cap on the number of groups: lumping the leftovers of a block that straddles two distant tiles into one
+        // group makes a beam as wide as the scene, which opens every leaf (measured: blocks of 4.7 ms at 16384 spheres).
+        const uint32_t valid_mask = __ballot_sync(0xffffffffu, valid);
 
 #pragma unroll 1
         for (int li = 0; li < NLI; li++) {
@@ -219,10 +205,13 @@ __global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_CTAS) shadow_sweep_ke
                 }
             }
 
+            uint32_t pending = valid_mask;
 #pragma unroll 1
-            for (int g = 0; g < n_groups; g++) {
-                const uint32_t gm = gmask[g];
-                const bool ing = (gm >> lane) & 1u;
+            while (pending) {
+                const int gid = __shfl_sync(0xffffffffu, my_id, __ffs(pending) - 1);
+                const bool ing = ((pending >> lane) & 1u) && my_id == gid;
+                const uint32_t gm = __ballot_sync(0xffffffffu, ing);
+                pending &= ~gm;
                 // ---- warp beam of this group and light: an axis line through the origins' centroid; the group's rays
                 //      stay within rho_perp + (axial distance) * tan(a) of it ----
                 Beam bm;

@@ -27,7 +27,8 @@ def main():
     for f in range(a.frames):
         r.render(camera(f), W, H, out=out, flags=a.flags)
         c = r.counters()
-        print(f, [round(v, 3) for v in r.kernel_ms()[:3]], c["hit_pixels"], "L1/warp", round(c["beam_l1"] / max(1, c["hit_pixels"] / 32), 1), "L2/px", round(c["beam_l2"] / max(1, c["hit_pixels"]), 2), "exactS/px", round(c["exact_shadow"] / max(1, c["hit_pixels"]), 1), "exactP/px", round(c["exact_primary"] / c["pixels"], 2), flush=True)
+        print(f, [round(v, 3) for v in r.kernel_ms()[:3]], c["hit_pixels"], "L1/warp", round(c["beam_l1"] / max(1, c["hit_pixels"] / 32), 1), "L2/px", round(c["beam_l2"] / max(1, c["hit_pixels"]), 2), "exactS/px", round(c["exact_shadow"] / max(1, c["hit_pixels"]), 1), "exactP/px", round(c["exact_primary"] / c["pixels"], 2),
+              "sweep steps/blk", round(c["sweep_steps"] / max(1, c["hit_pixels"] / 32), 1), "primary steps/tile", round(c["primary_steps"] / max(1, c["pixels"] / 256), 1), flush=True)
         frames.append(dict(c, kernel_ms=r.kernel_ms()))
     if a.json:
         import json
