@@ -828,24 +828,43 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
     }
     if (timing) ORE_CUDA(ctx, cudaEventRecord(ctx->ev[2], stream));
     {
-        // Two-stage pass (default): shade_setup_kernel -> staging buffer -> staged shadow_sweep_kernel, in chunks of the
-        // hit list that fit the staging buffer.  The host does not know the hit count (no sync): the first frame of a
-        // context sizes the chunk count from the pixel count, later frames from the previous frame's hit count (a hint
-        // read without synchronisation), and one catch-all launch of the fused sweep takes whatever lies beyond.
+        // Two-stage pass (default): shade_setup_kernel -> staging buffer -> staged shadow_sweep_kernel.  The host does
+        // not know the hit count (no sync): the first frame of a context sizes the staging buffer from the pixel count,
+        // later frames from the previous frame's hit count (a hint read without synchronisation) - normally ONE chunk
+        // pair per frame -, and one catch-all launch of the fused sweep takes whatever lies beyond the staged chunks.
+        // With no lights there is nothing to sweep: the primary kernel has already written 0 to every hit pixel.
         StageArgs st{};
         st.nv = STAGE_HEADER + STAGE_PER_LIGHT * ctx->n_lights;
         const size_t n_blocks_px = (n_px + 31) / 32;
-        size_t cap_blocks = 0;
         bool staged = !(fr->flags & ORE_FLAG_FUSED_SHADOW);
-        if (staged) {
-            size_t want_items = n_px / 4 > ((size_t)1 << 20) ? n_px / 4 : ((size_t)1 << 20);
-            if (want_items > ((size_t)16 << 20)) want_items = (size_t)16 << 20;
-            if (want_items > n_px) want_items = n_px;
-            cap_blocks = (want_items + 31) / 32;
-            if (ctx->stage_blocks_override) cap_blocks = ctx->stage_blocks_override;
-            while ((n_blocks_px + cap_blocks - 1) / cap_blocks > (size_t)MAX_STAGE_CHUNKS) cap_blocks *= 2;
+        size_t cap_blocks = 0, est_blocks = n_blocks_px;
+        if (ctx->n_lights == 0) {
+            staged = false;
+        } else if (staged) {
+            size_t est_items;
+            if (ctx->hits_hint_set) {
+                // previous frame's hit count + 12.5 % + 32 K items; the catch-all below covers a wrong guess
+                const unsigned long long h = *(volatile unsigned long long*)ctx->hits_hint;
+                est_items = (size_t)(h + h / 8 + 32768ull);
+            } else {
+                est_items = n_px / 4 > ((size_t)1 << 20) ? n_px / 4 : ((size_t)1 << 20);
+            }
+            if (est_items > n_px) est_items = n_px;
+            est_blocks = (est_items + 31) / 32;
+            const size_t have_blocks = ctx->stage ? ctx->stage_cap / (32 * (size_t)st.nv) : 0;
+            cap_blocks = have_blocks;
+            if (ctx->stage_blocks_override) {
+                cap_blocks = ctx->stage_blocks_override;
+                while ((n_blocks_px + cap_blocks - 1) / cap_blocks > (size_t)MAX_STAGE_CHUNKS) cap_blocks *= 2;
+            } else if (est_blocks > have_blocks) {
+                cap_blocks = est_blocks + est_blocks / 8;   // grow with some slack: reallocations stay rare
+                if (cap_blocks > n_blocks_px) cap_blocks = n_blocks_px;
+            }
+            while ((est_blocks + cap_blocks - 1) / cap_blocks > (size_t)MAX_STAGE_CHUNKS) cap_blocks *= 2;
             const size_t need = cap_blocks * 32 * (size_t)st.nv;
             if (need > ctx->stage_cap || !ctx->stage) {
+                // (an earlier frame of this context may still be reading the old buffer on another stream)
+                if ((rc = wait_last_render(ctx))) return rc;
                 if (ctx->stage) ORE_CUDA(ctx, cudaFree(ctx->stage));
                 ctx->stage = nullptr;
                 ctx->stage_cap = 0;
@@ -858,21 +877,18 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
                 }
             }
         }
-        if (!staged) {
+        if (ctx->n_lights == 0) {
+            // nothing to launch
+        } else if (!staged) {
             if ((rc = launch_sweep(ctx, prm, st, false, exh, fast_libm, stream))) return rc;
             ctx->last_launches++;
         } else {
             st.buf = ctx->stage;
             st.cap_blocks = (uint32_t)cap_blocks;
             const int n_chunks_max = (int)((n_blocks_px + cap_blocks - 1) / cap_blocks);
-            int n_chunks = n_chunks_max;
-            if (ctx->hits_hint_set) {
-                // previous frame's hit count + 25 % + 64 K items; the catch-all below covers a wrong guess
-                const unsigned long long h = *(volatile unsigned long long*)ctx->hits_hint;
-                const unsigned long long est_blocks = (h + h / 4 + 65536ull + 31ull) / 32ull;
-                const unsigned long long want = (est_blocks + cap_blocks - 1) / cap_blocks;
-                if (want < (unsigned long long)n_chunks_max) n_chunks = want < 1 ? 1 : (int)want;
-            }
+            int n_chunks = (int)((est_blocks + cap_blocks - 1) / cap_blocks);
+            if (n_chunks < 1) n_chunks = 1;
+            if (n_chunks > n_chunks_max) n_chunks = n_chunks_max;
             int grid_a = 0;
             if (!fast_libm && (rc = grid_for(ctx, shade_setup_kernel, 0, &grid_a, STAGE_A_THREADS))) return rc;
             if (n_chunks < n_chunks_max) {

@@ -354,11 +354,11 @@ __global__ void __launch_bounds__(PRIMARY_THREADS, ORE_PRIMARY_MIN_CTAS) primary
                     }
                     uint32_t* dst = prm.pixels + out_index(prm, k, x4);
                     if (vec_ok && x4 + 3 < prm.W) {
-                        if (hits4 != 0xFu) *reinterpret_cast<uint4*>(dst) = make_uint4(px[0], px[1], px[2], px[3]);  // 128-bit RGBA store
+                        *reinterpret_cast<uint4*>(dst) = make_uint4(px[0], px[1], px[2], px[3]);  // 128-bit RGBA store
                     } else {
 #pragma unroll
                         for (int j = 0; j < 4; j++)
-                            if (!((hits4 >> j) & 1u) && x4 + j < prm.W) dst[j] = px[j];
+                            if (x4 + j < prm.W) dst[j] = px[j];
                     }
                 }
             }

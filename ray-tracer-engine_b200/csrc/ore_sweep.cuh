@@ -88,6 +88,9 @@ __global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_CTAS) shadow_sweep_ke
         if (lane == 0) {
             const float* src = st.buf + ((size_t)wblk * (size_t)st.nv + (size_t)(STAGE_HEADER + STAGE_PER_LIGHT * light + STAGE_DIRS_AT)) * 32u;
             uint64_t* bar = &bars[seq_issued & 1u];
+            // the slot was read through the generic proxy (by every lane, all done: __syncwarp at the end of the light
+            // that used it) and is now written through the async proxy
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_expect_tx(bar, SWEEP_SLOT_BYTES);
             tma_bulk_g2s(slots + (seq_issued & 1u) * SWEEP_SLOT_FLOATS, src, SWEEP_SLOT_BYTES, bar);
         }
