@@ -212,7 +212,8 @@ def main():
     ap.add_argument("--workload", default="8k1024", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the N = 1 side measurements (4K, primary-only, fast libm, reference kernel)")
-    ap.add_argument("--in-flight", type=int, default=4, help="frames in flight per GPU (contexts/streams used round-robin)")
+    ap.add_argument("--batch", type=int, default=4, help="frames (cameras) per launch set: ore_render_batch_*")
+    ap.add_argument("--in-flight", type=int, default=2, help="batches in flight per GPU (contexts/streams used round-robin)")
     ap.add_argument("--host-buffers", type=int, default=3, help="frames in the shared host ring of the e2e path")
     ap.add_argument("--emulate-world", type=int, default=0,
                     help="tool, single process only: render just the rows rank --emulate-rank of this many ranks would "
@@ -257,6 +258,7 @@ def main():
     F = pkg.capi
     pkg.build.build_library()
     NF = max(1, args.in_flight)
+    KB = max(1, min(8, args.batch))
     ctxs = []
     for _ in range(NF):
         rx = pkg.Renderer(local)
@@ -265,20 +267,27 @@ def main():
     r, stream = ctxs[0]
     present_stream = torch.cuda.Stream(device=local)
     # frame ring on the presenter + completion / ack flags
-    peer = mg.PeerFrame(r, W, H, n_buffers=NF, band_of=(args.emulate_rank, emulate) if emulate else None)
+    peer = mg.PeerFrame(r, W, H, n_buffers=NF * KB, band_of=(args.emulate_rank, emulate) if emulate else None)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def render_step(f, flags=F.ORE_FLAG_NO_KERNEL_TIMING):
-        """device-resident step: this rank's rows of frame f into the presenter's ring, announced by a flag"""
-        rr, st = ctxs[peer.submitted % NF]
-        peer.submit(camera(f), stream=st.cuda_stream, flags=flags, renderer=rr)
-        if rank == 0:
-            # presenter: on the present stream, wait for every rank's rows of the frame, then acknowledge it to all
-            peer.present(present_stream.cuda_stream)
+    n_batches_done = [0]
+
+    def render_steps(f0, n, flags=F.ORE_FLAG_NO_KERNEL_TIMING):
+        """device-resident steps f0 .. f0+n-1: this rank's rows of those frames into the presenter's ring, KB frames per
+        launch set, each batch announced by a flag"""
+        for b0 in range(0, n, KB):
+            kk = min(KB, n - b0)
+            rr, st = ctxs[n_batches_done[0] % NF]
+            n_batches_done[0] += 1
+            peer.submit_batch([camera(f0 + b0 + i) for i in range(kk)], stream=st.cuda_stream, flags=flags, renderer=rr)
+            if rank == 0:
+                # presenter: on the present stream, wait for every rank's rows of each frame, then acknowledge it to all
+                for _ in range(kk):
+                    peer.present(present_stream.cuda_stream)
 
     def join_streams(ev_list=None):
         """make `stream` wait for everything enqueued on the other streams of this rank"""
@@ -293,8 +302,7 @@ def main():
     n_rows_mine = pkg.Renderer.rows(H, **mg.block_band(peer.band_rank, peer.band_world, H))
 
     # warm-up (every context)
-    for f in range(max(args.warmup, 2) * NF):
-        render_step(f)
+    render_steps(0, max(args.warmup, KB) * NF)
     barrier()
     # hit pixels of this rank's band (for the working-set note and the roofline units)
     warm_hits = r.counters()["hit_pixels"]
@@ -311,8 +319,7 @@ def main():
         st.wait_event(ev_start)
     present_stream.wait_event(ev_start)
     t_host0 = time.perf_counter()
-    for i in range(args.steps):
-        render_step(args.warmup + i)   # no host sync, no collective inside the timed region
+    render_steps(args.warmup, args.steps)   # no host sync, no collective inside the timed region
     t_host1 = time.perf_counter()
     join_streams()
     ev_end.record(stream)
@@ -329,15 +336,20 @@ def main():
     # ---- per-kernel device times (CUDA events inside the library, on the launching stream): separate untimed
     # ---- pass, one frame at a time
     kernel_ms = []
+    launches_per_batch = 0
     for i in range(min(args.steps, 8)):
-        render_step(args.warmup + i, flags=0)
+        render_steps(args.warmup + i, 1, flags=0)      # single frames: per-FRAME kernel times
         torch.cuda.synchronize()
-        kernel_ms.append(ctxs[(peer.submitted - 1) % NF][0].kernel_ms())
-    launches_per_frame = int(ctxs[(peer.submitted - 1) % NF][0].counters()["kernel_launches"])
+        rr = ctxs[(n_batches_done[0] - 1) % NF][0]
+        kernel_ms.append(rr.kernel_ms())
+    render_steps(args.warmup, KB, flags=0)
+    torch.cuda.synchronize()
+    launches_per_batch = int(ctxs[(n_batches_done[0] - 1) % NF][0].counters()["kernel_launches"])
+    launches_per_frame = launches_per_batch / KB
     barrier()
 
     # ---- e2e: ONE shared pinned host frame ring, every rank copies its own rows over its own PCIe link ----------
-    NHB = max(2, args.host_buffers)
+    NHB = max(2 * KB, args.host_buffers)
     name = [None]
     shared = None
     if rank == 0:
@@ -372,13 +384,15 @@ def main():
         if timed:
             e0 = torch.cuda.Event(enable_timing=True)
             e0.record(render_stream)
-        for i in range(n_frames):
-            while not shared.can_submit():       # ring full: wait for the presenter (rank 0 keeps presenting meanwhile)
+        for b0 in range(0, n_frames, KB):
+            kk = min(KB, n_frames - b0)
+            while not shared.can_submit_batch(kk):   # ring full: wait for the presenter (rank 0 keeps presenting meanwhile)
                 e2e_drain(target, False)
-            g, buf = shared.next_slot()
-            r.render_async(camera(first_cam + i), W, H, out=shared.row_addr(buf, band["y0"]), in_place=True,
-                           done_flag=shared.done_addr(shared.rank), done_value=g + 1,
-                           flags=F.ORE_FLAG_NO_KERNEL_TIMING, **band)
+            slots = [shared.next_slot() for _ in range(kk)]
+            r.render_batch_async([camera(first_cam + b0 + i) for i in range(kk)], W, H,
+                                 [shared.row_addr(buf, band["y0"]) for _, buf in slots], in_place=True,
+                                 done_flag=shared.done_addr(shared.rank), first_done_value=slots[0][0] + 1,
+                                 flags=F.ORE_FLAG_NO_KERNEL_TIMING, **band)
             e2e_drain(target, False)
         if timed:
             e1 = torch.cuda.Event(enable_timing=True)
@@ -387,7 +401,7 @@ def main():
         e2e_drain(target, True)                  # presenter: every rank's rows of every frame have landed
         r.wait()
 
-    e2e_run(max(2, NHB), 0, False)
+    e2e_run(2 * KB, 0, False)
     barrier()
     t0 = time.perf_counter()
     e2e_run(args.steps, args.warmup, True)
@@ -489,19 +503,25 @@ def main():
     count_out = peer.ptrs[0]
     if world == 1 and not emulate and not args.no_extras:
         def timed_frames(n, w, h, flags=0, cam0=args.warmup):
+            """ms per frame over n frames, KB frames per launch set like the main measurement (one context, one stream)"""
+            outs = peer.ptrs[:KB]
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            for i in range(3):
-                r.render_device(camera(i), w, h, out_ptr=count_out, stream=stream.cuda_stream, flags=flags | F.ORE_FLAG_NO_KERNEL_TIMING)
+
+            def run(first, count):
+                for b0 in range(0, count, KB):
+                    kk = min(KB, count - b0)
+                    r.render_batch_device([camera(first + b0 + i) for i in range(kk)], w, h, outs[:kk], stream=stream.cuda_stream,
+                                          flags=flags | F.ORE_FLAG_NO_KERNEL_TIMING)
+            run(0, KB)
             stream.synchronize()
             ev0.record(stream)
-            for i in range(n):
-                r.render_device(camera(cam0 + i), w, h, out_ptr=count_out, stream=stream.cuda_stream, flags=flags | F.ORE_FLAG_NO_KERNEL_TIMING)
+            run(cam0, n)
             ev1.record(stream)
             ev1.synchronize()
             return ev0.elapsed_time(ev1) / n
 
         if args.workload == "8k1024":
-            ms4 = timed_frames(10, 3840, 2160)
+            ms4 = timed_frames(12, 3840, 2160)
             kms4 = []
             for i in range(4):
                 r.render_device(camera(args.warmup + i), 3840, 2160, out_ptr=count_out, stream=stream.cuda_stream)
@@ -509,17 +529,17 @@ def main():
                 kms4.append(r.kernel_ms())
             extras["also_configs2_4k1024"] = {
                 "workload": WORKLOADS["4k1024"][5], "value": 3840 * 2160 / ms4 / 1e3, "unit": "Mrays/s", "ms_per_step": ms4,
-                "steps": 10, "kernel_ms": {"prep": statistics.mean(m[0] for m in kms4), "primary": statistics.mean(m[1] for m in kms4),
+                "steps": 12, "kernel_ms": {"prep": statistics.mean(m[0] for m in kms4), "primary": statistics.mean(m[1] for m in kms4),
                                            "shadow": statistics.mean(m[2] for m in kms4)}}
         r.set_lights(sc.lights[:0])
-        po_ms = timed_frames(10, W, H)
+        po_ms = timed_frames(12, W, H)
         r.set_lights(sc.lights)
         po_tf = FLOP_PER_TEST * W * H * sc.n_spheres / (po_ms * 1e-3) / 1e12
         extras["primary_only"] = {"what": "n_lights = 0: primary nearest hit + sky only; reference tests = W*H*N", "ms_per_step": po_ms,
                                   "value": W * H / po_ms / 1e3, "unit": "Mrays/s",
                                   "algorithmic_tflops": po_tf, "algorithmic_speedup_vs_literal": po_tf / peak_tf if peak_tf else None}
-        fl_ms = timed_frames(10, W, H, flags=F.ORE_FLAG_FAST_LIBM)
-        extras["fast_libm"] = {"flag": "ORE_FLAG_FAST_LIBM", "value": W * H / fl_ms / 1e3, "unit": "Mrays/s", "ms_per_step": fl_ms, "steps": 10,
+        fl_ms = timed_frames(12, W, H, flags=F.ORE_FLAG_FAST_LIBM)
+        extras["fast_libm"] = {"flag": "ORE_FLAG_FAST_LIBM", "value": W * H / fl_ms / 1e3, "unit": "Mrays/s", "ms_per_step": fl_ms, "steps": 12,
                                "note": "CUDA's cosf/sinf/acosf/atan2f instead of the glibc-bit-compatible device functions; ids/t "
                                        "unchanged, pixels within 1 LSB on >= 99.9 % instead of bit-identical"}
         if not args.no_cpu_baseline:
@@ -561,8 +581,9 @@ def main():
             "run": {
                 "l2": (f"not flushed at any N (one policy): the inputs a step reads are the 64 KB of scene records the kernels keep "
                        f"in shared memory by design; what it WRITES and re-reads is larger than L2 - per rank and step "
-                       f"{ws_mb:.0f} MB of framebuffer rows, hit records and shadow staging, x {NF} frames in flight, L2 126 MB"),
-                "frame_overlap": f"{NF} frames in flight per GPU (contexts/streams used round-robin), ring of {NF} presenter frames",
+                       f"{ws_mb:.0f} MB of framebuffer rows, hit records and shadow staging, x {NF * KB} frames in flight, L2 126 MB"),
+                "frame_overlap": (f"{KB} frames (cameras) per launch set (ore_render_batch_device / ore_render_batch_async), {NF} launch sets "
+                                  f"in flight per GPU (contexts/streams used round-robin), ring of {NF * KB} presenter frames; the same at every N"),
                 "parallelism": (f"row-bands x{world} (8-row blocks dealt round-robin), presenter = rank 0; rows stored over NVLink into "
                                 f"the presenter's ring; completion = per-rank flags (no collective in the timed region)"
                                 if world > 1 else "1 GPU (same code path: frame ring + flags)"),
@@ -588,8 +609,9 @@ def main():
                             "step is the whole framebuffer in pinned host memory plus a 4-byte counter per rank; "
                             "synchronous_value = ore_render (launch + sync + copy per call, the reference update() semantics, N = 1)",
                     "sharded_frame_check": frame_check},
-            "gpu_launches": launches_per_frame * args.steps,
-            "gpu_launches_per_frame": {"count": launches_per_frame, "kernels": "see DESIGN.md section 4"},
+            "gpu_launches": int(round(launches_per_frame * args.steps)),
+            "gpu_launches_per_frame": {"count": launches_per_frame, "per_launch_set": launches_per_batch, "frames_per_launch_set": KB,
+                                       "kernels": "prep_frame, primary_tile, catch-all sweep (normally empty), shade_setup, shadow_sweep"},
             "roofline": {
                 "bound": "fp32",
                 "kernel": "shadow pass (soft-shadow any-hit + shading; the dominant kernels of the step)",

@@ -171,6 +171,13 @@ int ore_render(ore_context* ctx, const ore_camera* cam, const ore_frame* frame, 
 int ore_render_device(ore_context* ctx, const ore_camera* cam, const ore_frame* frame,
                       uint32_t* out_device, void* stream);
 int ore_synchronize(ore_context* ctx);
+/* A BATCH of frames in one launch set: n_frames (1..8) cameras over the same scene, size and row band, frame f into
+ * out_device[f].  Same pixels as n_frames single calls.  Every kernel of the pass then sees n_frames times the work
+ * units, so launch latencies and the tail of each launch are paid once per batch - what decides throughput when one
+ * rank of a multi-GPU job only holds an eighth of a frame (the reference renders one frame per update(); an orbit or
+ * any scripted camera path can be submitted a few frames at a time).  ore_get_hits needs a single-frame render. */
+int ore_render_batch_device(ore_context* ctx, const ore_camera* cams, int32_t n_frames, const ore_frame* frame,
+                            uint32_t* const* out_device, void* stream);
 
 /* Pipelined presentation (throughput mode of update()): frame f is copied to the host on a second stream
  * while frame f+1 renders into the other of two device framebuffers.  `out_host` should be pinned
@@ -186,6 +193,10 @@ int ore_wait(ore_context* ctx);
  * memory) in stream order AFTER the copy has landed, without blocking the caller. */
 int ore_render_async_signal(ore_context* ctx, const ore_camera* cam, const ore_frame* frame, uint32_t* out_host,
                             uint32_t* done_flag, uint32_t done_value);
+/* The batch form of ore_render_async(_signal): frame f is copied to out_host[f]; when done_flag is not NULL,
+ * first_done_value + f is stored there once frame f's copy has landed (frames land in order). */
+int ore_render_batch_async(ore_context* ctx, const ore_camera* cams, int32_t n_frames, const ore_frame* frame,
+                           uint32_t* const* out_host, uint32_t* done_flag, uint32_t first_done_value);
 /* Pin caller memory (e.g. a POSIX shared-memory frame mapped by every rank) for asynchronous copies and flags. */
 int ore_host_register(ore_context* ctx, void* host_ptr, size_t bytes);
 int ore_host_unregister(ore_context* ctx, void* host_ptr);

@@ -27,7 +27,7 @@ EXPORTS = [
     "ore_render_async", "ore_wait", "ore_host_alloc", "ore_host_free",
     "ore_dev_alloc", "ore_dev_free", "ore_ipc_export", "ore_ipc_import", "ore_ipc_close", "ore_copy_to_host",
     "ore_render_async_signal", "ore_host_register", "ore_host_unregister", "ore_flag_write", "ore_flag_wait_geq",
-    "ore_flag_write_after", "ore_get_stream",
+    "ore_flag_write_after", "ore_get_stream", "ore_render_batch_device", "ore_render_batch_async",
 ]
 
 
@@ -102,6 +102,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.ore_flag_write.argtypes = [vp, vp, vp, C.c_uint32]
     lib.ore_flag_wait_geq.argtypes = [vp, vp, vp, C.c_uint32]
     lib.ore_flag_write_after.argtypes = [vp, vp, vp, C.c_uint32]
+    lib.ore_render_batch_device.argtypes = [vp, C.POINTER(OreCamera), i32, C.POINTER(OreFrame), C.POINTER(vp), vp]
+    lib.ore_render_batch_async.argtypes = [vp, C.POINTER(OreCamera), i32, C.POINTER(OreFrame), C.POINTER(vp), vp, C.c_uint32]
     lib.ore_get_stream.argtypes = [vp, C.c_int]
     lib.ore_get_stream.restype = vp
     for name in EXPORTS:
@@ -249,6 +251,32 @@ class Renderer:
         cam = self._cam(camera)
         self._check(self.lib.ore_render_device(self.ctx, C.byref(cam), C.byref(f), C.c_void_p(out_ptr),
                                                C.c_void_p(stream) if stream else None), "ore_render_device")
+
+    # ---- batches of frames (one launch set for several cameras) ----
+    def _cams(self, cameras):
+        arr = (OreCamera * len(cameras))()
+        for i, c in enumerate(cameras):
+            arr[i] = self._cam(c)
+        return arr
+
+    def render_batch_device(self, cameras, width, height, out_ptrs, stream: int = 0, y0=0, y1=None, y_step=1, aspect=None,
+                            flags=0, out_pitch=0, y_block=1):
+        """frames of `cameras` into the device framebuffers `out_ptrs` (same band arguments for all), one launch set"""
+        assert len(cameras) == len(out_ptrs)
+        f = self._frame(width, height, y0, y1, y_step, aspect, flags, out_pitch, y_block)
+        ptrs = (C.c_void_p * len(out_ptrs))(*[int(p) for p in out_ptrs])
+        self._check(self.lib.ore_render_batch_device(self.ctx, self._cams(cameras), len(cameras), C.byref(f), ptrs,
+                                                     C.c_void_p(stream) if stream else None), "ore_render_batch_device")
+
+    def render_batch_async(self, cameras, width, height, outs, y0=0, y1=None, y_step=1, aspect=None, flags=0, y_block=1,
+                           in_place=False, done_flag: int = 0, first_done_value: int = 0):
+        """pipelined render + device->host copy of a batch; outs: host addresses (int) or numpy arrays, one per frame"""
+        assert len(cameras) == len(outs)
+        f = self._frame(width, height, y0, y1, y_step, aspect, flags, width if in_place else 0, y_block)
+        ptrs = (C.c_void_p * len(outs))(*[(o if isinstance(o, int) else o.ctypes.data) for o in outs])
+        self._check(self.lib.ore_render_batch_async(self.ctx, self._cams(cameras), len(cameras), C.byref(f), ptrs,
+                                                    C.c_void_p(done_flag) if done_flag else None, int(first_done_value)),
+                    "ore_render_batch_async")
 
     # ---- device buffers / IPC (multi-GPU presentation) ----
     def dev_alloc(self, nbytes: int) -> int:

@@ -37,9 +37,13 @@ struct ore_context {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_rendered[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
-    uint32_t* pixels_b = nullptr;  // second device framebuffer (pipelined presentation)
-    size_t pixels_b_cap = 0;
-    unsigned long long async_frames = 0;
+    // device framebuffers of the pipelined presentation: two sets (one being copied out while the other is rendered)
+    // of `async_k` frames of `async_px` pixels each, one allocation
+    uint32_t* async_pool = nullptr;
+    size_t async_pool_cap = 0;   // pixels
+    size_t async_px = 0;
+    int async_k = 0;
+    unsigned long long async_batches = 0;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     bool ev_valid = false;
     bool ran_count = false;
@@ -91,8 +95,8 @@ struct ore_context {
     uint32_t* hit_list = nullptr;  // compact hit records (pixel, id, t), one per hit pixel
     int32_t* hit_ids = nullptr;
     float* hit_ts = nullptr;
-    uint32_t* pixels = nullptr;
-    size_t px_cap = 0;
+    uint32_t* pixels = nullptr;    // the context's own framebuffer (ore_render)
+    size_t px_cap = 0, pixels_cap = 0;
     int32_t* hit_id_map = nullptr;  // per-pixel id / t maps: only built by ore_get_hits
     float* hit_t_map = nullptr;
     size_t map_cap = 0;
@@ -100,6 +104,7 @@ struct ore_context {
     float* stage = nullptr;  // staging buffer between the two kernels of the default shadow pass
     size_t stage_cap = 0;    // floats
     size_t stage_blocks_override = 0;  // test hook (env ORE_STAGE_BLOCKS at ore_create): staging capacity in 32-item blocks
+    size_t stage_max_items = (size_t)8 << 20;  // env ORE_STAGE_MAX_ITEMS: upper bound of the staging buffer in hit pixels
     bool no_memops = false;            // test hook (env ORE_NO_STREAM_MEMOPS=1): flags through the one-thread kernels
     std::string dbg_cycles_path;       // tools hook (env ORE_DEBUG_BLOCK_CYCLES=file): per-block SM clocks of the shadow pass
     uint32_t* dbg_cycles = nullptr;
@@ -128,6 +133,7 @@ struct ore_context {
     unsigned n_signals = 0;
 
     // last frame
+    int last_frames = 1;
     size_t last_px = 0;
     int last_n_spheres = 0;
     uint64_t last_launches = 0;
@@ -211,6 +217,10 @@ extern "C" int ore_create(ore_context** out, int device) {
     ORE_CUDA(ctx, cudaMallocHost((void**)&ctx->hits_hint, sizeof(unsigned long long)));
     *ctx->hits_hint = 0;
     if (const char* e = getenv("ORE_NO_STREAM_MEMOPS")) ctx->no_memops = atoi(e) != 0;
+    if (const char* e = getenv("ORE_STAGE_MAX_ITEMS")) {
+        const long long v = atoll(e);
+        if (v >= 32) ctx->stage_max_items = (size_t)v;
+    }
     if (const char* e = getenv("ORE_DEBUG_BLOCK_CYCLES")) ctx->dbg_cycles_path = e;
     if (const char* e = getenv("ORE_STAGE_BLOCKS")) {
         const long v = atol(e);
@@ -272,7 +282,7 @@ extern "C" int ore_destroy(ore_context* ctx) {
             if (e) cudaEventDestroy(e);
         cudaStreamDestroy(ctx->signal_stream);
     }
-    if (ctx->pixels_b) cudaFree(ctx->pixels_b);
+    if (ctx->async_pool) cudaFree(ctx->async_pool);
     void* dev[] = {ctx->stage, ctx->sph_exact, ctx->sph_xsort, ctx->sph_sort, ctx->sort_index, ctx->leaf_sph, ctx->super_sph,
                    ctx->prim_sorted, ctx->cone_sorted, ctx->leaf_cone, ctx->super_cone, ctx->tex[0], ctx->tex[1], ctx->tex[2],
                    ctx->sky[0], ctx->sky[1], ctx->sky[2], ctx->dx_tab, ctx->dy_tab, ctx->hit_list, ctx->hit_ids, ctx->hit_ts,
@@ -330,17 +340,22 @@ static int upload_spheres(ore_context* ctx, const float* src, size_t stride_floa
     if ((rc = ensure_dev(ctx, &ctx->sph_xsort, &c1, n_sort))) return rc;
     if ((rc = ensure_dev(ctx, &ctx->sph_sort, &c2, n_sort))) return rc;
     if ((rc = ensure_dev(ctx, &ctx->sort_index, &c3, n_sort))) return rc;
-    if ((rc = ensure_dev(ctx, &ctx->prim_sorted, &c4, n_sort))) return rc;
-    if ((rc = ensure_dev(ctx, &ctx->cone_sorted, &c5, n_sort))) return rc;
-    ctx->sort_cap = std::min(std::min(c1, c2), std::min(std::min(c3, c4), c5));
+    // camera-space records: one set per frame of a batch
+    c4 *= MAX_BATCH;
+    c5 *= MAX_BATCH;
+    if ((rc = ensure_dev(ctx, &ctx->prim_sorted, &c4, n_sort * MAX_BATCH))) return rc;
+    if ((rc = ensure_dev(ctx, &ctx->cone_sorted, &c5, n_sort * MAX_BATCH))) return rc;
+    ctx->sort_cap = std::min(std::min(c1, c2), std::min(std::min(c3, c4 / MAX_BATCH), c5 / MAX_BATCH));
     size_t l1 = ctx->leaf_cap, l2 = l1;
     if ((rc = ensure_dev(ctx, &ctx->leaf_sph, &l1, n_leaf_pad))) return rc;
-    if ((rc = ensure_dev(ctx, &ctx->leaf_cone, &l2, n_leaf_pad))) return rc;
-    ctx->leaf_cap = std::min(l1, l2);
+    l2 *= MAX_BATCH;
+    if ((rc = ensure_dev(ctx, &ctx->leaf_cone, &l2, n_leaf_pad * MAX_BATCH))) return rc;
+    ctx->leaf_cap = std::min(l1, l2 / MAX_BATCH);
     size_t s1 = ctx->super_cap, s2 = s1;
     if ((rc = ensure_dev(ctx, &ctx->super_sph, &s1, n_sup_pad))) return rc;
-    if ((rc = ensure_dev(ctx, &ctx->super_cone, &s2, n_sup_pad))) return rc;
-    ctx->super_cap = std::min(s1, s2);
+    s2 *= MAX_BATCH;
+    if ((rc = ensure_dev(ctx, &ctx->super_cone, &s2, n_sup_pad * MAX_BATCH))) return rc;
+    ctx->super_cap = std::min(s1, s2 / MAX_BATCH);
     // pinned staging: the five arrays back to back (16-byte records first), one H2D copy each
     const size_t b_ex = (size_t)std::max(n, 1) * 16, b_sort = n_sort * 16, b_leaf = n_leaf_pad * 16, b_sup = n_sup_pad * 16;
     if ((rc = ensure_pinned(ctx, b_ex + 2 * b_sort + b_leaf + b_sup + n_sort * sizeof(int)))) return rc;
@@ -502,7 +517,7 @@ extern "C" int ore_set_mesh(ore_context* ctx, const float* tris27, int32_t n_tri
     ORE_CUDA(ctx, cudaMalloc((void**)&ctx->box_offsets, ob));
     ORE_CUDA(ctx, cudaMalloc((void**)&ctx->box_indices, ib));
     ORE_CUDA(ctx, cudaMalloc((void**)&ctx->box_sph, sb));
-    ORE_CUDA(ctx, cudaMalloc((void**)&ctx->box_cone, sb));
+    ORE_CUDA(ctx, cudaMalloc((void**)&ctx->box_cone, sb * MAX_BATCH));
     ORE_CUDA(ctx, cudaMemcpyAsync(ctx->box_sph, hs, sb, cudaMemcpyHostToDevice, ctx->stream));
     ORE_CUDA(ctx, cudaMemcpyAsync(ctx->tris, h + off_t, tb, cudaMemcpyHostToDevice, ctx->stream));
     ORE_CUDA(ctx, cudaMemcpyAsync(ctx->boxes, hb, bb, cudaMemcpyHostToDevice, ctx->stream));
@@ -628,10 +643,14 @@ static int launch_sweep(ore_context* ctx, const FrameParams& prm, const StageArg
     return ORE_OK;
 }
 
-static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame* fr, uint32_t* out_device,
+// One launch set for a batch of n_frames cameras.  outs: n_frames device framebuffers, or null (n_frames == 1 only): the
+// context's own framebuffer.
+static int render_impl(ore_context* ctx, const ore_camera* cams, int n_frames, const ore_frame* fr, uint32_t* const* outs,
                        cudaStream_t stream) {
     if (!ctx) return ORE_ERR_INVALID;
-    if (!cam || !fr) return fail(ctx, ORE_ERR_INVALID, "ore_render: null camera/frame");
+    if (!cams || !fr) return fail(ctx, ORE_ERR_INVALID, "ore_render: null camera/frame");
+    if (n_frames < 1 || n_frames > MAX_BATCH || (!outs && n_frames != 1))
+        return fail(ctx, ORE_ERR_INVALID, "ore_render: a batch holds 1..8 frames");
     // a band may be empty (y0 >= y1: a rank with no rows of a short frame) but never reaches past the image
     if (fr->width <= 0 || fr->height <= 0 || fr->y_step <= 0 || fr->y0 < 0 || fr->y1 < 0 || fr->y1 > fr->height ||
         (fr->out_pitch != 0 && fr->out_pitch < fr->width))
@@ -649,9 +668,11 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
     const int yb = fr->y_block > 0 ? fr->y_block : 1;
     if (yb > fr->y_step && fr->y_step != 1) return fail(ctx, ORE_ERR_INVALID, "ore_render: y_block must not exceed y_step");
     const int n_rows = frame_rows(fr);
-    const size_t n_px = (size_t)n_rows * W;
-    if (n_px >= (size_t)1 << 31) return fail(ctx, ORE_ERR_INVALID, "ore_render: band too large");
-    ctx->last_px = n_px;
+    const size_t n_px_frame = (size_t)n_rows * W;
+    const size_t n_px = n_px_frame * (size_t)n_frames;   // pixels of the whole batch
+    if (n_px_frame >= (size_t)1 << 31 || n_px >= ((size_t)1 << 32) - 64) return fail(ctx, ORE_ERR_INVALID, "ore_render: band / batch too large");
+    ctx->last_px = n_px_frame;
+    ctx->last_frames = n_frames;
     ctx->last_n_spheres = ctx->n_spheres;
     ctx->last_launches = 0;
     ctx->ev_valid = false;
@@ -664,12 +685,17 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
     if ((rc = ensure_dev(ctx, &ctx->dx_tab, &ctx->dx_cap, (size_t)W_pad))) return rc;
     if ((rc = ensure_dev(ctx, &ctx->dy_tab, &ctx->dy_cap, (size_t)n_rows))) return rc;
     if (n_px > ctx->px_cap || !ctx->hit_list) {
-        size_t c1 = ctx->hit_list ? ctx->px_cap : 0, c2 = c1, c3 = c1, c4 = c1;
+        if ((rc = wait_last_render(ctx))) return rc;   // (an earlier frame may still be running on another stream)
+        size_t c1 = ctx->hit_list ? ctx->px_cap : 0, c2 = c1, c3 = c1;
         if ((rc = ensure_dev(ctx, &ctx->hit_list, &c1, n_px))) return rc;
         if ((rc = ensure_dev(ctx, &ctx->hit_ids, &c2, n_px))) return rc;
         if ((rc = ensure_dev(ctx, &ctx->hit_ts, &c3, n_px))) return rc;
-        if ((rc = ensure_dev(ctx, &ctx->pixels, &c4, n_px))) return rc;
-        ctx->px_cap = std::min(std::min(c1, c2), std::min(c3, c4));
+        ctx->px_cap = std::min(std::min(c1, c2), c3);
+    }
+    if (!outs && (n_px_frame > ctx->pixels_cap || !ctx->pixels)) {
+        // the context's own framebuffer: only ore_render (one frame, host output) renders into it
+        if ((rc = wait_last_render(ctx))) return rc;
+        if ((rc = ensure_dev(ctx, &ctx->pixels, &ctx->pixels_cap, n_px_frame))) return rc;
     }
 
     FrameParams prm;
@@ -680,8 +706,10 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
     prm.y0 = fr->y0;
     prm.y_step = (yb >= fr->y_step) ? 1 : fr->y_step;
     prm.n_rows = n_rows;
+    prm.n_frames = n_frames;
+    prm.n_px_frame = (uint32_t)n_px_frame;
     prm.y_block = (yb >= fr->y_step) ? 1 : yb;
-    prm.out_global = (out_device && fr->out_pitch > 0) ? 1 : 0;
+    prm.out_global = (outs && fr->out_pitch > 0) ? 1 : 0;
     prm.pitch = prm.out_global ? fr->out_pitch : W;
     prm.n_spheres = ctx->n_spheres;
     prm.n_lights = ctx->n_lights;
@@ -689,17 +717,21 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
     prm.aspect = fr->aspect;
     prm.ez = (-1 / fr->aspect);  // kernel.cu:1629
     prm.fz = 0.f - prm.ez;
-    prm.Ox = 0.f + cam->org[0];  // add(eyePos, cam.Org), kernel.cu:1631
-    prm.Oy = 0.f + cam->org[1];
-    prm.Oz = prm.ez + cam->org[2];
-    {
+    for (int f = 0; f < n_frames; f++) {
+        const ore_camera* cam = &cams[f];
+        CamP& c = prm.cam[f];
+        c.Ox = 0.f + cam->org[0];  // add(eyePos, cam.Org), kernel.cu:1631
+        c.Oy = 0.f + cam->org[1];
+        c.Oz = prm.ez + cam->org[2];
         // camera::rotateDir, kernel.cu:249-255: frame-uniform, evaluated once on the host
         float yawRad = cam->yaw * (3.1415 / 180);
         float pitchRad = cam->pitch * (3.1415 / 180);
-        prm.cp = cosf(pitchRad);
-        prm.sp = sinf(pitchRad);
-        prm.cy = cosf(yawRad);
-        prm.sy = sinf(yawRad);
+        c.cp = cosf(pitchRad);
+        c.sp = sinf(pitchRad);
+        c.cy = cosf(yawRad);
+        c.sy = sinf(yawRad);
+        prm.pixels[f] = outs ? outs[f] : ctx->pixels;
+        if (!prm.pixels[f]) return fail(ctx, ORE_ERR_INVALID, "ore_render: null framebuffer in the batch");
     }
     {
         // largest half-angle of a 32 x TILE_ROWS pixel tile seen from the eye (tile cone of the primary
@@ -777,7 +809,6 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
     prm.hit_ids = ctx->hit_ids;
     prm.hit_ts = ctx->hit_ts;
     prm.counters = ctx->counters;
-    prm.pixels = out_device ? out_device : ctx->pixels;
     if (!ctx->dbg_cycles_path.empty()) {
         const size_t nb = (n_px + 31) / 32;
         if (nb > ctx->dbg_cap) {
@@ -792,10 +823,6 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
     for (int i = 0; i < ctx->n_lights; i++) prm.lights[i] = ctx->lights[i];
 
     const bool timing = !(fr->flags & ORE_FLAG_NO_KERNEL_TIMING);
-    if (!out_device) {
-        // the context's own framebuffer may still be the source of a pipelined device->host copy
-        ORE_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->ev_copied[0], 0));
-    }
     if (timing) ORE_CUDA(ctx, cudaEventRecord(ctx->ev[0], stream));
     {
         int m = W_pad > n_rows ? W_pad : n_rows;
@@ -811,7 +838,7 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
     {
         int grid = 0;
         const long long tiles = (long long)((W + 31) / 32) * ((n_rows + TILE_ROWS - 1) / TILE_ROWS);
-        const long long n_batches = (tiles + PRIMARY_WARPS - 1) / PRIMARY_WARPS;
+        const long long n_batches = ((tiles + PRIMARY_WARPS - 1) / PRIMARY_WARPS) * n_frames;
         if (fast_libm) {
             ORE_CUDA(ctx, (cudaError_t)ore_fast_primary_tile(&prm, ctx->sm_count, psmem, n_batches, exh ? 1 : 0, stream));
         } else if (exh) {
@@ -851,14 +878,18 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
             }
             if (est_items > n_px) est_items = n_px;
             est_blocks = (est_items + 31) / 32;
+            // the staging buffer never grows past stage_max_items (448 bytes each with three lights: 3.6 GB); a longer hit
+            // list - a batch of several 8K frames - is walked in chunk pairs of that size, each a full-size launch
+            const size_t max_blocks = (ctx->stage_max_items + 31) / 32;
             const size_t have_blocks = ctx->stage ? ctx->stage_cap / (32 * (size_t)st.nv) : 0;
             cap_blocks = have_blocks;
             if (ctx->stage_blocks_override) {
                 cap_blocks = ctx->stage_blocks_override;
                 while ((n_blocks_px + cap_blocks - 1) / cap_blocks > (size_t)MAX_STAGE_CHUNKS) cap_blocks *= 2;
-            } else if (est_blocks > have_blocks) {
+            } else if (est_blocks > have_blocks && have_blocks < max_blocks) {
                 cap_blocks = est_blocks + est_blocks / 8;   // grow with some slack: reallocations stay rare
                 if (cap_blocks > n_blocks_px) cap_blocks = n_blocks_px;
+                if (cap_blocks > max_blocks) cap_blocks = max_blocks;
             }
             while ((est_blocks + cap_blocks - 1) / cap_blocks > (size_t)MAX_STAGE_CHUNKS) cap_blocks *= 2;
             const size_t need = cap_blocks * 32 * (size_t)st.nv;
@@ -884,10 +915,12 @@ static int render_impl(ore_context* ctx, const ore_camera* cam, const ore_frame*
             ctx->last_launches++;
         } else {
             st.buf = ctx->stage;
-            st.cap_blocks = (uint32_t)cap_blocks;
-            const int n_chunks_max = (int)((n_blocks_px + cap_blocks - 1) / cap_blocks);
             int n_chunks = (int)((est_blocks + cap_blocks - 1) / cap_blocks);
             if (n_chunks < 1) n_chunks = 1;
+            // equal chunks: the expected hit list is split evenly instead of into full buffers plus a small remainder
+            if (!ctx->stage_blocks_override) cap_blocks = (est_blocks + n_chunks - 1) / n_chunks;
+            st.cap_blocks = (uint32_t)cap_blocks;
+            const int n_chunks_max = (int)((n_blocks_px + cap_blocks - 1) / cap_blocks);
             if (n_chunks > n_chunks_max) n_chunks = n_chunks_max;
             int grid_a = 0;
             if (!fast_libm && (rc = grid_for(ctx, shade_setup_kernel, 0, &grid_a, STAGE_A_THREADS))) return rc;
@@ -937,13 +970,21 @@ extern "C" int ore_render_device(ore_context* ctx, const ore_camera* cam, const 
                                  uint32_t* out_device, void* stream) {
     if (!ctx) return ORE_ERR_INVALID;
     if (!out_device) return fail(ctx, ORE_ERR_INVALID, "ore_render_device: null output");
-    return render_impl(ctx, cam, frame, out_device, stream ? (cudaStream_t)stream : ctx->stream);
+    uint32_t* outs[1] = {out_device};
+    return render_impl(ctx, cam, 1, frame, outs, stream ? (cudaStream_t)stream : ctx->stream);
+}
+
+extern "C" int ore_render_batch_device(ore_context* ctx, const ore_camera* cams, int32_t n_frames, const ore_frame* frame,
+                                       uint32_t* const* out_device, void* stream) {
+    if (!ctx) return ORE_ERR_INVALID;
+    if (!out_device) return fail(ctx, ORE_ERR_INVALID, "ore_render_batch_device: null output");
+    return render_impl(ctx, cams, n_frames, frame, out_device, stream ? (cudaStream_t)stream : ctx->stream);
 }
 
 extern "C" int ore_render(ore_context* ctx, const ore_camera* cam, const ore_frame* frame, uint32_t* out_host) {
     if (!ctx) return ORE_ERR_INVALID;
     if (!out_host) return fail(ctx, ORE_ERR_INVALID, "ore_render: null output");
-    int rc = render_impl(ctx, cam, frame, nullptr, ctx->stream);
+    int rc = render_impl(ctx, cam, 1, frame, nullptr, ctx->stream);
     if (rc) return rc;
     if (ctx->last_px) {
         // device -> host of the band; CUDA stages pageable destinations through its own pinned pool
@@ -1064,74 +1105,81 @@ extern "C" int ore_host_unregister(ore_context* ctx, void* host_ptr) {
     return ORE_OK;
 }
 
-// Pipelined presentation.  The band is rendered into one of two device framebuffers and copied to the host on the
-// copy stream while the next frame renders.  frame->out_pitch == 0: rows packed at out_host.  out_pitch == width:
-// out_host is image row y0 of a FULL host frame and every rendered row lands at its image position (a rank of a
-// multi-GPU job copies its own row blocks into the shared host frame over its own PCIe link).
-static int render_async_impl(ore_context* ctx, const ore_camera* cam, const ore_frame* frame, uint32_t* out_host,
-                             uint32_t* done_flag, uint32_t done_value) {
+// Pipelined presentation.  A batch of frames is rendered into one of two sets of device framebuffers and copied to
+// the host on the copy stream while the next batch renders.  frame->out_pitch == 0: rows packed at out_host[f].
+// out_pitch == width: out_host[f] is image row y0 of a FULL host frame and every rendered row lands at its image
+// position (a rank of a multi-GPU job copies its own row blocks into the shared host frame over its own PCIe link).
+// done_flag (optional): first_value + f is stored there, in stream order, once frame f's copy has landed.
+static int render_async_impl(ore_context* ctx, const ore_camera* cams, int n_frames, const ore_frame* frame,
+                             uint32_t* const* out_host, uint32_t* done_flag, uint32_t first_value) {
     if (!ctx) return ORE_ERR_INVALID;
-    if (!out_host || !frame) return fail(ctx, ORE_ERR_INVALID, "ore_render_async: null output/frame");
+    if (!out_host || !frame || !cams) return fail(ctx, ORE_ERR_INVALID, "ore_render_async: null output/frame");
+    if (n_frames < 1 || n_frames > MAX_BATCH) return fail(ctx, ORE_ERR_INVALID, "ore_render_async: a batch holds 1..8 frames");
+    for (int f = 0; f < n_frames; f++)
+        if (!out_host[f]) return fail(ctx, ORE_ERR_INVALID, "ore_render_async: null host frame in the batch");
     if (frame->out_pitch != 0 && frame->out_pitch != frame->width)
         return fail(ctx, ORE_ERR_INVALID, "ore_render_async: out_pitch must be 0 (packed) or the frame width (rows in place)");
     ORE_CUDA(ctx, cudaSetDevice(ctx->device));
     const int n_rows = frame_rows(frame);
     const size_t W = (size_t)(frame->width > 0 ? frame->width : 0);
     const size_t n_px = (size_t)(n_rows > 0 ? n_rows : 0) * W;
-    const int buf = (int)(ctx->async_frames & 1ull);
+    const int set = (int)(ctx->async_batches & 1ull);
     int rc;
-    // two device framebuffers: the context's own and a second one
-    if (n_px > ctx->pixels_b_cap) {
-        ORE_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
-        if ((rc = ensure_dev(ctx, &ctx->pixels_b, &ctx->pixels_b_cap, n_px))) return rc;
-    }
-    if (n_px > ctx->px_cap || !ctx->pixels) {
-        // let render_impl size the per-frame buffers first (synchronously, once)
-        ORE_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
-        ore_frame probe = *frame;
-        probe.out_pitch = 0;
-        if ((rc = render_impl(ctx, cam, &probe, nullptr, ctx->stream))) return rc;
+    if (n_px != ctx->async_px || n_frames != ctx->async_k || !ctx->async_pool) {
+        // new geometry: the two sets are laid out afresh, so nothing of the old layout may still be in flight
         ORE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ORE_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+        if ((rc = ensure_dev(ctx, &ctx->async_pool, &ctx->async_pool_cap, 2 * (size_t)n_frames * (n_px ? n_px : 1)))) return rc;
+        ctx->async_px = n_px;
+        ctx->async_k = n_frames;
     }
-    uint32_t* target = buf ? ctx->pixels_b : ctx->pixels;
-    // do not overwrite a framebuffer whose previous copy is still in flight
-    ORE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[buf], 0));
+    uint32_t* targets[MAX_BATCH];
+    for (int f = 0; f < n_frames; f++) targets[f] = ctx->async_pool + ((size_t)set * n_frames + f) * n_px;
+    // do not overwrite framebuffers whose previous copy is still in flight
+    ORE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[set], 0));
     ore_frame fr = *frame;
     fr.out_pitch = 0;
-    if ((rc = render_impl(ctx, cam, &fr, target, ctx->stream))) return rc;
-    ORE_CUDA(ctx, cudaEventRecord(ctx->ev_rendered[buf], ctx->stream));
-    ORE_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rendered[buf], 0));
-    if (ctx->last_px) {
-        const int yb = frame->y_block > 0 ? frame->y_block : 1;
-        if (frame->out_pitch == 0 || yb >= frame->y_step) {
-            // packed, or a contiguous band: one linear copy
-            ORE_CUDA(ctx, cudaMemcpyAsync(out_host, target, ctx->last_px * sizeof(uint32_t), cudaMemcpyDeviceToHost,
-                                          ctx->copy_stream));
-        } else {
-            // block-interleaved rows: blocks of yb rows, y_step image rows apart -> one strided copy (+ a ragged tail)
-            const size_t blk_bytes = (size_t)yb * W * sizeof(uint32_t);
-            const size_t full = (size_t)n_rows / yb, rem = (size_t)n_rows % yb;
-            if (full)
-                ORE_CUDA(ctx, cudaMemcpy2DAsync(out_host, (size_t)frame->y_step * W * sizeof(uint32_t), target, blk_bytes,
-                                                blk_bytes, full, cudaMemcpyDeviceToHost, ctx->copy_stream));
-            if (rem)
-                ORE_CUDA(ctx, cudaMemcpyAsync(out_host + full * (size_t)frame->y_step * W, target + full * (size_t)yb * W,
-                                              rem * W * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->copy_stream));
+    if ((rc = render_impl(ctx, cams, n_frames, &fr, targets, ctx->stream))) return rc;
+    ORE_CUDA(ctx, cudaEventRecord(ctx->ev_rendered[set], ctx->stream));
+    ORE_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rendered[set], 0));
+    for (int f = 0; f < n_frames; f++) {
+        if (n_px) {
+            const int yb = frame->y_block > 0 ? frame->y_block : 1;
+            if (frame->out_pitch == 0 || yb >= frame->y_step) {
+                // packed, or a contiguous band: one linear copy
+                ORE_CUDA(ctx, cudaMemcpyAsync(out_host[f], targets[f], n_px * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->copy_stream));
+            } else {
+                // block-interleaved rows: blocks of yb rows, y_step image rows apart -> one strided copy (+ a ragged tail)
+                const size_t blk_bytes = (size_t)yb * W * sizeof(uint32_t);
+                const size_t full = (size_t)n_rows / yb, rem = (size_t)n_rows % yb;
+                if (full)
+                    ORE_CUDA(ctx, cudaMemcpy2DAsync(out_host[f], (size_t)frame->y_step * W * sizeof(uint32_t), targets[f], blk_bytes,
+                                                    blk_bytes, full, cudaMemcpyDeviceToHost, ctx->copy_stream));
+                if (rem)
+                    ORE_CUDA(ctx, cudaMemcpyAsync(out_host[f] + full * (size_t)frame->y_step * W, targets[f] + full * (size_t)yb * W,
+                                                  rem * W * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->copy_stream));
+            }
         }
+        if (done_flag && (rc = ore_flag_write(ctx, ctx->copy_stream, done_flag, first_value + (uint32_t)f))) return rc;
     }
-    ORE_CUDA(ctx, cudaEventRecord(ctx->ev_copied[buf], ctx->copy_stream));
-    ctx->async_frames++;
-    if (done_flag) return ore_flag_write(ctx, ctx->copy_stream, done_flag, done_value);
+    ORE_CUDA(ctx, cudaEventRecord(ctx->ev_copied[set], ctx->copy_stream));
+    ctx->async_batches++;
     return ORE_OK;
 }
 
 extern "C" int ore_render_async(ore_context* ctx, const ore_camera* cam, const ore_frame* frame, uint32_t* out_host) {
-    return render_async_impl(ctx, cam, frame, out_host, nullptr, 0);
+    uint32_t* outs[1] = {out_host};
+    return render_async_impl(ctx, cam, 1, frame, outs, nullptr, 0);
 }
 extern "C" int ore_render_async_signal(ore_context* ctx, const ore_camera* cam, const ore_frame* frame, uint32_t* out_host,
                                        uint32_t* done_flag, uint32_t done_value) {
     if (!done_flag) return fail(ctx, ORE_ERR_INVALID, "ore_render_async_signal: null flag");
-    return render_async_impl(ctx, cam, frame, out_host, done_flag, done_value);
+    uint32_t* outs[1] = {out_host};
+    return render_async_impl(ctx, cam, 1, frame, outs, done_flag, done_value);
+}
+extern "C" int ore_render_batch_async(ore_context* ctx, const ore_camera* cams, int32_t n_frames, const ore_frame* frame,
+                                      uint32_t* const* out_host, uint32_t* done_flag, uint32_t first_done_value) {
+    return render_async_impl(ctx, cams, n_frames, frame, out_host, done_flag, first_done_value);
 }
 
 extern "C" int ore_wait(ore_context* ctx) {
@@ -1212,6 +1260,7 @@ extern "C" int ore_get_hits(ore_context* ctx, int32_t* hit_id_host, float* hit_t
     ORE_CUDA(ctx, cudaDeviceSynchronize());
     if (ctx->last_px == 0) return ORE_OK;
     if (!ctx->last_prm_valid) return fail(ctx, ORE_ERR_INVALID, "ore_get_hits: no frame rendered");
+    if (ctx->last_frames != 1) return fail(ctx, ORE_ERR_INVALID, "ore_get_hits: the last render was a batch (render the frame alone)");
     // the render path keeps compact hit records only; the per-pixel maps are built here, on demand
     int rc;
     size_t c1 = ctx->map_cap, c2 = c1;
@@ -1236,11 +1285,12 @@ extern "C" int ore_get_counters(ore_context* ctx, ore_counters* out) {
     unsigned long long c[CNT_SLOTS];
     ORE_CUDA(ctx, cudaMemcpy(c, ctx->counters, sizeof c, cudaMemcpyDeviceToHost));
     memset(out, 0, sizeof *out);
-    out->pixels = ctx->last_px;
-    out->hit_pixels = ctx->last_px ? c[CNT_HITS] : 0;
-    out->primary_tests = (uint64_t)ctx->last_px * (uint64_t)ctx->last_n_spheres;
+    const uint64_t batch_px = (uint64_t)ctx->last_px * (uint64_t)ctx->last_frames;
+    out->pixels = batch_px;
+    out->hit_pixels = batch_px ? c[CNT_HITS] : 0;
+    out->primary_tests = batch_px * (uint64_t)ctx->last_n_spheres;
     out->shadow_tests_ref = c[CNT_SHADOW_TESTS_REF];
-    out->sky_tests = ctx->last_px ? ctx->last_px - c[CNT_HITS] : 0;
+    out->sky_tests = batch_px ? batch_px - c[CNT_HITS] : 0;
     out->exact_primary = c[CNT_EXACT_PRIMARY];
     out->exact_shadow = c[CNT_EXACT_SHADOW];
     out->kernel_launches = ctx->last_launches;

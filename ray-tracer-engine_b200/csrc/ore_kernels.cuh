@@ -14,6 +14,7 @@
 namespace ore {
 
 constexpr int MAX_LIGHTS = 16;
+constexpr int MAX_BATCH = 8;   // frames (cameras) rendered by one launch set
 constexpr int CTA_THREADS = 256;
 #ifndef ORE_STAGE_A_THREADS
 #define ORE_STAGE_A_THREADS 64   // warp-independent persistent kernel: small CTAs hand an SM back almost warp by warp
@@ -68,8 +69,20 @@ struct LightP {
     float px, py, pz, size, r, g, b;
 };
 
+// camera of one frame of the batch
+struct CamP {
+    float Ox, Oy, Oz;      // add(eyePos, cam.Org), kernel.cu:1631
+    float cp, sp, cy, sy;  // cosf/sinf of pitchRad / yawRad (kernel.cu:249-255), host libm
+};
+
+// One launch set renders n_frames frames (1..MAX_BATCH cameras over the same scene, size and row band): every kernel
+// sees n_frames times the work units, so launch latencies and the tail of each launch are paid once per batch - what
+// matters when a rank of a multi-GPU job only holds an eighth of a frame.  Rendered-pixel indices in the hit list
+// are frame * n_px_frame + k * W + x.
 struct FrameParams {
     int W, H, y0, y_step, n_rows;
+    int n_frames;
+    uint32_t n_px_frame;   // n_rows * W
     int W_pad;       // W rounded up to a multiple of 32 (dx_tab entries)
     int y_block;     // rows come in blocks of y_block consecutive image rows, block starts y_step apart
     int pitch;       // output row pitch in pixels
@@ -77,8 +90,7 @@ struct FrameParams {
     int n_spheres, n_lights;
     uint32_t flags;
     float aspect, ez, fz;  // ez = -1/aspect (kernel.cu:1629), fz = 0 - ez
-    float Ox, Oy, Oz;      // add(eyePos, cam.Org), kernel.cu:1631
-    float cp, sp, cy, sy;  // cosf/sinf of pitchRad / yawRad (kernel.cu:249-255), host libm
+    CamP cam[MAX_BATCH];
     const float* dx_tab;
     const float* dy_tab;
     float tile_ca, tile_sa;   // cos/sin of the largest pixel-tile half-angle (+ margins), host-computed
@@ -92,9 +104,10 @@ struct FrameParams {
     const float4* leaf_sph;   // bounding balls (centre, radius; radius +inf: always a candidate)
     const float4* super_sph;
     int n_sort, n_leaves, n_leaves_pad, n_supers, n_supers_pad;
-    float4* prim_sorted;      // per frame: per-pixel primary filter coefficients a',b',c' (sorted order)
-    float4* cone_sorted;      // per frame: tile-cone record Mx,My,Mz,W of every sphere (sorted order)
-    float4* leaf_cone;        // per frame: tile-cone record of every leaf / super-cluster ball
+    // camera-space records, one set per frame of the batch (frame f at base + f * {n_sort, n_leaves_pad, n_supers_pad})
+    float4* prim_sorted;      // per-pixel primary filter coefficients a',b',c' (sorted order)
+    float4* cone_sorted;      // tile-cone record Mx,My,Mz,W of every sphere (sorted order)
+    float4* leaf_cone;        // tile-cone record of every leaf / super-cluster ball
     float4* super_cone;
     int cone_resident;        // the sphere-level cone records fit in the primary kernel's shared memory
     const float *tex_r, *tex_g, *tex_b;
@@ -103,11 +116,11 @@ struct FrameParams {
     int sky_w, sky_h;
     float sky_radius;  // skybox sphere member = size*size (kernel.cu:287,1122)
     // compact hit records, in hit-list order (nothing is stored for miss pixels)
-    uint32_t* hit_list;   // rendered-pixel index k * W + x
+    uint32_t* hit_list;   // rendered-pixel index frame * n_px_frame + k * W + x
     int32_t* hit_ids;     // nearest primitive
     float* hit_ts;        // nearest t
     unsigned long long* counters;
-    uint32_t* pixels;
+    uint32_t* pixels[MAX_BATCH];   // one framebuffer per frame of the batch
     // "next" primitives (kernel.cu:360-509): cube i = 3 float4 {bounds[0], bounds[1], orgin}, plane i = 2 float4
     // {orgin, normal}; hit ids continue after the spheres: cube i -> n_spheres + i, plane i -> n_spheres + n_cubes + i
     const float4* cubes;
@@ -119,7 +132,7 @@ struct FrameParams {
     const float* tris;
     const float4* boxes;
     const float4* box_sph;    // bounding sphere of each leaf box (centre, radius incl. margin) for the cone filters
-    float4* box_cone;         // per-frame tile-cone record of each leaf box (camera frame)
+    float4* box_cone;         // tile-cone record of each leaf box (camera frame; frame f at base + f * n_boxes)
     const int* box_offsets;
     const int* box_indices;
     int n_tris, n_boxes, mesh_has_normals;
@@ -141,15 +154,22 @@ __constant__ float c_b_of_k[11];
 // ------------------------------------------------------------------------------------
 // primary ray of pixel (x, row k): kernel.cu:1624-1631 with dx/dy from the tables
 // ------------------------------------------------------------------------------------
-__device__ __forceinline__ v3 primary_dir(const FrameParams& prm, float dx, float dy) {
-    v3 v = mk(dx - 0.f, dy - 0.f, 0.f - prm.ez);  // sub(dir, eyePos)
+__device__ __forceinline__ v3 primary_dir(const CamP& c, float ez, float dx, float dy) {
+    v3 v = mk(dx - 0.f, dy - 0.f, 0.f - ez);  // sub(dir, eyePos)
     v3 n = ref_normalise(v);
     // camera::rotateDir, kernel.cu:252-255
-    float y = n.y * prm.cp - n.z * prm.sp;
-    float z = n.y * prm.sp + n.z * prm.cp;
-    float x = n.x * prm.cy + z * prm.sy;
-    z = -n.x * prm.sy + z * prm.cy;
+    float y = n.y * c.cp - n.z * c.sp;
+    float z = n.y * c.sp + n.z * c.cp;
+    float x = n.x * c.cy + z * c.sy;
+    z = -n.x * c.sy + z * c.cy;
     return mk(x, y, z);
+}
+// frame and in-frame pixel of a hit-list entry
+__device__ __forceinline__ void split_pixel(const FrameParams& prm, uint32_t o, int& frame, int& k, int& x) {
+    frame = (int)(o / prm.n_px_frame);
+    const uint32_t r = o - (uint32_t)frame * prm.n_px_frame;
+    k = (int)(r / (uint32_t)prm.W);
+    x = (int)(r - (uint32_t)k * (uint32_t)prm.W);
 }
 
 __device__ __forceinline__ int clamp_index(int idx, int n) { return idx < 0 ? 0 : (idx >= n ? n - 1 : idx); }
@@ -443,12 +463,15 @@ __device__ __noinline__ float4 cone_of10(const float* __restrict__ d /* 32 float
 // shade_point: the shading set-up of one hit pixel (kernel.cu:1380-1425, 1643-1655): hit point, normal, shadow-ray
 // origin `start`, texel colour.  `item` indexes the hit list.
 // ------------------------------------------------------------------------------------
-__device__ __forceinline__ void shade_point(const FrameParams& prm, uint32_t item, const v3 O0, size_t& o_out, int& my_id,
+__device__ __forceinline__ void shade_point(const FrameParams& prm, uint32_t item, uint32_t*& out_px, int& my_id,
                                             v3& start, v3& normal, float& tr, float& tg, float& tb) {
     const uint32_t o = prm.hit_list[item];
-    const int k = (int)(o / (uint32_t)prm.W), x = (int)(o % (uint32_t)prm.W);
-    o_out = out_index(prm, k, x);
-    const v3 D = primary_dir(prm, prm.dx_tab[x], prm.dy_tab[k]);
+    int frame, k, x;
+    split_pixel(prm, o, frame, k, x);
+    out_px = prm.pixels[frame] + out_index(prm, k, x);
+    const CamP cam = prm.cam[frame];
+    const v3 O0 = mk(cam.Ox, cam.Oy, cam.Oz);
+    const v3 D = primary_dir(cam, prm.ez, prm.dx_tab[x], prm.dy_tab[k]);
     const float nt = prm.hit_ts[item];
     my_id = prm.hit_ids[item];
     v3 new_org = ref_add(O0, ref_scale(D, nt));
@@ -495,7 +518,6 @@ __device__ __forceinline__ void shade_point(const FrameParams& prm, uint32_t ite
 __global__ void __launch_bounds__(STAGE_A_THREADS, ORE_STAGE_A_MIN_CTAS) shade_setup_kernel(const FrameParams prm, const StageArgs st) {
     const int lane = threadIdx.x & 31;
     const uint32_t n_items = (uint32_t)prm.counters[CNT_HITS];
-    const v3 O0 = mk(prm.Ox, prm.Oy, prm.Oz);
     for (;;) {
         uint32_t wb = 0;
         if (lane == 0) wb = (uint32_t)atomicAdd(&prm.counters[CNT_STAGE_A0 + st.chunk], 1ull);
@@ -506,11 +528,11 @@ __global__ void __launch_bounds__(STAGE_A_THREADS, ORE_STAGE_A_MIN_CTAS) shade_s
         const uint32_t item = blk * 32u + lane;
         const bool valid = item < n_items;
         const long long dbg_t0 = prm.dbg_cycles ? clock64() : 0;
-        size_t o_out = 0;
+        uint32_t* out_px = nullptr;
         int my_id = -1;
         v3 start = mk(1e9f, 1e9f, 1e9f), normal = mk(0.f, 0.f, 0.f);
         float tr = 0.f, tg = 0.f, tb = 0.f;
-        if (valid) shade_point(prm, item, O0, o_out, my_id, start, normal, tr, tg, tb);
+        if (valid) shade_point(prm, item, out_px, my_id, start, normal, tr, tg, tb);
         float* __restrict__ sp = st.buf + ((size_t)wb * (size_t)st.nv) * 32u + lane;
         sp[0] = start.x;
         sp[32] = start.y;
@@ -571,7 +593,6 @@ namespace ore {
 __global__ void __launch_bounds__(CTA_THREADS) count_reference_tests_kernel(const FrameParams prm) {
     const uint32_t n_items = (uint32_t)prm.counters[CNT_HITS];
     const unsigned long long total = (unsigned long long)n_items * (unsigned long long)prm.n_lights;
-    const v3 O0 = mk(prm.Ox, prm.Oy, prm.Oz);
     unsigned long long mine = 0;
     for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < total;
          w += (unsigned long long)gridDim.x * blockDim.x) {
@@ -580,8 +601,11 @@ __global__ void __launch_bounds__(CTA_THREADS) count_reference_tests_kernel(cons
         const int id = prm.hit_ids[item];
         if (id >= prm.n_spheres) continue;   // the count is defined for sphere scenes
         const uint32_t o = prm.hit_list[item];
-        const int k = (int)(o / (uint32_t)prm.W), x = (int)(o % (uint32_t)prm.W);
-        const v3 D = primary_dir(prm, prm.dx_tab[x], prm.dy_tab[k]);
+        int frame, k, x;
+        split_pixel(prm, o, frame, k, x);
+        const CamP cam = prm.cam[frame];
+        const v3 O0 = mk(cam.Ox, cam.Oy, cam.Oz);
+        const v3 D = primary_dir(cam, prm.ez, prm.dx_tab[x], prm.dy_tab[k]);
         const float nt = prm.hit_ts[item];
         const float4 sc = __ldg(&prm.sph_exact[id]);
         const v3 new_org = ref_add(O0, ref_scale(D, nt));

@@ -35,8 +35,8 @@ constexpr int SUPER_LEAVES = 32;   // = ore_host::SUPER_LEAVES
 // Tile-cone record of a ball (centre c, radius R) seen from the eye O: a pixel tile whose directions
 // lie within `a` of its axis A can only contain a hit if  A.M + cos(a) sv - sin(a) sqrt(LL - sv^2) <= 0  with
 // M = R^T (O - c), sv = sqrt(Cm).  r2 = R^2 (already including the caller's margin).
-__device__ __forceinline__ void ball_records(const FrameParams& prm, double Lx, double Ly, double Lz, double r2, float4* prim,
-                                             float4* cone) {
+__device__ __forceinline__ void ball_records(const FrameParams& prm, const CamP& cam, double Lx, double Ly, double Lz, double r2,
+                                             float4* prim, float4* cone) {
     const double LL = Lx * Lx + Ly * Ly + Lz * Lz;
     const double Cm = LL * (1.0 - ORE_KAPPA_PRIMARY) - r2 * (1.0 + ORE_KAPPA_PRIMARY);
     if (!(Cm > 1e-9 * LL) || !(Cm > 1e-30)) {
@@ -46,7 +46,7 @@ __device__ __forceinline__ void ball_records(const FrameParams& prm, double Lx, 
         return;
     }
     const double sv = sqrt(Cm);
-    const double cp = prm.cp, sp = prm.sp, cy = prm.cy, sy = prm.sy;
+    const double cp = cam.cp, sp = cam.sp, cy = cam.cy, sy = cam.sy;
     const double Mx = cy * Lx - sy * Lz;
     const double My = sp * sy * Lx + cp * Ly + sp * cy * Lz;
     const double Mz = cp * sy * Lx - sp * Ly + cp * cy * Lz;
@@ -71,40 +71,44 @@ __global__ void prep_frame_kernel(const FrameParams prm) {
         double v = (double)prm.aspect * (2 * (y + 0.5) / (double)(float)prm.H) * (double)hw - 1;
         const_cast<float*>(prm.dy_tab)[i] = (float)v;
     }
-    if (i < prm.n_sort) {
-        // sphere at sorted position i (positions >= n_spheres are padding: never a candidate)
-        float4 out = make_float4(0.f, 0.f, ORE_BIG, 0.f);
-        float4 cone = make_float4(0.f, 0.f, 0.f, ORE_BIG);
-        if (i < prm.n_spheres) {
-            const float4 s = prm.sph_xsort[i];
-            // L exactly as the reference forms it (float), then the filter works in double
-            ball_records(prm, (double)(prm.Ox - s.x), (double)(prm.Oy - s.y), (double)(prm.Oz - s.z), (double)(s.w * s.w), &out, &cone);
+    // camera-space records: one set per frame of the batch
+    for (int f = 0; f < prm.n_frames; f++) {
+        const CamP cam = prm.cam[f];
+        if (i < prm.n_sort) {
+            // sphere at sorted position i (positions >= n_spheres are padding: never a candidate)
+            float4 out = make_float4(0.f, 0.f, ORE_BIG, 0.f);
+            float4 cone = make_float4(0.f, 0.f, 0.f, ORE_BIG);
+            if (i < prm.n_spheres) {
+                const float4 s = prm.sph_xsort[i];
+                // L exactly as the reference forms it (float), then the filter works in double
+                ball_records(prm, cam, (double)(cam.Ox - s.x), (double)(cam.Oy - s.y), (double)(cam.Oz - s.z), (double)(s.w * s.w), &out, &cone);
+            }
+            prm.prim_sorted[(size_t)f * prm.n_sort + i] = out;
+            prm.cone_sorted[(size_t)f * prm.n_sort + i] = cone;
         }
-        prm.prim_sorted[i] = out;
-        prm.cone_sorted[i] = cone;
-    }
-    if (i < prm.n_leaves_pad) {
-        float4 cone = make_float4(0.f, 0.f, 0.f, ORE_BIG);
-        if (i < prm.n_leaves) {
-            const float4 q = prm.leaf_sph[i];
-            ball_records(prm, (double)prm.Ox - q.x, (double)prm.Oy - q.y, (double)prm.Oz - q.z, (double)q.w * q.w, nullptr, &cone);
+        if (i < prm.n_leaves_pad) {
+            float4 cone = make_float4(0.f, 0.f, 0.f, ORE_BIG);
+            if (i < prm.n_leaves) {
+                const float4 q = prm.leaf_sph[i];
+                ball_records(prm, cam, (double)cam.Ox - q.x, (double)cam.Oy - q.y, (double)cam.Oz - q.z, (double)q.w * q.w, nullptr, &cone);
+            }
+            prm.leaf_cone[(size_t)f * prm.n_leaves_pad + i] = cone;
         }
-        prm.leaf_cone[i] = cone;
-    }
-    if (i < prm.n_supers_pad) {
-        float4 cone = make_float4(0.f, 0.f, 0.f, ORE_BIG);
-        if (i < prm.n_supers) {
-            const float4 q = prm.super_sph[i];
-            ball_records(prm, (double)prm.Ox - q.x, (double)prm.Oy - q.y, (double)prm.Oz - q.z, (double)q.w * q.w, nullptr, &cone);
+        if (i < prm.n_supers_pad) {
+            float4 cone = make_float4(0.f, 0.f, 0.f, ORE_BIG);
+            if (i < prm.n_supers) {
+                const float4 q = prm.super_sph[i];
+                ball_records(prm, cam, (double)cam.Ox - q.x, (double)cam.Oy - q.y, (double)cam.Oz - q.z, (double)q.w * q.w, nullptr, &cone);
+            }
+            prm.super_cone[(size_t)f * prm.n_supers_pad + i] = cone;
         }
-        prm.super_cone[i] = cone;
-    }
-    if (i < prm.n_boxes) {
-        // tile-cone record of leaf box i of the mesh from its bounding sphere (same formula)
-        const float4 q = prm.box_sph[i];
-        float4 rec;
-        ball_records(prm, (double)prm.Ox - q.x, (double)prm.Oy - q.y, (double)prm.Oz - q.z, (double)q.w * q.w, nullptr, &rec);
-        prm.box_cone[i] = rec;
+        if (i < prm.n_boxes) {
+            // tile-cone record of leaf box i of the mesh from its bounding sphere (same formula)
+            const float4 q = prm.box_sph[i];
+            float4 rec;
+            ball_records(prm, cam, (double)cam.Ox - q.x, (double)cam.Oy - q.y, (double)cam.Oz - q.z, (double)q.w * q.w, nullptr, &rec);
+            prm.box_cone[(size_t)f * prm.n_boxes + i] = rec;
+        }
     }
 }
 
@@ -113,18 +117,12 @@ struct SkyArgs {
     const float *r, *g, *b;
     int w, h;
     float radius;
-    float Ox, Oy, Oz;
-    float ez, cp, sp, cy, sy;
+    float ez;
 };
-__device__ __noinline__ uint32_t sky_pixel(const SkyArgs sk, float dx, float dy) {
+__device__ __noinline__ uint32_t sky_pixel(const SkyArgs sk, const CamP cam, float dx, float dy) {
     // primary ray, kernel.cu:1624-1631 + camera::rotateDir :252-255
-    v3 v = mk(dx - 0.f, dy - 0.f, 0.f - sk.ez);
-    v3 nd = ref_normalise(v);
-    float y = nd.y * sk.cp - nd.z * sk.sp;
-    float z = nd.y * sk.sp + nd.z * sk.cp;
-    float x = nd.x * sk.cy + z * sk.sy;
-    z = -nd.x * sk.sy + z * sk.cy;
-    const v3 O = mk(sk.Ox, sk.Oy, sk.Oz), D = mk(x, y, z);
+    const v3 D = primary_dir(cam, sk.ez, dx, dy);
+    const v3 O = mk(cam.Ox, cam.Oy, cam.Oz);
     float t;
     ref_intersect(O, D, 0.f, 0.f, 0.f, sk.radius, t);
     v3 hp = ref_add(O, ref_scale(D, t));
@@ -151,8 +149,9 @@ __global__ void __launch_bounds__(PRIMARY_THREADS, ORE_PRIMARY_MIN_CTAS) primary
     __shared__ int s_batch;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    // ---- stage the per-frame cone records: [supers][leaves][spheres, when they fit] - one TMA bulk copy each,
-    //      shared by the CTA's warps for all their tiles ----
+    // ---- the cone records of ONE frame at a time are staged in shared memory: [supers][leaves][spheres, when they fit]
+    //      - one TMA bulk copy each, shared by the CTA's warps for all their tiles of that frame.  Batches are fetched
+    //      in ascending order, so a CTA restages at most once per frame of the batch. ----
     float4* const s_super = reinterpret_cast<float4*>(smem_raw);
     float4* const s_leaf = s_super + prm.n_supers_pad;
     float4* const s_sph = s_leaf + prm.n_leaves_pad;
@@ -162,36 +161,53 @@ __global__ void __launch_bounds__(PRIMARY_THREADS, ORE_PRIMARY_MIN_CTAS) primary
         s_batch = (int)atomicAdd(&prm.counters[CNT_PRIMARY_CURSOR], 1ull);
     }
     __syncthreads();
-    if (tid == 0) {
-        const uint32_t b_sup = (uint32_t)prm.n_supers_pad * 16u, b_leaf = (uint32_t)prm.n_leaves_pad * 16u;
-        const uint32_t b_sph = prm.cone_resident ? (uint32_t)prm.n_sort * 16u : 0u;
-        mbar_expect_tx(&bar, b_sup + b_leaf + b_sph);
-        if (b_sup) tma_bulk_g2s(s_super, prm.super_cone, b_sup, &bar);
-        if (b_leaf) tma_bulk_g2s(s_leaf, prm.leaf_cone, b_leaf, &bar);
-        if (b_sph) tma_bulk_g2s(s_sph, prm.cone_sorted, b_sph, &bar);
-    }
-    mbar_wait(&bar, 0);
-    const float4* __restrict__ sph_cone = prm.cone_resident ? s_sph : prm.cone_sorted;
+    uint32_t bar_phase = 0;
+    int staged_frame = -1;
+    const float4* __restrict__ sph_cone = s_sph;
 
     const int tiles_x = (prm.W + 31) / 32;
     const int tiles_y = (prm.n_rows + P - 1) / P;
     const int total_tiles = tiles_x * tiles_y;
-    const int n_batches = (total_tiles + PRIMARY_WARPS - 1) / PRIMARY_WARPS;
+    const int batches_per_frame = (total_tiles + PRIMARY_WARPS - 1) / PRIMARY_WARPS;
+    const int n_batches = batches_per_frame * prm.n_frames;
     const int n_sph = prm.n_spheres, n_leaf = prm.n_leaves, n_sup = prm.n_supers;
-    const v3 O = mk(prm.Ox, prm.Oy, prm.Oz);
-    const DirArgs da = {prm.ez, prm.cp, prm.sp, prm.cy, prm.sy};
-    const SkyArgs sk = {prm.sky_r, prm.sky_g, prm.sky_b, prm.sky_w, prm.sky_h, prm.sky_radius, prm.Ox, prm.Oy, prm.Oz,
-                        prm.ez, prm.cp, prm.sp, prm.cy, prm.sy};
-    const bool vec_ok = (prm.pitch & 3) == 0 && ((reinterpret_cast<uintptr_t>(prm.pixels) & 15u) == 0);
+    const bool pitch_ok = (prm.pitch & 3) == 0;
+    const SkyArgs sk = {prm.sky_r, prm.sky_g, prm.sky_b, prm.sky_w, prm.sky_h, prm.sky_radius, prm.ez};
     unsigned long long n_exact = 0;
     unsigned int n_steps = 0;
 
-    // batches of PRIMARY_WARPS adjacent tiles, fetched dynamically (tile cost varies ~8x between sky and sphere tiles);
-    // the CTA appends the hit records of a batch with ONE atomic, so neighbouring tiles stay neighbours in the hit list
+    // batches of PRIMARY_WARPS adjacent tiles of one frame, fetched dynamically (tile cost varies ~8x between sky and
+    // sphere tiles); the CTA appends the hit records of a batch with ONE atomic, so neighbouring tiles stay neighbours in
+    // the hit list
     for (;;) {
         const int batch = s_batch;
         if (batch >= n_batches) break;
-        const int tile_id = batch * PRIMARY_WARPS + warp;
+        const int frame = batch / batches_per_frame;
+        if (frame != staged_frame) {
+            // (every warp is past its reads of the previous frame's records: it has gone through the barriers of the
+            // previous batch since)
+            __syncthreads();
+            if (tid == 0) {
+                const uint32_t b_sup = (uint32_t)prm.n_supers_pad * 16u, b_leaf = (uint32_t)prm.n_leaves_pad * 16u;
+                const uint32_t b_sph = prm.cone_resident ? (uint32_t)prm.n_sort * 16u : 0u;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(&bar, b_sup + b_leaf + b_sph);
+                if (b_sup) tma_bulk_g2s(s_super, prm.super_cone + (size_t)frame * prm.n_supers_pad, b_sup, &bar);
+                if (b_leaf) tma_bulk_g2s(s_leaf, prm.leaf_cone + (size_t)frame * prm.n_leaves_pad, b_leaf, &bar);
+                if (b_sph) tma_bulk_g2s(s_sph, prm.cone_sorted + (size_t)frame * prm.n_sort, b_sph, &bar);
+            }
+            mbar_wait(&bar, bar_phase);
+            bar_phase ^= 1u;
+            staged_frame = frame;
+            sph_cone = prm.cone_resident ? s_sph : prm.cone_sorted + (size_t)frame * prm.n_sort;
+        }
+        const CamP cam = prm.cam[frame];
+        const v3 O = mk(cam.Ox, cam.Oy, cam.Oz);
+        const DirArgs da = {prm.ez, cam.cp, cam.sp, cam.cy, cam.sy};
+        const float4* __restrict__ prim_rec = prm.prim_sorted + (size_t)frame * prm.n_sort;
+        uint32_t* const frame_px = prm.pixels[frame];
+        const bool vec_ok = pitch_ok && ((reinterpret_cast<uintptr_t>(frame_px) & 15u) == 0);
+        const int tile_id = (batch - frame * batches_per_frame) * PRIMARY_WARPS + warp;
         const bool tile_ok = tile_id < total_tiles;
         const int ty = tile_ok ? tile_id / tiles_x : 0;
         const int tx = tile_ok ? tile_id % tiles_x : 0;
@@ -232,7 +248,7 @@ __global__ void __launch_bounds__(PRIMARY_THREADS, ORE_PRIMARY_MIN_CTAS) primary
 #pragma unroll 1
             for (int s0 = 0; s0 < prm.n_boxes; s0 += 32) {
                 bool cand = false;
-                if (s0 + lane < prm.n_boxes) cand = EXH || cone_touches(ax, ay, az, __ldg(&prm.box_cone[s0 + lane]));
+                if (s0 + lane < prm.n_boxes) cand = EXH || cone_touches(ax, ay, az, __ldg(&prm.box_cone[(size_t)frame * prm.n_boxes + s0 + lane]));
                 uint32_t mask = __ballot_sync(0xffffffffu, cand && tile_ok);
                 while (mask) {
                     const int i = __ffs(mask) - 1;
@@ -278,7 +294,7 @@ __global__ void __launch_bounds__(PRIMARY_THREADS, ORE_PRIMARY_MIN_CTAS) primary
                         const int i = __ffs(wmask) - 1;
                         wmask &= wmask - 1;
                         const int s = __shfl_sync(0xffffffffu, s_mine, i);
-                        const float4 q = __ldg(&prm.prim_sorted[s]);
+                        const float4 q = __ldg(&prim_rec[s]);
                         const float e = fmaf(dx, q.x, q.z);
                         uint32_t pass = 0;
 #pragma unroll
@@ -350,9 +366,9 @@ __global__ void __launch_bounds__(PRIMARY_THREADS, ORE_PRIMARY_MIN_CTAS) primary
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         px[j] = 0u;
-                        if (!((hits4 >> j) & 1u) && x4 + j < prm.W) px[j] = sky_pixel(sk, dxs[j], dy);
+                        if (!((hits4 >> j) & 1u) && x4 + j < prm.W) px[j] = sky_pixel(sk, cam, dxs[j], dy);
                     }
-                    uint32_t* dst = prm.pixels + out_index(prm, k, x4);
+                    uint32_t* dst = frame_px + out_index(prm, k, x4);
                     if (vec_ok && x4 + 3 < prm.W) {
                         *reinterpret_cast<uint4*>(dst) = make_uint4(px[0], px[1], px[2], px[3]);  // 128-bit RGBA store
                     } else {
@@ -411,7 +427,7 @@ __global__ void __launch_bounds__(PRIMARY_THREADS, ORE_PRIMARY_MIN_CTAS) primary
         for (int p = 0; p < P; p++) {
             if (best_id[p] >= 0) {
                 const uint32_t at = wbase + my_off[p];
-                prm.hit_list[at] = (uint32_t)((size_t)(ty * P + p) * prm.W + x);
+                prm.hit_list[at] = (uint32_t)frame * prm.n_px_frame + (uint32_t)((ty * P + p) * prm.W + x);
                 prm.hit_ids[at] = best_id[p];
                 prm.hit_ts[at] = best_t[p];
             }

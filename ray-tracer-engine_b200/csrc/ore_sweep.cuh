@@ -77,7 +77,6 @@ __global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_CTAS) shadow_sweep_ke
     const float4* __restrict__ supers = prm.super_sph;   // bounding ball of leaves [32k, 32k+32)
     const int n_sph = prm.n_spheres, n_leaf = prm.n_leaves, n_sup = prm.n_supers;
     const uint32_t n_items = (uint32_t)prm.counters[CNT_HITS];
-    const v3 O0 = mk(prm.Ox, prm.Oy, prm.Oz);
     const int NLI = prm.n_lights;
     unsigned long long n_exact = 0;
     unsigned int n_l1 = 0, n_l2 = 0, n_steps = 0;
@@ -120,16 +119,16 @@ __global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_CTAS) shadow_sweep_ke
         }
 
         // ---- shading set-up (kernel.cu:1396-1405, 1643-1655), or its staged result ----
-        size_t o_out = 0;
+        uint32_t* out_px = nullptr;
         int my_id = -1;
         v3 start = mk(1e9f, 1e9f, 1e9f), normal = mk(0.f, 0.f, 0.f);
         float tr = 0.f, tg = 0.f, tb = 0.f;
         const float* __restrict__ sp = STAGED ? st.buf + ((size_t)wb * (size_t)st.nv) * 32u + lane : nullptr;
         if (STAGED) {
             if (valid) {
-                const uint32_t o = prm.hit_list[item];
-                const int k = (int)(o / (uint32_t)prm.W), x = (int)(o % (uint32_t)prm.W);
-                o_out = out_index(prm, k, x);
+                int frame, k, x;
+                split_pixel(prm, prm.hit_list[item], frame, k, x);
+                out_px = prm.pixels[frame] + out_index(prm, k, x);
                 my_id = (int)__ldg(&prm.hit_ids[item]);
                 start = mk(sp[0], sp[32], sp[64]);
                 tr = sp[96];
@@ -137,7 +136,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_CTAS) shadow_sweep_ke
                 tb = sp[160];
             }
         } else if (valid) {
-            shade_point(prm, item, O0, o_out, my_id, start, normal, tr, tg, tb);
+            shade_point(prm, item, out_px, my_id, start, normal, tr, tg, tb);
         }
         float fr = 0.f, fg = 0.f, fb = 0.f;
 
@@ -394,7 +393,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_CTAS) shadow_sweep_ke
             }
             __syncwarp();   // every lane is done with this light's slot before a later copy may overwrite it
         }
-        if (valid) prm.pixels[o_out] = ref_rgb_to_int((int)(fr * 254.f), (int)(fg * 254.f), (int)(fb * 254.f));
+        if (valid) *out_px = ref_rgb_to_int((int)(fr * 254.f), (int)(fg * 254.f), (int)(fb * 254.f));
         if (STAGED && prm.dbg_cycles && lane == 0 && blk < prm.dbg_cap)
             prm.dbg_cycles[prm.dbg_cap + blk] = (uint32_t)(clock64() - dbg_t0);
         if (!ahead) {

@@ -221,6 +221,21 @@ class PeerFrame:
         self.submitted = g + 1
         return g
 
+    def submit_batch(self, cameras, stream: int = 0, flags: int = 0, renderer=None):
+        """Render this rank's rows of the next len(cameras) frames in ONE launch set (ore_render_batch_device) into their
+        ring buffers and announce them together.  len(cameras) <= n_buffers."""
+        rr = renderer or self.r
+        g, k = self.submitted, len(cameras)
+        assert 1 <= k <= self.n_buffers
+        if g + k > self.n_buffers:
+            rr.flag_wait_geq(self.ack, g + k - self.n_buffers, stream)   # the oldest buffer this batch reuses is free
+        args = [self.band_args((g + i) % self.n_buffers) for i in range(k)]
+        band = {key: v for key, v in args[0].items() if key != "out_ptr"}
+        rr.render_batch_device(cameras, self.width, self.height, [a["out_ptr"] for a in args], stream=stream, flags=flags, **band)
+        self.r.flag_write_after(self.done + 256 * self.rank, g + k, stream)
+        self.submitted = g + k
+        return g
+
     def present(self, stream: int, consume=None):
         """Presenter only: on `stream`, wait for every rank's rows of the next frame, run `consume(buffer_ptr, g)`
         (enqueue-only work such as a device->host copy), then acknowledge the frame to every rank."""
@@ -310,6 +325,9 @@ class SharedHostFrame:
     def can_submit(self) -> bool:
         """the ring buffer of the next frame is free once the presenter has consumed the frame that used it before"""
         return self.consumed + self.n_buffers > self.submitted
+
+    def can_submit_batch(self, k: int) -> bool:
+        return self.consumed + self.n_buffers >= self.submitted + k
 
     def next_slot(self):
         """(frame number g, buffer index) of this rank's next frame; call can_submit() first"""

@@ -318,3 +318,71 @@ def test_onstart_update_frame_equals_the_oracle(pipelined, oracle_best, pkg, tmp
     ref = oracle_best.render(sc, cam, W, H)["pixels"]
     _exact(got, ref, libm_matches)
     assert info["checksum"] == int(got.astype(np.uint64).sum())
+
+
+# ---- batches of frames: one launch set for several cameras ---------------------------------------------------------
+
+def test_batch_of_frames_equals_single_frames(renderer, pkg):
+    """ore_render_batch_device: K cameras in one launch set give exactly the K single-frame renders - full frames,
+    block-interleaved bands stored in place, the fused form and the exhaustive mode"""
+    import torch
+    sc = pkg.scene.scaled_scene(64, 2)
+    renderer.set_scene(sc)
+    W, H = 333, 203
+    cams = [pkg.scene.orbit_camera(sc, f) for f in (0, 31, 77, 140, 200)]
+    want = [renderer.render(c, W, H).copy() for c in cams]
+    F = pkg.capi
+    for flags in (0, F.ORE_FLAG_FUSED_SHADOW, F.ORE_FLAG_EXHAUSTIVE, F.ORE_FLAG_FAST_LIBM):
+        ref = want if flags != F.ORE_FLAG_FAST_LIBM else [renderer.render(c, W, H, flags=flags).copy() for c in cams]
+        frames = torch.zeros((len(cams), H, W), dtype=torch.int32, device="cuda:0")
+        renderer.render_batch_device(cams, W, H, [frames[i].data_ptr() for i in range(len(cams))], flags=flags)
+        renderer.synchronize()
+        got = frames.cpu().numpy().view(np.uint32)
+        for i in range(len(cams)):
+            assert np.array_equal(got[i], ref[i]), (flags, i, int(np.count_nonzero(got[i] != ref[i])))
+    # three "ranks" rendering their row blocks of a batch of two frames straight into two shared frames
+    frames = torch.zeros((2, H, W), dtype=torch.int32, device="cuda:0")
+    for rank in range(3):
+        b = pkg.multigpu.block_band(rank, 3, H)
+        renderer.render_batch_device(cams[:2], W, H, [frames[i].data_ptr() + 4 * W * b["y0"] for i in range(2)], out_pitch=W, **b)
+    renderer.synchronize()
+    got = frames.cpu().numpy().view(np.uint32)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    c = renderer.counters()
+    assert c["pixels"] == 2 * pkg.Renderer.rows(H, **pkg.multigpu.block_band(2, 3, H)) * W
+    with pytest.raises(pkg.OreError):     # per-pixel maps need a single-frame render
+        renderer.hits(H, W)
+    with pytest.raises(pkg.OreError):     # at most 8 frames per launch set
+        renderer.render_batch_device(cams + cams, W, H, [frames[0].data_ptr()] * 10)
+
+
+def test_batch_async_lands_frames_in_order_with_flags(renderer, pkg):
+    sc = pkg.scene.scaled_scene(64, 2)
+    renderer.set_scene(sc)
+    W, H, K = 320, 180, 3
+    host = [renderer.host_alloc((H, W)) for _ in range(2 * K)]
+    flag = renderer.host_alloc((16,))
+    flag[:] = 0
+    try:
+        cams = [pkg.scene.orbit_camera(sc, 10 * f) for f in range(2 * K)]
+        want = [renderer.render(c, W, H).copy() for c in cams]
+        renderer.render_batch_async(cams[:K], W, H, host[:K], done_flag=flag.ctypes.data, first_done_value=1)
+        renderer.render_batch_async(cams[K:], W, H, host[K:], done_flag=flag.ctypes.data, first_done_value=K + 1)
+        t0 = time.time()
+        while int(flag[0]) < 2 * K:
+            assert time.time() - t0 < 20
+        for a, b in zip(host, want):
+            assert np.array_equal(a, b)
+        # rows in place, two ranks, batch of two frames into two full host frames
+        for h_ in host[:2]:
+            h_[:] = 0
+        for rank in range(2):
+            b = pkg.multigpu.block_band(rank, 2, H)
+            renderer.render_batch_async(cams[:2], W, H, [host[i].ctypes.data + 4 * W * b["y0"] for i in range(2)], in_place=True, **b)
+        renderer.wait()
+        assert np.array_equal(host[0], want[0]) and np.array_equal(host[1], want[1])
+    finally:
+        renderer.wait()
+        for h_ in host:
+            renderer.host_free(h_)
+        renderer.host_free(flag)
