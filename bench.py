@@ -215,6 +215,7 @@ def main():
     ap.add_argument("--batch", type=int, default=4, help="frames (cameras) per launch set: ore_render_batch_*")
     ap.add_argument("--in-flight", type=int, default=2, help="batches in flight per GPU (contexts/streams used round-robin)")
     ap.add_argument("--host-buffers", type=int, default=3, help="frames in the shared host ring of the e2e path")
+    ap.add_argument("--ring", type=int, default=0, help="frames in the presenter's ring (default: batch x (in-flight + 1))")
     ap.add_argument("--emulate-world", type=int, default=0,
                     help="tool, single process only: render just the rows rank --emulate-rank of this many ranks would "
                          "render (isolates per-rank effects of short frames from NVLink effects); the line says so")
@@ -242,6 +243,12 @@ def main():
         return 0
 
     # ---------------- our arm ----------------
+    # rank 0's stdout is ONE JSON line: anything libraries print while the job runs (NCCL's version banner, ...) goes to
+    # stderr; the saved descriptor is restored for the line itself
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
 
@@ -267,7 +274,8 @@ def main():
     r, stream = ctxs[0]
     present_stream = torch.cuda.Stream(device=local)
     # frame ring on the presenter + completion / ack flags
-    peer = mg.PeerFrame(r, W, H, n_buffers=NF * KB, band_of=(args.emulate_rank, emulate) if emulate else None)
+    NRING = args.ring if args.ring >= NF * KB else KB * (NF + 1)   # one batch of slack: a rank may run ahead of the slowest
+    peer = mg.PeerFrame(r, W, H, n_buffers=NRING, band_of=(args.emulate_rank, emulate) if emulate else None)
 
     def barrier():
         if world > 1:
@@ -285,9 +293,8 @@ def main():
             n_batches_done[0] += 1
             peer.submit_batch([camera(f0 + b0 + i) for i in range(kk)], stream=st.cuda_stream, flags=flags, renderer=rr)
             if rank == 0:
-                # presenter: on the present stream, wait for every rank's rows of each frame, then acknowledge it to all
-                for _ in range(kk):
-                    peer.present(present_stream.cuda_stream)
+                # presenter: on the present stream, wait for every rank's rows of the batch, then acknowledge it to all
+                peer.present_batch(present_stream.cuda_stream, kk)
 
     def join_streams(ev_list=None):
         """make `stream` wait for everything enqueued on the other streams of this rank"""
@@ -301,8 +308,9 @@ def main():
     frame_bytes = W * H * 4
     n_rows_mine = pkg.Renderer.rows(H, **mg.block_band(peer.band_rank, peer.band_world, H))
 
-    # warm-up (every context)
-    render_steps(0, max(args.warmup, KB) * NF)
+    # warm-up: at least three launch sets per context (the staging buffer of a context is sized from the hit count of
+    # its previous frames and has settled by then)
+    render_steps(0, max(args.warmup, 3 * KB * NF))
     barrier()
     # hit pixels of this rank's band (for the working-set note and the roofline units)
     warm_hits = r.counters()["hit_pixels"]
@@ -356,11 +364,27 @@ def main():
         shared = mg.SharedHostFrame(W, H, peer.band_rank, peer.band_world, n_buffers=NHB,
                                     register=r.host_register, unregister=r.host_unregister)
         name = [shared.name]
+    numa_note = "single process"
     if world > 1:
         dist.broadcast_object_list(name, src=0)
         if rank != 0:
             shared = mg.SharedHostFrame(W, H, rank, world, n_buffers=NHB, name=name[0], register=r.host_register,
                                         unregister=r.host_unregister)
+        # NUMA: every rank first-touches ITS rows from a CPU next to its GPU, then everybody pins the ring
+        try:
+            bus = torch.cuda.get_device_properties(local).pci_bus_id
+            dom = getattr(torch.cuda.get_device_properties(local), "pci_domain_id", 0)
+            devn = getattr(torch.cuda.get_device_properties(local), "pci_device_id", 0)
+            pci = f"{dom:08x}:{bus:02x}:{devn:02x}.0"
+        except Exception:
+            pci = None
+        cpus = mg.gpu_local_cpus(pci) if pci else None
+        numa_note = (f"rows first-touched from the {len(cpus)} CPUs NVML reports local to each rank's GPU" if cpus
+                     else "GPU-local CPUs unknown: rows first-touched where the rank happens to run")
+        shared.touch_own_rows(pci)
+        dist.barrier()
+        shared.pin()
+        dist.barrier()
     band = shared.band()
     e2e_ranks = [shared.rank] if emulate else list(range(world))
 
@@ -583,7 +607,7 @@ def main():
                        f"in shared memory by design; what it WRITES and re-reads is larger than L2 - per rank and step "
                        f"{ws_mb:.0f} MB of framebuffer rows, hit records and shadow staging, x {NF * KB} frames in flight, L2 126 MB"),
                 "frame_overlap": (f"{KB} frames (cameras) per launch set (ore_render_batch_device / ore_render_batch_async), {NF} launch sets "
-                                  f"in flight per GPU (contexts/streams used round-robin), ring of {NF * KB} presenter frames; the same at every N"),
+                                  f"in flight per GPU (contexts/streams used round-robin), ring of {NRING} presenter frames; the same at every N"),
                 "parallelism": (f"row-bands x{world} (8-row blocks dealt round-robin), presenter = rank 0; rows stored over NVLink into "
                                 f"the presenter's ring; completion = per-rank flags (no collective in the timed region)"
                                 if world > 1 else "1 GPU (same code path: frame ring + flags)"),
@@ -608,6 +632,7 @@ def main():
                     "note": "inputs per step are the 36-byte camera and the 36-byte frame descriptor (kernel arguments); output per "
                             "step is the whole framebuffer in pinned host memory plus a 4-byte counter per rank; "
                             "synchronous_value = ore_render (launch + sync + copy per call, the reference update() semantics, N = 1)",
+                    "host_pages": numa_note,
                     "sharded_frame_check": frame_check},
             "gpu_launches": int(round(launches_per_frame * args.steps)),
             "gpu_launches_per_frame": {"count": launches_per_frame, "per_launch_set": launches_per_batch, "frames_per_launch_set": KB,
@@ -642,7 +667,11 @@ def main():
             "cpu_baseline": cpu,
         }
         line.update(extras)
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(2, 1)
     shared.close()
     peer.close()
     for rx, _ in ctxs[1:]:

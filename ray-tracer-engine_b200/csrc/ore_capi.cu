@@ -874,7 +874,9 @@ static int render_impl(ore_context* ctx, const ore_camera* cams, int n_frames, c
                 const unsigned long long h = *(volatile unsigned long long*)ctx->hits_hint;
                 est_items = (size_t)(h + h / 8 + 32768ull);
             } else {
-                est_items = n_px / 4 > ((size_t)1 << 20) ? n_px / 4 : ((size_t)1 << 20);
+                // no frame of this context has finished yet: half the pixels (growing the buffer later costs a
+                // device-wide synchronisation; the cap below bounds the memory)
+                est_items = n_px / 2 > ((size_t)1 << 20) ? n_px / 2 : ((size_t)1 << 20);
             }
             if (est_items > n_px) est_items = n_px;
             est_blocks = (est_items + 31) / 32;
@@ -887,7 +889,7 @@ static int render_impl(ore_context* ctx, const ore_camera* cams, int n_frames, c
                 cap_blocks = ctx->stage_blocks_override;
                 while ((n_blocks_px + cap_blocks - 1) / cap_blocks > (size_t)MAX_STAGE_CHUNKS) cap_blocks *= 2;
             } else if (est_blocks > have_blocks && have_blocks < max_blocks) {
-                cap_blocks = est_blocks + est_blocks / 8;   // grow with some slack: reallocations stay rare
+                cap_blocks = est_blocks + est_blocks / 4;   // grow with some slack: reallocations stay rare
                 if (cap_blocks > n_blocks_px) cap_blocks = n_blocks_px;
                 if (cap_blocks > max_blocks) cap_blocks = max_blocks;
             }

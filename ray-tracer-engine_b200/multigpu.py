@@ -150,10 +150,16 @@ class PeerFrame:
       ack      (one flag in EVERY rank's memory, written by the presenter): frames the presenter has consumed"""
 
     ROW_BLOCK = ROW_BLOCK
+    FLAG_BYTES = 4096
 
     def __init__(self, renderer, width: int, height: int, n_buffers: int = 2, group=None, band_of=None):
         """band_of = (rank, world): render the rows THAT rank of THAT many ranks would own while the flags stay those
-        of this process (single-process tools that look at one rank's share of a frame)"""
+        of this process (single-process tools that look at one rank's share of a frame).
+
+        Where the flags live: with one process, in device memory.  With several, in a page of POSIX shared memory that
+        every rank pins (ore_host_register): a stream writes / waits on pinned host memory with cuStreamWriteValue32 /
+        cuStreamWaitValue32, which needs NO SM - a one-thread kernel storing to a peer GPU's memory would queue behind
+        the persistent render kernels that fill every SM (measured: acknowledgements milliseconds late)."""
         import torch.distributed as dist
 
         self.r = renderer
@@ -168,37 +174,40 @@ class PeerFrame:
         self.n_buffers = n_buffers
         self.submitted = 0    # frames this rank has submitted
         self.presented = 0    # frames the presenter has enqueued for presentation (rank 0 only)
+        self._shm = None
         if self.rank == 0:
             for _ in range(n_buffers):
                 p = renderer.dev_alloc(self.nbytes)
                 self._owned.append(p)
                 self.ptrs.append(p)
-            self.done = renderer.dev_alloc(256 * max(1, self.world))   # one 256-byte line per rank (zeroed)
-            self._owned.append(self.done)
-            payload = [[renderer.ipc_export(p) for p in self.ptrs] + [renderer.ipc_export(self.done)]]
+            payload = [[renderer.ipc_export(p) for p in self.ptrs]]
         else:
             payload = [None]
         if self.world > 1:
-            dist.broadcast_object_list(payload, src=0, group=group)
-        if self.rank != 0:
-            for handle in payload[0]:
-                p = renderer.ipc_import(handle)
-                self._opened.append(p)
-            self.ptrs = self._opened[:-1]
-            self.done = self._opened[-1]
-        # every rank's ack flag, mapped by the presenter
-        self.ack = renderer.dev_alloc(256)
-        self._owned.append(self.ack)
-        self.acks = [self.ack]
-        if self.world > 1:
-            handles = [None] * self.world
-            dist.all_gather_object(handles, renderer.ipc_export(self.ack), group=group)
+            from multiprocessing import shared_memory
             if self.rank == 0:
-                self.acks = [self.ack]
-                for h in handles[1:]:
-                    p = renderer.ipc_import(h)
-                    self._opened.append(p)
-                    self.acks.append(p)
+                self._shm = shared_memory.SharedMemory(create=True, size=self.FLAG_BYTES)
+                self._shm.buf[:] = bytes(self.FLAG_BYTES)
+                payload[0].append(self._shm.name)
+            dist.broadcast_object_list(payload, src=0, group=group)
+            if self.rank != 0:
+                self._shm = shared_memory.SharedMemory(name=payload[0][-1])
+                for handle in payload[0][:-1]:
+                    self._opened.append(renderer.ipc_import(handle))
+                self.ptrs = list(self._opened)
+            self._flag_view = np.ndarray((self.FLAG_BYTES // 4,), dtype=np.uint32, buffer=self._shm.buf)
+            base = self._flag_view.ctypes.data
+            renderer.host_register(base, self.FLAG_BYTES)
+            self._flag_base = base
+            self.done = base                                  # done[r] at base + 256 r
+            self.ack = base + 256 * self.world                # ONE acknowledgement counter, read by every rank
+            self.acks = [self.ack]
+            dist.barrier(group=group)                         # everybody has mapped and pinned the page
+        else:
+            self.done = renderer.dev_alloc(256)               # single process: device memory
+            self.ack = renderer.dev_alloc(256)
+            self._owned += [self.done, self.ack]
+            self.acks = [self.ack]
 
     def band_args(self, buf: int) -> dict:
         """kwargs for Renderer.render_device: this rank's block-interleaved rows of buffer `buf`, stored at
@@ -250,12 +259,91 @@ class PeerFrame:
         self.presented = g + 1
         return g
 
+    def present_batch(self, stream: int, k: int, consume=None):
+        """Presenter only: the same for the next k frames at once (one wait per rank, one acknowledgement)"""
+        assert self.rank == 0
+        g = self.presented
+        for r in range(self.world):
+            self.r.flag_wait_geq(self.done + 256 * r, g + k, stream)
+        if consume is not None:
+            for i in range(k):
+                consume(self.ptrs[(g + i) % self.n_buffers], g + i)
+        for a in self.acks:
+            self.r.flag_write(a, g + k, stream)
+        self.presented = g + k
+        return g
+
     def close(self):
         for p in self._opened:
             self.r.ipc_close(p)
         for p in self._owned:
             self.r.dev_free(p)
         self._opened, self._owned = [], []
+        if self._shm is not None:
+            try:
+                self.r.host_unregister(self._flag_base)
+            except Exception:
+                pass
+            self._flag_view = None
+            try:
+                self._shm.close()
+            except BufferError:
+                pass
+            if self.rank == 0:
+                try:
+                    self._shm.unlink()
+                except FileNotFoundError:
+                    pass
+            self._shm = None
+
+
+# ---- NUMA placement of host pages next to the GPU that writes them ---------------------------------------------
+
+def gpu_local_cpus(pci_bus_id: str | None):
+    """CPUs NVML reports as local to the GPU (its NUMA node), or None when that cannot be determined"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(pci_bus_id.encode() if isinstance(pci_bus_id, str) else pci_bus_id)
+        import os
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1}
+        return cpus or None
+    except Exception:
+        return None
+
+
+class run_near_gpu:
+    """Context manager: pin the calling thread to the CPUs local to a GPU (so that pages it first touches land on that
+    GPU's NUMA node), restoring the affinity afterwards.  Does nothing when the topology is unknown."""
+
+    def __init__(self, pci_bus_id):
+        self.cpus = gpu_local_cpus(pci_bus_id) if pci_bus_id else None
+        self.saved = None
+
+    def __enter__(self):
+        import os
+        if self.cpus:
+            try:
+                self.saved = os.sched_getaffinity(0)
+                want = self.cpus & self.saved
+                if want:
+                    os.sched_setaffinity(0, want)
+                else:
+                    self.saved = None
+            except Exception:
+                self.saved = None
+        return self
+
+    def __exit__(self, *exc):
+        import os
+        if self.saved is not None:
+            try:
+                os.sched_setaffinity(0, self.saved)
+            except Exception:
+                pass
+        return False
 
 
 # ---- one shared, pinned HOST frame ring written by every rank over its own PCIe link ------------------------
@@ -290,13 +378,30 @@ class SharedHostFrame:
         self.frames = [np.ndarray((height, width), dtype=np.uint32, buffer=self.shm.buf,
                                   offset=self.HEADER + i * self.frame_bytes) for i in range(n_buffers)]
         self.base = self._flags.ctypes.data
-        self._unregister = unregister
+        self.total_bytes = total
+        self._register, self._unregister = register, unregister
         self._registered = False
-        if register is not None:
-            register(self.base, total)
-            self._registered = True
+        if register is not None and world == 1:
+            self.pin()      # (with several ranks: touch_own_rows() on every rank, a barrier, then pin() - see there)
         self.submitted = 0
         self.presented = 0
+
+    def touch_own_rows(self, pci_bus_id=None):
+        """First touch of this rank's row blocks in every ring buffer, from a CPU next to this rank's GPU: the pages a
+        GPU will write over PCIe are then allocated on ITS NUMA node instead of all on the creator's (shared memory is
+        sparse until touched; pinning faults the rest in wherever the pinning process runs, so touch first, pin after)."""
+        rows = block_rows(self.rank, self.world, self.height, self.block)
+        if not rows:
+            return
+        with run_near_gpu(pci_bus_id):
+            for fr in self.frames:
+                for y0 in rows[:: self.block]:
+                    fr[y0:min(y0 + self.block, self.height)] = 0
+
+    def pin(self):
+        if self._register is not None and not self._registered:
+            self._register(self.base, self.total_bytes)
+            self._registered = True
 
     # addresses / views
     def done_addr(self, r: int) -> int:

@@ -242,6 +242,9 @@ def test_shared_host_frame_registered_and_written_by_the_gpu(renderer, pkg):
     W, H, P, NB = 200, 90, 2, 2
     owner = mg.SharedHostFrame(W, H, 0, P, n_buffers=NB, register=renderer.host_register, unregister=renderer.host_unregister)
     other = mg.SharedHostFrame(W, H, 1, P, n_buffers=NB, name=owner.name)   # same mapping, second rank's view
+    owner.touch_own_rows()      # several ranks: every rank touches its rows first, then the ring is pinned
+    other.touch_own_rows()
+    owner.pin()
     try:
         shown = []
         for g in range(5):
