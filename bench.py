@@ -334,8 +334,13 @@ def main():
     barrier()
     t_end = time.perf_counter()
     clocks = sampler.stop(t_begin, t_end)
-    total_ms = torch.tensor([ev_start.elapsed_time(ev_end)], dtype=torch.float64, device=dev)
+    my_ms = ev_start.elapsed_time(ev_end)
+    per_rank_ms = [my_ms]
+    total_ms = torch.tensor([my_ms], dtype=torch.float64, device=dev)
     if world > 1:
+        gathered = [torch.zeros_like(total_ms) for _ in range(world)]
+        dist.all_gather(gathered, total_ms)
+        per_rank_ms = [float(g.item()) for g in gathered]
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
     value = W * H * args.steps / (total_ms * 1e-3) / 1e6
@@ -365,6 +370,8 @@ def main():
                                     register=r.host_register, unregister=r.host_unregister)
         name = [shared.name]
     numa_note = "single process"
+    if world == 1:
+        shared.pin()     # (also when only one rank's rows of a larger job are rendered: --emulate-world)
     if world > 1:
         dist.broadcast_object_list(name, src=0)
         if rank != 0:
@@ -449,6 +456,35 @@ def main():
             frame_check = "identical" if np.array_equal(alone[rows], got[rows]) else "MISMATCH"
         else:
             frame_check = "identical" if np.array_equal(alone, got) else "MISMATCH"
+    # ---- what the platform allows: all ranks copy device -> host at the same time, no rendering (the bound of e2e) ----
+    d2h_probe = None
+    try:
+        slice_bytes = min(64 << 20, (NHB * frame_bytes // max(1, world)) & ~0xFFF)
+        src = torch.empty(slice_bytes, dtype=torch.uint8, device=dev)
+        pinned = torch.empty(slice_bytes, dtype=torch.uint8).pin_memory()
+        reps = 6
+        res = {}
+        for label in ("cudaHostAlloc", "registered_shared_ring"):
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                if label == "cudaHostAlloc":
+                    pinned.copy_(src, non_blocking=True)
+                    torch.cuda.current_stream().synchronize()
+                else:
+                    r.copy_to_host(np.frombuffer(shared.shm.buf, dtype=np.uint8, count=slice_bytes,
+                                                 offset=shared.HEADER + (rank if not emulate else 0) * slice_bytes), src.data_ptr())
+            barrier()
+            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            res[label] = world * reps * slice_bytes / float(dt.item()) / 1e9
+        d2h_probe = {"aggregate_gbs": res, "bytes_per_copy": slice_bytes, "copies": reps,
+                     "what": "every rank copies device -> pinned host memory at the same time, nothing else running; "
+                             "Mrays/s bound of ANY host-resident frame = aggregate GB/s / 4 bytes per pixel"}
+        d2h_probe["e2e_bound_mrays"] = res["registered_shared_ring"] / 4 * 1e3
+    except Exception as e:   # a measurement extra only
+        d2h_probe = {"unavailable": str(e)[:200]}
     # synchronous update() semantics at N = 1, for reference: launch + sync + copy per call
     e2e_sync_value = None
     if world == 1 and not emulate:
@@ -616,6 +652,7 @@ def main():
                              if emulate else None),
                 "hit_pixel_fraction": tot["hits"] / max(1.0, tot["pixels"]),
                 "host_issue_ms_per_step": host_issue_ms,
+                "timed_region_ms_per_rank": per_rank_ms,
                 "device_memory_used_gb": mem_used,
                 "tests_per_pixel": {"primary": tot["primary"] / max(1.0, tot["pixels"]),
                                     "shadow_reference_order": tot["shadow"] / max(1.0, tot["pixels"])},
@@ -633,6 +670,7 @@ def main():
                             "step is the whole framebuffer in pinned host memory plus a 4-byte counter per rank; "
                             "synchronous_value = ore_render (launch + sync + copy per call, the reference update() semantics, N = 1)",
                     "host_pages": numa_note,
+                    "platform_d2h_probe": d2h_probe,
                     "sharded_frame_check": frame_check},
             "gpu_launches": int(round(launches_per_frame * args.steps)),
             "gpu_launches_per_frame": {"count": launches_per_frame, "per_launch_set": launches_per_batch, "frames_per_launch_set": KB,
