@@ -27,7 +27,15 @@ def main():
     rep, out, note = sys.argv[1], sys.argv[2], (sys.argv[3] if len(sys.argv) > 3 else "")
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
-    hdr, units, vals = rows[0], rows[1], rows[2]
+    hdr, units = rows[0], rows[1]
+    # several launches in the report: summarise the longest one
+    ti = hdr.index("gpu__time_duration.sum")
+    def dur(r):
+        try:
+            return float(r[ti].replace(",", ""))
+        except Exception:
+            return 0.0
+    vals = max((r for r in rows[2:] if len(r) == len(hdr)), key=dur)
     d = {"report": rep, "note": note, "kernel": vals[hdr.index("Kernel Name")], "metrics": {}}
     col = {}
     for h, u, v in zip(hdr, units, vals):
