@@ -212,7 +212,10 @@ def main():
     ap.add_argument("--workload", default="8k1024", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the N = 1 side measurements (4K, primary-only, fast libm, reference kernel)")
-    ap.add_argument("--batch", type=int, default=4, help="frames (cameras) per launch set: ore_render_batch_*")
+    ap.add_argument("--batch", type=int, default=8, help="frames (cameras) per launch set of the device-resident path: ore_render_batch_device")
+    ap.add_argument("--e2e-batch", type=int, default=4,
+                    help="frames per launch set of the host-resident path (ore_render_batch_async): smaller, because a batch's "
+                         "device->host copies only start when its kernels are done and the run is 20 steps long")
     ap.add_argument("--in-flight", type=int, default=2, help="batches in flight per GPU (contexts/streams used round-robin)")
     ap.add_argument("--host-buffers", type=int, default=3, help="frames in the shared host ring of the e2e path")
     ap.add_argument("--ring", type=int, default=0, help="frames in the presenter's ring (default: batch x (in-flight + 1))")
@@ -220,6 +223,9 @@ def main():
                     help="tool, single process only: render just the rows rank --emulate-rank of this many ranks would "
                          "render (isolates per-rank effects of short frames from NVLink effects); the line says so")
     ap.add_argument("--emulate-rank", type=int, default=0)
+    ap.add_argument("--diag-local-frames", action="store_true",
+                    help="diagnostic, N > 1: every rank stores its rows into its own memory instead of the presenter's frame "
+                         "(no NVLink stores; the frame is never assembled and the line says so)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank, local, world = dist_env()
@@ -275,7 +281,8 @@ def main():
     present_stream = torch.cuda.Stream(device=local)
     # frame ring on the presenter + completion / ack flags
     NRING = args.ring if args.ring >= NF * KB else KB * (NF + 1)   # one batch of slack: a rank may run ahead of the slowest
-    peer = mg.PeerFrame(r, W, H, n_buffers=NRING, band_of=(args.emulate_rank, emulate) if emulate else None)
+    peer = mg.PeerFrame(r, W, H, n_buffers=NRING, band_of=(args.emulate_rank, emulate) if emulate else None,
+                        local_frames=args.diag_local_frames and world > 1)
 
     def barrier():
         if world > 1:
@@ -362,7 +369,8 @@ def main():
     barrier()
 
     # ---- e2e: ONE shared pinned host frame ring, every rank copies its own rows over its own PCIe link ----------
-    NHB = max(2 * KB, args.host_buffers)
+    KE = max(1, min(KB, args.e2e_batch))
+    NHB = max(2 * KE, args.host_buffers)
     name = [None]
     shared = None
     if rank == 0:
@@ -415,8 +423,8 @@ def main():
         if timed:
             e0 = torch.cuda.Event(enable_timing=True)
             e0.record(render_stream)
-        for b0 in range(0, n_frames, KB):
-            kk = min(KB, n_frames - b0)
+        for b0 in range(0, n_frames, KE):
+            kk = min(KE, n_frames - b0)
             while not shared.can_submit_batch(kk):   # ring full: wait for the presenter (rank 0 keeps presenting meanwhile)
                 e2e_drain(target, False)
             slots = [shared.next_slot() for _ in range(kk)]
@@ -432,7 +440,7 @@ def main():
         e2e_drain(target, True)                  # presenter: every rank's rows of every frame have landed
         r.wait()
 
-    e2e_run(2 * KB, 0, False)
+    e2e_run(2 * KE, 0, False)
     barrier()
     t0 = time.perf_counter()
     e2e_run(args.steps, args.warmup, True)
@@ -650,6 +658,8 @@ def main():
                 "emulated": (f"rows of rank {peer.band_rank} of {emulate} only, on ONE GPU: value counts the WHOLE frame's pixels, i.e. it is "
                              f"the rate {emulate} such ranks would reach together if NVLink cost nothing - a tool output, not a bench line"
                              if emulate else None),
+                "diagnostic": ("--diag-local-frames: rows stored into each rank's own memory, frame never assembled - not a bench line"
+                               if (args.diag_local_frames and world > 1) else None),
                 "hit_pixel_fraction": tot["hits"] / max(1.0, tot["pixels"]),
                 "host_issue_ms_per_step": host_issue_ms,
                 "timed_region_ms_per_rank": per_rank_ms,
@@ -660,7 +670,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 36 + 36,
                     "d2h_bytes_per_step": W * H * 4 + 4 * world,
-                    "mode": (f"ore_render_async_signal: every rank copies its own row blocks into ONE shared pinned host frame ring "
+                    "mode": (f"ore_render_batch_async, {KE} frames per launch set: every rank copies its own row blocks into ONE shared pinned host frame ring "
                              f"({NHB} frames, POSIX shm registered with CUDA) over its own PCIe link, copy of frame f behind the kernels "
                              f"of f+1; per-rank completion counters in the same shared memory; the presenter's host thread consumes "
                              f"frames in order. Timed with CUDA events (first render -> last copy + flag landed), max over ranks"),

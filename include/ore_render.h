@@ -106,6 +106,7 @@ typedef struct ore_counters {
     uint64_t beam_l2;         /* (pixel, sphere, light) triples passing the per-pixel cone test */
     uint64_t primary_steps;   /* warp steps of the primary sweep: 32 tile-cone tests each (super / leaf / sphere) */
     uint64_t sweep_steps;     /* warp steps of the shadow sweep: 32 beam tests each                */
+    uint64_t sky_exact;       /* miss pixels whose sky texel needed the exact sequence (near a texel boundary / a pole) */
 } ore_counters;
 
 /* ---- lifetime ---------------------------------------------------------------------

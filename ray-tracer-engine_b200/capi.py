@@ -44,7 +44,7 @@ class OreFrame(C.Structure):
 class OreCounters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "pixels", "hit_pixels", "primary_tests", "shadow_tests_ref", "sky_tests",
-        "exact_primary", "exact_shadow", "kernel_launches", "beam_l1", "beam_l2", "primary_steps", "sweep_steps")]
+        "exact_primary", "exact_shadow", "kernel_launches", "beam_l1", "beam_l2", "primary_steps", "sweep_steps", "sky_exact")]
 
 
 class OreError(RuntimeError):

@@ -73,6 +73,7 @@ struct ore_context {
     LightP lights[MAX_LIGHTS];
     float* tex[3] = {nullptr, nullptr, nullptr};
     int tex_w = 0, tex_h = 0;
+    bool tex_finite = false;   // every texel of the object texture is finite (checked at upload; FrameParams::skip_dark)
     float* sky[3] = {nullptr, nullptr, nullptr};
     int sky_w = 0, sky_h = 0;
     float sky_radius = 0.f;
@@ -568,6 +569,17 @@ extern "C" int ore_set_texture(ore_context* ctx, const float* r, const float* g,
     if (rc) return rc;
     ctx->tex_w = width;
     ctx->tex_h = height;
+    // (0 x texel must be 0 for lights that do not face a pixel to be skippable: see FrameParams::skip_dark)
+    bool finite = true;
+    const size_t n = (size_t)width * height;
+    const float* planes[3] = {r, g, b};
+    for (int c = 0; c < 3 && finite; c++)
+        for (size_t i = 0; i < n; i++)
+            if (!std::isfinite(planes[c][i])) {
+                finite = false;
+                break;
+            }
+    ctx->tex_finite = finite;
     return ORE_OK;
 }
 
@@ -586,7 +598,7 @@ extern "C" int ore_set_sky(ore_context* ctx, const float* r, const float* g, con
 static constexpr int TILE_ROWS = TILE_P;   // rows per tile of the primary kernel
 // shared memory of the primary kernel: the leaf / super-cluster cone records always, the sphere-level records when
 // everything stays within this budget (6 CTAs of 128 threads per SM)
-static constexpr size_t PRIMARY_RESIDENT_BYTES = 36 * 1024;
+static constexpr size_t PRIMARY_RESIDENT_BYTES = 30 * 1024;
 
 template <typename K>
 static int grid_for(ore_context* ctx, K kernel, size_t smem, int* grid, int threads = CTA_THREADS) {
@@ -805,6 +817,12 @@ static int render_impl(ore_context* ctx, const ore_camera* cams, int n_frames, c
     prm.n_tris = ctx->n_tris;
     prm.n_boxes = ctx->n_boxes;
     prm.mesh_has_normals = ctx->mesh_has_normals;
+    {
+        bool skip = ctx->tex_finite && !(fr->flags & ORE_FLAG_EXHAUSTIVE);
+        for (int i = 0; i < ctx->n_lights && skip; i++)
+            skip = std::isfinite(ctx->lights[i].r) && std::isfinite(ctx->lights[i].g) && std::isfinite(ctx->lights[i].b);
+        prm.skip_dark = skip ? 1 : 0;
+    }
     prm.hit_list = ctx->hit_list;
     prm.hit_ids = ctx->hit_ids;
     prm.hit_ts = ctx->hit_ts;
@@ -1300,6 +1318,7 @@ extern "C" int ore_get_counters(ore_context* ctx, ore_counters* out) {
     out->beam_l2 = c[CNT_BEAM_L2];
     out->primary_steps = c[CNT_PRIMARY_STEPS];
     out->sweep_steps = c[CNT_SWEEP_STEPS];
+    out->sky_exact = c[CNT_SKY_EXACT];
     return ORE_OK;
 }
 

@@ -43,7 +43,8 @@ enum CounterSlot {
     CNT_PRIMARY_CURSOR = 8,  // tile-batch cursor of the primary kernel
     CNT_PRIMARY_STEPS = 9,   // warp steps of the primary sweep (32 cone tests each)
     CNT_SWEEP_STEPS = 10,    // warp steps of the shadow sweep (32 beam tests each)
-    CNT_STAGE_A0 = 11,                         // per-chunk block cursors of shade_setup_kernel
+    CNT_SKY_EXACT = 11,      // miss pixels whose sky texel needed the exact sequence (the rest: sky_fast)
+    CNT_STAGE_A0 = 12,                         // per-chunk block cursors of shade_setup_kernel
     CNT_STAGE_B0 = CNT_STAGE_A0 + 32,          // per-chunk block cursors of the staged shadow_sweep_kernel
     CNT_SLOTS = CNT_STAGE_B0 + 32
 };
@@ -136,6 +137,11 @@ struct FrameParams {
     const int* box_offsets;
     const int* box_indices;
     int n_tris, n_boxes, mesh_has_normals;
+    // 1: a light whose castLightRay factor a = normal.toL is not > 0 contributes exactly +0 to the pixel whatever its
+    // shadow rays do (kernel.cu:1541-1542, 1673-1675: b *= a > 0 ? a : 0 with b finite, then b * colour * texel with
+    // finite colours and texels), so its directions and its sweep are skipped.  0 (exhaustive mode, or a non-finite
+    // light colour / texel somewhere): every light is evaluated in full.
+    int skip_dark;
     // tools only (env ORE_DEBUG_BLOCK_CYCLES at ore_create): SM clocks spent on every hit-list block, [2][dbg_cap]
     // (0: shade_setup_kernel, 1: staged shadow_sweep_kernel); null on every product path
     uint32_t* dbg_cycles;
@@ -381,6 +387,26 @@ __device__ __noinline__ void triangle_attributes(const float* __restrict__ tri, 
 }
 
 // ------------------------------------------------------------------------------------
+// light_facing: a = dot(normal, toL) exactly as castLightRay ends up computing it (kernel.cu:1541).  toL is
+// normalise(l.pos - start) (:1438), re-normalised IN PLACE twice per sample (:1465-1466), i.e. 20 times per light;
+// once two normalisations reproduce their input bit for bit the remaining ones do too, so the chain stops there.
+// Costs a few normalisations - against ~2500 warp instructions for the ten directions of a light whose contribution
+// is then multiplied by zero.
+// ------------------------------------------------------------------------------------
+__device__ __noinline__ float light_facing(float lpx, float lpy, float lpz, const v3 start, const v3 normal) {
+    v3 tmp = ref_sub(mk(lpx, lpy, lpz), start);
+    v3 toL = ref_normalise(tmp);
+#pragma unroll 1
+    for (int j = 0; j < 10; j++) {
+        const v3 prev = toL;
+        ref_normalise(toL);
+        ref_normalise(toL);
+        if (same_bits(toL, prev)) break;
+    }
+    return ref_dot(normal, toL);
+}
+
+// ------------------------------------------------------------------------------------
 // light_directions_reuse: one light, one copy of the code (instruction-cache friendly), same exact reuse
 // of angle / rotate() matrix while toL repeats bit for bit.  Returns a = dot(normal, toL_final).
 // ------------------------------------------------------------------------------------
@@ -545,15 +571,26 @@ __global__ void __launch_bounds__(STAGE_A_THREADS, ORE_STAGE_A_MIN_CTAS) shade_s
             __align__(16) float d[32];
             float a = 0.f;
             float4 cn = make_float4(0.f, 0.f, 0.f, -1.f);
-            if (valid) {
-                LightP L;
+            float* __restrict__ q = sp + (size_t)(STAGE_HEADER + STAGE_PER_LIGHT * li) * 32u;
+            LightP L;
+            {
                 const LightP* __restrict__ src = &prm.lights[0];
                 L.px = src[li].px; L.py = src[li].py; L.pz = src[li].pz; L.size = src[li].size;
                 L.r = src[li].r; L.g = src[li].g; L.b = src[li].b;
+            }
+            if (prm.skip_dark) {
+                // a light that faces none of the block's pixels (a > 0 nowhere) adds +0 to each of them: only `a` is
+                // staged, the sweep skips the light as well
+                if (valid) a = light_facing(L.px, L.py, L.pz, start, normal);
+                if (!__any_sync(0xffffffffu, valid && a > 0.f)) {
+                    q[128] = a;
+                    continue;
+                }
+            }
+            if (valid) {
                 a = light_directions_reuse(L, start, normal, d);
                 cn = cone_of10(d);
             }
-            float* __restrict__ q = sp + (size_t)(STAGE_HEADER + STAGE_PER_LIGHT * li) * 32u;
             q[0] = cn.x;
             q[32] = cn.y;
             q[64] = cn.z;

@@ -15,7 +15,11 @@
 //                              tile - nothing is written for miss pixels;
 //                           4. the sky (skybox::getFColor, kernel.cu:1146-1166) for the tile's miss pixels in a QUAD
 //                              layout: every lane owns four consecutive pixels of a row and stores them with one 128-bit
-//                              store (hit pixels of a quad are written as 0 and overwritten by the shadow pass).
+//                              store (hit pixels of a quad are written as 0 and overwritten by the shadow pass).  The
+//                              texel index is a piecewise constant function of the direction: a cheap approximate
+//                              evaluation (sky_fast) decides it wherever the pixel lies clear of a texel boundary by
+//                              more than its own error bound; the few pixels near a boundary (and those near the
+//                              poles) are queued in shared memory and run the exact sequence 32 at a time.
 //                         Warps fetch tiles dynamically (tile cost varies ~8x between sky and sphere tiles).
 #pragma once
 
@@ -135,6 +139,106 @@ __device__ __noinline__ uint32_t sky_pixel(const SkyArgs sk, const CamP cam, flo
     return ref_rgb_to_int((int)(r * 254.f), (int)(g * 254.f), (int)(b * 254.f));
 }
 
+// ------------------------------------------------------------------------------------
+// sky_fast: conservative shortcut for skybox::getFColor.  The exact sequence (sky_pixel above) computes
+//   n = normalise(O + D t), t = the NEAR root of the sky sphere (negative: kernel.cu:346-351 keeps the smaller root, so the
+//   sky is looked up BEHIND the ray), sx = (int)((1 + atan2f(n.z, n.x) / 3.1415f) 0.5f w), sy = (int)(acosf(n.y) / 3.1415f h)
+// and fetches texel sy * w + sx.  sky_fast evaluates u ~ (1 + phi/3.1415) w/2 and v ~ theta/3.1415 h with fused
+// arithmetic, MUFU reciprocals / square roots and a degree-13 polynomial arctangent, and accepts its own (floor(u), floor(v))
+// only when u and v lie further than Eu, Ev from the next integer:
+//   direction error  |n~ - n| <= 8e-6 (budget: 1e-6 for D~ against the reference's float D, 0.7e-6 for t~ - relative
+//                    error 1e-6 times |O|/R <= 0.5, guarded per frame - and 0.7e-6 for the roundings of both paths: 2.4e-6,
+//                    x3), which moves phi and theta by at most 8e-6 / rho, rho = |(n.x, n.z)| (pixels with rho < 0.02, i.e.
+//                    within 1.2 degrees of a pole, always take the exact path);
+//   angle error      4e-6 rad for the polynomial (3.2e-7 evaluated in float, tests/test_sky_filter_cpu.py), the approximate
+//                    reciprocal (1.2e-7), the quadrant fix-ups (2.4e-7) and the 1-ulp error of either libm's atan2f / acosf
+//                    (2.4e-7; 2 ulp for CUDA's in the FAST_LIBM build) - under 1e-6 in total;
+//   float roundings  of the u, v expressions on both sides: < 2.7e-7 (w or h) texels, budgeted 1e-6 (w or h) + 1e-4.
+// NaNs fail every comparison and fall through to the exact path.
+// ------------------------------------------------------------------------------------
+struct SkyFast {
+    float Ox, Oy, Oz, cp, sp, cy, sy, fz, fz2;
+    float c;                  // O.O - R^2  (R^2 = sky_radius^2: the squared member, kernel.cu:334)
+    float ku, hw, kv;         // u = phi * ku + hw, v = theta * kv
+    float eu0, eu1, ev0, ev1; // Eu = eu0 + eu1 / rho, Ev = ev0 + ev1 / rho
+    int ok;                   // 0: exact path for every pixel (exhaustive mode, camera not well inside the sky sphere)
+};
+__device__ __forceinline__ SkyFast make_sky_fast(const CamP& cam, float fz, int w, int h, float sky_radius, bool enabled) {
+    SkyFast s;
+    s.Ox = cam.Ox; s.Oy = cam.Oy; s.Oz = cam.Oz;
+    s.cp = cam.cp; s.sp = cam.sp; s.cy = cam.cy; s.sy = cam.sy;
+    s.fz = fz;
+    s.fz2 = fz * fz;
+    const float R2 = sky_radius * sky_radius;
+    const float OO = fmaf(cam.Ox, cam.Ox, fmaf(cam.Oy, cam.Oy, cam.Oz * cam.Oz));
+    s.c = OO - R2;
+    s.ku = 0.5f * (float)w / 3.1415f;
+    s.hw = 0.5f * (float)w;
+    s.kv = (float)h / 3.1415f;
+    s.eu1 = 8e-6f * s.ku;
+    s.eu0 = fmaf(4e-6f, s.ku, fmaf(1e-6f, (float)w, 1e-4f));
+    s.ev1 = 8e-6f * s.kv;
+    s.ev0 = fmaf(4e-6f, s.kv, fmaf(1e-6f, (float)h, 1e-4f));
+    // the camera well inside a sky sphere of sane size: the near root is the negative one and |O| / R <= 0.5
+    s.ok = (enabled && R2 >= 1.f && R2 < 1e30f && OO <= 0.25f * R2 && fabsf(cam.cp) <= 1.f && fabsf(cam.sp) <= 1.f &&
+            fabsf(cam.cy) <= 1.f && fabsf(cam.sy) <= 1.f && w > 0 && h > 0 && w <= 65536 && h <= 65536) ? 1 : 0;
+    return s;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// atan2(y, x) for (x, y) != (0, 0), absolute error < 1e-6: a / b = min / max of the magnitudes, odd polynomial on [0, 1]
+__device__ __forceinline__ float atan2_approx(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float a = mn * rcp_approx(mx);
+    const float q = a * a;
+    float p = 0.006791701540350914f;
+    p = fmaf(p, q, -0.03352927789092064f);
+    p = fmaf(p, q, 0.07951410859823227f);
+    p = fmaf(p, q, -0.132254496216774f);
+    p = fmaf(p, q, 0.19804944097995758f);
+    p = fmaf(p, q, -0.3331688940525055f);
+    p = fmaf(p, q, 0.9999958276748657f);
+    float r = p * a;
+    if (ay > ax) r = 1.57079632679f - r;
+    if (x < 0.f) r = 3.14159265359f - r;
+    return y < 0.f ? -r : r;
+}
+// returns true and the pixel when the texel is decided without the exact sequence
+__device__ __forceinline__ bool sky_fast(const SkyFast& s, const float* __restrict__ tr, const float* __restrict__ tg,
+                                         const float* __restrict__ tb, int w, int h, float dx, float dy, uint32_t& px) {
+    // primary direction (kernel.cu:1624-1631, 252-255), approximately
+    const float inv = rsqrt_approx(fmaf(dx, dx, fmaf(dy, dy, s.fz2)));
+    const float nx0 = dx * inv, ny0 = dy * inv, nz0 = s.fz * inv;
+    const float Dy = fmaf(ny0, s.cp, -(nz0 * s.sp));
+    const float z1 = fmaf(ny0, s.sp, nz0 * s.cp);
+    const float Dx = fmaf(nx0, s.cy, z1 * s.sy);
+    const float Dz = fmaf(-nx0, s.sy, z1 * s.cy);
+    // near root of |O + D t| = R with A = |D|^2 ~ 1:  t = -(b + sqrt(b^2 - c)),  b = D.O,  c = O.O - R^2 < 0
+    const float b = fmaf(Dx, s.Ox, fmaf(Dy, s.Oy, Dz * s.Oz));
+    const float t = -(b + sqrt_approx(fmaf(b, b, -s.c)));
+    const float hx = fmaf(Dx, t, s.Ox), hy = fmaf(Dy, t, s.Oy), hz = fmaf(Dz, t, s.Oz);
+    const float hinv = rsqrt_approx(fmaf(hx, hx, fmaf(hy, hy, hz * hz)));
+    const float nx = hx * hinv, ny = hy * hinv, nz = hz * hinv;
+    const float rho2 = fmaf(nx, nx, nz * nz);
+    if (!(rho2 > 4e-4f)) return false;                 // within 1.2 degrees of a pole (or NaN)
+    const float irho = rsqrt_approx(rho2);
+    const float rho = rho2 * irho;
+    const float u = fmaf(atan2_approx(nz, nx), s.ku, s.hw);
+    const float v = atan2_approx(rho, ny) * s.kv;      // theta = acos(n.y) = atan2(rho, n.y) for a unit n (|n|^2 - 1 <= 4e-7: inside the budget)
+    const float fu = floorf(u), fv = floorf(v);
+    const float Eu = fmaf(s.eu1, irho, s.eu0), Ev = fmaf(s.ev1, irho, s.ev0);
+    const float du = u - fu, dv = v - fv;
+    if (!(du >= Eu && du <= 1.f - Eu && dv >= Ev && dv <= 1.f - Ev && fu >= 0.f && fv >= 0.f)) return false;
+    const int index = clamp_index((int)fv * w + (int)fu, w * h);
+    const float r = __ldg(&tr[index]), g = __ldg(&tg[index]), bl = __ldg(&tb[index]);
+    px = ref_rgb_to_int((int)(r * 254.f), (int)(g * 254.f), (int)(bl * 254.f));
+    return true;
+}
+
 // tile cone against a staged record: candidate iff A.M + W <= 0
 __device__ __forceinline__ bool cone_touches(float ax, float ay, float az, const float4 rec) {
     return fmaf(ax, rec.x, fmaf(ay, rec.y, fmaf(az, rec.z, rec.w))) <= 0.f;
@@ -147,6 +251,10 @@ __global__ void __launch_bounds__(PRIMARY_THREADS, ORE_PRIMARY_MIN_CTAS) primary
     __shared__ uint32_t warp_tot[PRIMARY_WARPS];
     __shared__ uint32_t cta_base;
     __shared__ int s_batch;
+    // sky phase: the tile's pixels (row p, column c at p * 32 + c) and the queue of pixels that need the exact sequence
+    __shared__ __align__(16) uint32_t s_tile[PRIMARY_WARPS][32 * P];
+    __shared__ uint8_t s_queue[PRIMARY_WARPS][32 * P];
+    static_assert(32 * P <= 256, "queue entries are bytes");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     // ---- the cone records of ONE frame at a time are staged in shared memory: [supers][leaves][spheres, when they fit]
@@ -174,7 +282,7 @@ __global__ void __launch_bounds__(PRIMARY_THREADS, ORE_PRIMARY_MIN_CTAS) primary
     const bool pitch_ok = (prm.pitch & 3) == 0;
     const SkyArgs sk = {prm.sky_r, prm.sky_g, prm.sky_b, prm.sky_w, prm.sky_h, prm.sky_radius, prm.ez};
     unsigned long long n_exact = 0;
-    unsigned int n_steps = 0;
+    unsigned int n_steps = 0, n_sky_exact = 0;
 
     // batches of PRIMARY_WARPS adjacent tiles of one frame, fetched dynamically (tile cost varies ~8x between sky and
     // sphere tiles); the CTA appends the hit records of a batch with ONE atomic, so neighbouring tiles stay neighbours in
@@ -340,11 +448,18 @@ __global__ void __launch_bounds__(PRIMARY_THREADS, ORE_PRIMARY_MIN_CTAS) primary
         }
 
         // ---- sky for the miss pixels, quad layout: lane L owns pixels x4 .. x4+3 of row 4h + L/8 and stores them
-        //      with one 128-bit store (hit pixels of a quad are written as 0; the shadow pass overwrites them) ----
+        //      with one 128-bit store (hit pixels of a quad are written as 0; the shadow pass overwrites them).
+        //      Pass 1: sky_fast per pixel into the warp's tile buffer, undecided pixels into the queue; pass 2: the exact
+        //      sequence for the queue, 32 entries at a time; pass 3: the stores. ----
         uint32_t hmask[P];
 #pragma unroll
         for (int p = 0; p < P; p++) hmask[p] = __ballot_sync(0xffffffffu, best_id[p] >= 0);
         if (tile_ok) {
+            uint32_t* const tp = s_tile[warp];
+            uint8_t* const tq = s_queue[warp];
+            const SkyFast sf = make_sky_fast(cam, prm.fz, prm.sky_w, prm.sky_h, prm.sky_radius, !EXH);
+            const int x4 = tx * 32 + 4 * (lane & 7);
+            uint32_t n_q = 0;
 #pragma unroll 1
             for (int h = 0; h < P / 4; h++) {
                 const int pr = 4 * h + (lane >> 3);
@@ -357,27 +472,62 @@ __global__ void __launch_bounds__(PRIMARY_THREADS, ORE_PRIMARY_MIN_CTAS) primary
                         dy = dyp[p];
                     }
                 const int k = ty * P + pr;
-                const int x4 = tx * 32 + 4 * (lane & 7);
                 const uint32_t hits4 = (hm >> (4 * (lane & 7))) & 0xFu;
+                uint4 px = make_uint4(0u, 0u, 0u, 0u);
+                uint32_t need = 0;
                 if (k < prm.n_rows && x4 < prm.W) {
                     const float4 dx4 = *reinterpret_cast<const float4*>(&prm.dx_tab[x4]);
-                    const float dxs[4] = {dx4.x, dx4.y, dx4.z, dx4.w};
-                    uint32_t px[4];
-#pragma unroll
+                    // (rolled, with selects instead of indexed registers: ONE copy of sky_fast in the instruction stream)
+#pragma unroll 1
                     for (int j = 0; j < 4; j++) {
-                        px[j] = 0u;
-                        if (!((hits4 >> j) & 1u) && x4 + j < prm.W) px[j] = sky_pixel(sk, cam, dxs[j], dy);
+                        if (!((hits4 >> j) & 1u) && x4 + j < prm.W) {
+                            const float dxj = j == 0 ? dx4.x : (j == 1 ? dx4.y : (j == 2 ? dx4.z : dx4.w));
+                            uint32_t pj = 0u;
+                            if (!sf.ok || !sky_fast(sf, sk.r, sk.g, sk.b, sk.w, sk.h, dxj, dy, pj)) need |= 1u << j;
+                            px.x = j == 0 ? pj : px.x;
+                            px.y = j == 1 ? pj : px.y;
+                            px.z = j == 2 ? pj : px.z;
+                            px.w = j == 3 ? pj : px.w;
+                        }
                     }
+                }
+                *reinterpret_cast<uint4*>(&tp[pr * 32 + 4 * (lane & 7)]) = px;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const bool nd = (need >> j) & 1u;
+                    const uint32_t bal = __ballot_sync(0xffffffffu, nd);
+                    if (nd) tq[n_q + __popc(bal & ((1u << lane) - 1u))] = (uint8_t)(pr * 32 + 4 * (lane & 7) + j);
+                    n_q += __popc(bal);
+                }
+            }
+            __syncwarp();
+#pragma unroll 1
+            for (uint32_t q0 = 0; q0 < n_q; q0 += 32) {
+                if (q0 + lane < n_q) {
+                    const int e = tq[q0 + lane];
+                    const int kq = min(ty * P + (e >> 5), prm.n_rows - 1);
+                    tp[e] = sky_pixel(sk, cam, prm.dx_tab[tx * 32 + (e & 31)], prm.dy_tab[kq]);
+                }
+            }
+            __syncwarp();
+#pragma unroll 1
+            for (int h = 0; h < P / 4; h++) {
+                const int pr = 4 * h + (lane >> 3);
+                const int k = ty * P + pr;
+                if (k < prm.n_rows && x4 < prm.W) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(&tp[pr * 32 + 4 * (lane & 7)]);
                     uint32_t* dst = frame_px + out_index(prm, k, x4);
                     if (vec_ok && x4 + 3 < prm.W) {
-                        *reinterpret_cast<uint4*>(dst) = make_uint4(px[0], px[1], px[2], px[3]);  // 128-bit RGBA store
+                        *reinterpret_cast<uint4*>(dst) = v;  // 128-bit RGBA store
                     } else {
+                        const uint32_t pv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                         for (int j = 0; j < 4; j++)
-                            if (x4 + j < prm.W) dst[j] = px[j];
+                            if (x4 + j < prm.W) dst[j] = pv[j];
                     }
                 }
             }
+            n_sky_exact += n_q;
         }
 
         // ---- hit records, grouped by hit primitive (ascending id), row-major inside a group, so that the 32
@@ -437,6 +587,7 @@ __global__ void __launch_bounds__(PRIMARY_THREADS, ORE_PRIMARY_MIN_CTAS) primary
     }
     if (n_exact) atomicAdd(&prm.counters[CNT_EXACT_PRIMARY], n_exact);
     if (lane == 0 && n_steps) atomicAdd(&prm.counters[CNT_PRIMARY_STEPS], (unsigned long long)n_steps);
+    if (lane == 0 && n_sky_exact) atomicAdd(&prm.counters[CNT_SKY_EXACT], (unsigned long long)n_sky_exact);
 }
 
 // ------------------------------------------------------------------------------------

@@ -21,6 +21,12 @@
 //    The sphere / cluster records are therefore read through L1 (34 KB hot at 1024 spheres) instead of a per-CTA
 //    shared-memory copy.
 //
+//  * Lights that face none of a block's pixels are skipped altogether (FrameParams::skip_dark): castLightRay multiplies
+//    its sample count by max(0, normal.toL) (kernel.cu:1541-1542), so such a light adds exactly +0 whatever its shadow
+//    rays do.  Stage A stages only `a` for it, the sweep neither copies its directions nor walks the spheres; a lane whose
+//    own a is not > 0 drops out of a light the rest of its block still needs.  About half of all (pixel, light) pairs of
+//    the benchmark scenes.
+//
 // The filters are those of DESIGN.md 2.1-2.5 unchanged (beam -> per-pixel cone -> per-ray -> sure hit -> exact
 // sequence); only their schedule differs, and the any-hit result does not depend on the order spheres are visited in.
 #pragma once
@@ -96,11 +102,25 @@ __global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_CTAS) shadow_sweep_ke
         seq_issued++;
     };
 
+    // lights that face at least one pixel of stage block wblk (bit li); every light when nothing may be skipped
+    const uint32_t all_lights = NLI >= 32 ? 0xffffffffu : ((1u << NLI) - 1u);
+    const bool skip_dark = prm.skip_dark != 0 && !EXH;
+    auto lit_lights = [&](uint32_t wblk) -> uint32_t {
+        if (!STAGED || !skip_dark) return all_lights;
+        const float* __restrict__ a_at = st.buf + ((size_t)wblk * (size_t)st.nv + (size_t)(STAGE_HEADER + 4)) * 32u + lane;
+        uint32_t m = 0;
+#pragma unroll 1
+        for (int li = 0; li < NLI; li++)
+            if (__any_sync(0xffffffffu, a_at[(size_t)(STAGE_PER_LIGHT * li) * 32u] > 0.f)) m |= 1u << li;   // (lanes past the list hold a = 0)
+        return m;
+    };
+
     unsigned long long* const cursor = &prm.counters[STAGED ? CNT_STAGE_B0 + st.chunk : CNT_SHADOW_CURSOR];
     uint32_t wb = 0;
     if (lane == 0) wb = (uint32_t)atomicAdd(cursor, 1ull);
     wb = __shfl_sync(0xffffffffu, wb, 0);
-    bool have_first = false;   // the first light of block wb is already in flight
+    bool have_first = false;   // lit_cur describes block wb already, and its first lit light (if any) is in flight
+    uint32_t lit_cur = all_lights;
     for (;;) {
         if (STAGED && wb >= st.cap_blocks) break;
         const uint32_t blk = st.first_block + wb;  // fused: 0, or the first block past the staged chunks (catch-all)
@@ -108,7 +128,10 @@ __global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_CTAS) shadow_sweep_ke
         const uint32_t item = blk * 32u + lane;
         const bool valid = item < n_items;
         const long long dbg_t0 = prm.dbg_cycles ? clock64() : 0;
-        if (STAGED && NLI > 0 && !have_first) issue_dirs(wb, 0);
+        if (STAGED && !have_first) {
+            lit_cur = lit_lights(wb);
+            if (lit_cur) issue_dirs(wb, __ffs(lit_cur) - 1);
+        }
         // the next block is reserved one ahead (its first light is then copied while this block's last light is swept),
         // except near the end of the list / chunk, where a reserved block would wait behind this one while other warps run dry
         const bool ahead = (unsigned long long)(blk + 8192u) * 32ull < n_items && (!STAGED || wb + 8192u < st.cap_blocks);
@@ -146,20 +169,23 @@ __global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_CTAS) shadow_sweep_ke
         // group makes a beam as wide as the scene, which opens every leaf (measured: blocks of 4.7 ms at 16384 spheres).
         const uint32_t valid_mask = __ballot_sync(0xffffffffu, valid);
 
+        uint32_t lit_rem = STAGED ? lit_cur : all_lights;
+        have_first = false;
 #pragma unroll 1
-        for (int li = 0; li < NLI; li++) {
+        while (lit_rem) {
+            const int li = __ffs(lit_rem) - 1;
+            lit_rem &= lit_rem - 1;
             const float* __restrict__ dslot;   // this light's directions: component c of ray r at dslot[(3 r + c) * 32]
             float Ax = 0.f, Ay = 0.f, Az = 0.f, ca = 0.f, sa = 0.f, a_dot = 0.f, cmin = -1.f;
             bool force = false;   // the cone test cannot be used for this lane's bundle: every sphere is a candidate
             if (STAGED) {
-                // keep the copies one ahead: the next light of this block, or the first light of the reserved block
-                if (li + 1 < NLI) {
-                    issue_dirs(wb, li + 1);
+                // keep the copies one ahead: the next lit light of this block, or the first lit light of the reserved block
+                if (lit_rem) {
+                    issue_dirs(wb, __ffs(lit_rem) - 1);
                 } else if (ahead && wb_next < st.cap_blocks && (unsigned long long)(st.first_block + wb_next) * 32ull < n_items) {
-                    issue_dirs(wb_next, 0);
+                    lit_cur = lit_lights(wb_next);
+                    if (lit_cur) issue_dirs(wb_next, __ffs(lit_cur) - 1);
                     have_first = true;
-                } else {
-                    have_first = false;
                 }
                 const float* __restrict__ q = sp + (size_t)(STAGE_HEADER + STAGE_PER_LIGHT * li) * 32u;
                 if (valid) {
@@ -176,11 +202,17 @@ __global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_CTAS) shadow_sweep_ke
                 // fused form (catch-all / no staging memory): the lane computes its own bundle into the slot
                 float* ds = slots + lane;
                 __align__(16) float d[32];
-                if (valid) {
-                    LightP L;
+                LightP L;
+                {
                     const LightP* __restrict__ src = &prm.lights[0];
                     L.px = src[li].px; L.py = src[li].py; L.pz = src[li].pz; L.size = src[li].size;
                     L.r = src[li].r; L.g = src[li].g; L.b = src[li].b;
+                }
+                if (skip_dark) {
+                    if (valid) a_dot = light_facing(L.px, L.py, L.pz, start, normal);
+                    if (!__any_sync(0xffffffffu, valid && a_dot > 0.f)) continue;   // adds +0 to every pixel of the block
+                }
+                if (valid) {
                     a_dot = light_directions_reuse(L, start, normal, d);
                     const float4 cn = cone_of10(d);
                     Ax = cn.x;
@@ -193,8 +225,11 @@ __global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_CTAS) shadow_sweep_ke
                 __syncwarp();
                 dslot = ds;
             }
-            uint32_t blocked = valid ? 0u : 0x3ffu;
-            if (valid) {
+            // a lane this light does not face (a <= 0 or NaN: its contribution is multiplied by zero) takes no part
+            const bool takes_part = valid && !(skip_dark && !(a_dot > 0.f));
+            uint32_t blocked = takes_part ? 0u : 0x3ffu;
+            if (!takes_part) Ax = Ay = Az = 0.f;
+            if (takes_part) {
                 if (cmin > 0.5f && !EXH) {
                     const float cosa = cmin - 4e-6f;
                     const float sina = sqrtf(fmaxf(0.f, fmaf(-cosa, cosa, 1.f))) * 1.0001f + 1e-6f;

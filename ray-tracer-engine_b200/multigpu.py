@@ -152,7 +152,7 @@ class PeerFrame:
     ROW_BLOCK = ROW_BLOCK
     FLAG_BYTES = 4096
 
-    def __init__(self, renderer, width: int, height: int, n_buffers: int = 2, group=None, band_of=None):
+    def __init__(self, renderer, width: int, height: int, n_buffers: int = 2, group=None, band_of=None, local_frames=False):
         """band_of = (rank, world): render the rows THAT rank of THAT many ranks would own while the flags stay those
         of this process (single-process tools that look at one rank's share of a frame).
 
@@ -175,7 +175,10 @@ class PeerFrame:
         self.submitted = 0    # frames this rank has submitted
         self.presented = 0    # frames the presenter has enqueued for presentation (rank 0 only)
         self._shm = None
-        if self.rank == 0:
+        # local_frames (diagnostic only): every rank stores into ring buffers of its OWN memory - the frame is never
+        # assembled; isolates the cost of the NVLink stores from everything else in a multi-GPU measurement
+        self.local_frames = bool(local_frames)
+        if self.rank == 0 or self.local_frames:
             for _ in range(n_buffers):
                 p = renderer.dev_alloc(self.nbytes)
                 self._owned.append(p)
@@ -192,9 +195,10 @@ class PeerFrame:
             dist.broadcast_object_list(payload, src=0, group=group)
             if self.rank != 0:
                 self._shm = shared_memory.SharedMemory(name=payload[0][-1])
-                for handle in payload[0][:-1]:
-                    self._opened.append(renderer.ipc_import(handle))
-                self.ptrs = list(self._opened)
+                if not self.local_frames:
+                    for handle in payload[0][:-1]:
+                        self._opened.append(renderer.ipc_import(handle))
+                    self.ptrs = list(self._opened)
             self._flag_view = np.ndarray((self.FLAG_BYTES // 4,), dtype=np.uint32, buffer=self._shm.buf)
             base = self._flag_view.ctypes.data
             renderer.host_register(base, self.FLAG_BYTES)

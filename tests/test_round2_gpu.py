@@ -389,3 +389,89 @@ def test_batch_async_lands_frames_in_order_with_flags(renderer, pkg):
         for h_ in host:
             renderer.host_free(h_)
         renderer.host_free(flag)
+
+
+# ---- lights that do not face a pixel (a = normal.toL <= 0) add exactly +0 and are skipped (FrameParams::skip_dark) ----
+@pytest.mark.parametrize("case", ["below", "mixed", "one_of_three", "nan_colour"])
+def test_lights_facing_away_are_skipped_without_changing_a_pixel(case, renderer, oracle_best, pkg, libm_matches):
+    sc = pkg.scene.reference_scene(64, 1)
+    lights = sc.lights.copy()
+    if case == "below":
+        lights = lights[:1].copy()
+        lights[0, :3] = (5.0, -60.0, 5.0)        # under the scene: dark for every pixel seen from above -> whole blocks skipped
+    elif case == "mixed":
+        lights[0, :3] = (5.0, -60.0, 5.0)        # one light below, one level with the camera, one above
+        lights[1, :3] = (4.0, 3.0, 30.0)
+    elif case == "one_of_three":
+        lights[2, :3] = (-40.0, 2.0, 4.0)        # grazing from the side: the terminator crosses many blocks
+    elif case == "nan_colour":
+        lights[1, 4] = np.float32("nan")         # 0 x NaN is not 0: nothing may be skipped for this scene
+    sc2 = pkg.scene.Scene(spheres=sc.spheres, lights=np.ascontiguousarray(lights, dtype=np.float32), texture=sc.texture,
+                          sky=sc.sky, extent=sc.extent, name=f"dark_{case}")
+    cam = pkg.scene.reference_camera()
+    W, H = 200, 150
+    F = pkg.capi
+    renderer.set_scene(sc2)
+    a = renderer.render(cam, W, H)
+    for flags in (F.ORE_FLAG_EXHAUSTIVE, F.ORE_FLAG_FUSED_SHADOW):
+        b = renderer.render(cam, W, H, flags=flags)
+        assert np.array_equal(a, b), (case, flags, int(np.count_nonzero(a != b)))
+    if case != "nan_colour":      # (NaN -> int is implementation-defined on the host: out of the oracle's domain)
+        ref = oracle_best.render(sc2, cam, W, H)
+        if libm_matches:
+            assert np.array_equal(a, ref["pixels"]), (case, int(np.count_nonzero(a != ref["pixels"])))
+        else:
+            d = np.zeros(a.shape, dtype=np.int32)
+            for sh in (0, 8, 16):
+                d = np.maximum(d, np.abs(((a >> sh) & 255).astype(np.int32) - ((ref["pixels"] >> sh) & 255).astype(np.int32)))
+            assert np.count_nonzero(d <= 1) >= 0.999 * d.size
+    renderer.set_scene(sc)
+
+
+# ---- sky texel shortcut (sky_fast, csrc/ore_primary.cuh) against the oracle with an INDEX-ENCODING sky: every texel has
+# ---- its own colour, so a pixel that picked a neighbouring texel differs from the reference's frame ----
+def _index_sky(pkg, w, h):
+    i = np.arange(w * h, dtype=np.int64)
+    def chan(k):
+        return ((k.astype(np.float64) + 0.5) / 254.0).astype(np.float32).reshape(h, w)
+    return pkg.scene.Sprite(width=w, height=h, r=chan(i // 65025), g=chan((i // 255) % 255), b=chan(i % 255))
+
+
+SKY_CASES = [
+    # (sky w, h, sky size, camera org, yaw, pitch)
+    (1024, 512, 10000.0, (4.0, 3.0, 10.0), 180.0, -20.0),       # the reference's camera
+    (1024, 512, 10000.0, (4.0, 3.0, 10.0), 37.0, 88.5),         # a pole in view
+    (1024, 512, 10000.0, (4.0, 3.0, 10.0), 200.0, -89.0),       # the other pole
+    (300, 200, 10000.0, (-3.0, 12.0, 2.0), 301.0, 10.0),        # odd texture size
+    (4096, 2048, 10000.0, (4.0, 3.0, 10.0), 90.0, 0.0),         # texels smaller than pixels
+    (1024, 512, 10000.0, (3.0e7, 1.0e7, -2.0e7), 10.0, 5.0),    # camera a third of the way to the sky sphere
+    (1024, 512, 10000.0, (6.0e7, 0.0, 0.0), 10.0, 5.0),         # |O| > R/2: the shortcut must stand down
+    (512, 256, 3.0, (4.0, 3.0, 10.0), 180.0, -20.0),            # tiny sky sphere: camera outside it (NaN roots)
+    (512, 256, 0.5, (0.1, 0.0, 0.05), 45.0, 30.0),              # R^2 < 1
+]
+
+
+@pytest.mark.parametrize("case", range(len(SKY_CASES)))
+def test_sky_texel_shortcut_equals_the_oracle_with_an_index_encoding_sky(case, renderer, oracle_best, pkg, libm_matches):
+    w, h, size, org, yaw, pitch = SKY_CASES[case]
+    base = pkg.scene.reference_scene(64, 1)
+    sc = pkg.scene.Scene(spheres=base.spheres, lights=base.lights, texture=base.texture, sky=_index_sky(pkg, w, h),
+                         sky_size=size, extent=base.extent, name=f"index_sky_{case}")
+    cam = pkg.scene.Camera(org=org, yaw=yaw, pitch=pitch)
+    W, H = 333, 187
+    F = pkg.capi
+    renderer.set_scene(sc)
+    a = renderer.render(cam, W, H)
+    c = renderer.counters()
+    b = renderer.render(cam, W, H, flags=F.ORE_FLAG_EXHAUSTIVE)
+    assert np.array_equal(a, b), (case, int(np.count_nonzero(a != b)))
+    miss = c["pixels"] - c["hit_pixels"]
+    if case in (0, 3):
+        assert c["sky_exact"] < 0.25 * miss, (c["sky_exact"], miss)       # the shortcut decides most pixels
+    if case in (6, 7, 8):
+        assert c["sky_exact"] == miss, (c["sky_exact"], miss)             # ... and none where it must not be used
+    if case not in (7, 8):   # (degenerate sky spheres: NaN roots, the reference indexes its texture out of bounds - no oracle)
+        ref = oracle_best.render(sc, cam, W, H)
+        if libm_matches:
+            assert np.array_equal(a, ref["pixels"]), (case, int(np.count_nonzero(a != ref["pixels"])))
+    renderer.set_scene(base)
