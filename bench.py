@@ -223,6 +223,9 @@ def main():
                     help="tool, single process only: render just the rows rank --emulate-rank of this many ranks would "
                          "render (isolates per-rank effects of short frames from NVLink effects); the line says so")
     ap.add_argument("--emulate-rank", type=int, default=0)
+    ap.add_argument("--no-band-dma", action="store_true",
+                    help="N > 1: store every pixel straight into the presenter's frame from the kernels (ORE_FLAG_NO_BAND_DMA) "
+                         "instead of moving the primary kernel's rows with a copy engine - the A/B switch of that design choice")
     ap.add_argument("--diag-local-frames", action="store_true",
                     help="diagnostic, N > 1: every rank stores its rows into its own memory instead of the presenter's frame "
                          "(no NVLink stores; the frame is never assembled and the line says so)")
@@ -291,6 +294,8 @@ def main():
 
     n_batches_done = [0]
 
+    XF = F.ORE_FLAG_NO_BAND_DMA if args.no_band_dma else 0
+
     def render_steps(f0, n, flags=F.ORE_FLAG_NO_KERNEL_TIMING):
         """device-resident steps f0 .. f0+n-1: this rank's rows of those frames into the presenter's ring, KB frames per
         launch set, each batch announced by a flag"""
@@ -298,7 +303,7 @@ def main():
             kk = min(KB, n - b0)
             rr, st = ctxs[n_batches_done[0] % NF]
             n_batches_done[0] += 1
-            peer.submit_batch([camera(f0 + b0 + i) for i in range(kk)], stream=st.cuda_stream, flags=flags, renderer=rr)
+            peer.submit_batch([camera(f0 + b0 + i) for i in range(kk)], stream=st.cuda_stream, flags=flags | XF, renderer=rr)
             if rank == 0:
                 # presenter: on the present stream, wait for every rank's rows of the batch, then acknowledge it to all
                 peer.present_batch(present_stream.cuda_stream, kk)
@@ -652,8 +657,10 @@ def main():
                        f"{ws_mb:.0f} MB of framebuffer rows, hit records and shadow staging, x {NF * KB} frames in flight, L2 126 MB"),
                 "frame_overlap": (f"{KB} frames (cameras) per launch set (ore_render_batch_device / ore_render_batch_async), {NF} launch sets "
                                   f"in flight per GPU (contexts/streams used round-robin), ring of {NRING} presenter frames; the same at every N"),
-                "parallelism": (f"row-bands x{world} (8-row blocks dealt round-robin), presenter = rank 0; rows stored over NVLink into "
-                                f"the presenter's ring; completion = per-rank flags (no collective in the timed region)"
+                "parallelism": (f"row-bands x{world} (8-row blocks dealt round-robin), presenter = rank 0; rows land in the presenter's "
+                                f"ring over NVLink - " + ("every pixel stored by the kernels (--no-band-dma)" if args.no_band_dma else
+                                "the primary kernel's rows by copy engine behind the shadow pass, hit pixels stored by the sweep") +
+                                f"; completion = per-rank flags (no collective in the timed region)"
                                 if world > 1 else "1 GPU (same code path: frame ring + flags)"),
                 "emulated": (f"rows of rank {peer.band_rank} of {emulate} only, on ONE GPU: value counts the WHOLE frame's pixels, i.e. it is "
                              f"the rate {emulate} such ranks would reach together if NVLink cost nothing - a tool output, not a bench line"

@@ -102,6 +102,11 @@ struct ore_context {
     float* hit_t_map = nullptr;
     size_t map_cap = 0;
     unsigned long long* counters = nullptr;
+    // band DMA (ORE_FLAG_BAND_DMA): packed local rows of the primary kernel + the stream / events of their copy
+    uint32_t* band_buf = nullptr;
+    size_t band_cap = 0;   // pixels
+    cudaStream_t band_stream = nullptr;
+    cudaEvent_t ev_band_go = nullptr, ev_band_done = nullptr;
     float* stage = nullptr;  // staging buffer between the two kernels of the default shadow pass
     size_t stage_cap = 0;    // floats
     size_t stage_blocks_override = 0;  // test hook (env ORE_STAGE_BLOCKS at ore_create): staging capacity in 32-item blocks
@@ -283,8 +288,14 @@ extern "C" int ore_destroy(ore_context* ctx) {
             if (e) cudaEventDestroy(e);
         cudaStreamDestroy(ctx->signal_stream);
     }
+    if (ctx->band_stream) {
+        cudaStreamSynchronize(ctx->band_stream);
+        cudaEventDestroy(ctx->ev_band_go);
+        cudaEventDestroy(ctx->ev_band_done);
+        cudaStreamDestroy(ctx->band_stream);
+    }
     if (ctx->async_pool) cudaFree(ctx->async_pool);
-    void* dev[] = {ctx->stage, ctx->sph_exact, ctx->sph_xsort, ctx->sph_sort, ctx->sort_index, ctx->leaf_sph, ctx->super_sph,
+    void* dev[] = {ctx->band_buf, ctx->stage, ctx->sph_exact, ctx->sph_xsort, ctx->sph_sort, ctx->sort_index, ctx->leaf_sph, ctx->super_sph,
                    ctx->prim_sorted, ctx->cone_sorted, ctx->leaf_cone, ctx->super_cone, ctx->tex[0], ctx->tex[1], ctx->tex[2],
                    ctx->sky[0], ctx->sky[1], ctx->sky[2], ctx->dx_tab, ctx->dy_tab, ctx->hit_list, ctx->hit_ids, ctx->hit_ts,
                    ctx->hit_id_map, ctx->hit_t_map, ctx->pixels, ctx->counters, ctx->cubes, ctx->planes, ctx->tris, ctx->boxes,
@@ -668,7 +679,7 @@ static int render_impl(ore_context* ctx, const ore_camera* cams, int n_frames, c
         (fr->out_pitch != 0 && fr->out_pitch < fr->width))
         return fail(ctx, ORE_ERR_INVALID, "ore_render: bad frame geometry");
     if (fr->flags & ~(uint32_t)(ORE_FLAG_EXHAUSTIVE | ORE_FLAG_COUNT_REFERENCE_TESTS | ORE_FLAG_FAST_LIBM | ORE_FLAG_FUSED_SHADOW |
-                                ORE_FLAG_NO_KERNEL_TIMING))
+                                ORE_FLAG_NO_KERNEL_TIMING | ORE_FLAG_BAND_DMA | ORE_FLAG_NO_BAND_DMA))
         return fail(ctx, ORE_ERR_INVALID, "ore_render: unknown flag");
     if (!ctx->tex[0] || !ctx->sky[0]) return fail(ctx, ORE_ERR_INVALID, "ore_render: texture and sky must be set first");
     if (!ctx->sph_exact) {
@@ -744,6 +755,35 @@ static int render_impl(ore_context* ctx, const ore_camera* cams, int n_frames, c
         c.sy = sinf(yawRad);
         prm.pixels[f] = outs ? outs[f] : ctx->pixels;
         if (!prm.pixels[f]) return fail(ctx, ORE_ERR_INVALID, "ore_render: null framebuffer in the batch");
+        prm.sky_pixels[f] = prm.pixels[f];
+    }
+    prm.sky_pitch = prm.pitch;
+    prm.sky_global = prm.out_global;
+    // Band DMA (include/ore_render.h): rows whose 8-row blocks are contiguous at the destination (pitch == width) and
+    // whose destination is another GPU's memory - or any memory when forced
+    bool band_dma = false;
+    if (prm.out_global && fr->out_pitch == W && !(fr->flags & ORE_FLAG_NO_BAND_DMA)) {
+        band_dma = (fr->flags & ORE_FLAG_BAND_DMA) != 0;
+        if (!band_dma) {
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, outs[0]) == cudaSuccess)
+                band_dma = at.type == cudaMemoryTypeDevice && at.device != ctx->device;
+            (void)cudaGetLastError();
+        }
+    }
+    if (band_dma) {
+        if (n_px > ctx->band_cap || !ctx->band_buf) {
+            if ((rc = wait_last_render(ctx))) return rc;
+            if ((rc = ensure_dev(ctx, &ctx->band_buf, &ctx->band_cap, n_px))) return rc;
+        }
+        if (!ctx->band_stream) {
+            ORE_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->band_stream, cudaStreamNonBlocking));
+            ORE_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_band_go, cudaEventDisableTiming));
+            ORE_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_band_done, cudaEventDisableTiming));
+        }
+        for (int f = 0; f < n_frames; f++) prm.sky_pixels[f] = ctx->band_buf + (size_t)f * n_px_frame;
+        prm.sky_pitch = W;
+        prm.sky_global = 0;
     }
     {
         // largest half-angle of a 32 x TILE_ROWS pixel tile seen from the eye (tile cone of the primary
@@ -872,6 +912,35 @@ static int render_impl(ore_context* ctx, const ore_camera* cams, int n_frames, c
         ctx->last_launches++;
     }
     if (timing) ORE_CUDA(ctx, cudaEventRecord(ctx->ev[2], stream));
+    bool band_pending = false;
+    if (band_dma) {
+        // the rows the primary kernel has just written (sky pixels, 0 for hit pixels) travel to their place in the
+        // destination frames on a copy engine, behind the primary kernel and concurrently with stage A of the shadow
+        // pass; the sweep, which stores the hit pixels into the same rows, waits for them
+        ORE_CUDA(ctx, cudaEventRecord(ctx->ev_band_go, stream));
+        ORE_CUDA(ctx, cudaStreamWaitEvent(ctx->band_stream, ctx->ev_band_go, 0));
+        const int B = prm.y_block, S = prm.y_step;           // (1, 1 for a contiguous band)
+        const int full = n_rows / B, rem = n_rows % B;
+        for (int f = 0; f < n_frames; f++) {
+            const uint32_t* src = ctx->band_buf + (size_t)f * n_px_frame;
+            uint32_t* dst = outs[f];
+            if (full > 0)
+                ORE_CUDA(ctx, cudaMemcpy2DAsync(dst, (size_t)S * W * sizeof(uint32_t), src, (size_t)B * W * sizeof(uint32_t),
+                                                (size_t)B * W * sizeof(uint32_t), (size_t)full, cudaMemcpyDefault, ctx->band_stream));
+            if (rem > 0)
+                ORE_CUDA(ctx, cudaMemcpyAsync(dst + (size_t)full * S * W, src + (size_t)full * B * W,
+                                              (size_t)rem * W * sizeof(uint32_t), cudaMemcpyDefault, ctx->band_stream));
+        }
+        ORE_CUDA(ctx, cudaEventRecord(ctx->ev_band_done, ctx->band_stream));
+        band_pending = true;
+    }
+    auto join_band = [&]() -> int {
+        if (band_pending) {
+            ORE_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->ev_band_done, 0));
+            band_pending = false;
+        }
+        return ORE_OK;
+    };
     {
         // Two-stage pass (default): shade_setup_kernel -> staging buffer -> staged shadow_sweep_kernel.  The host does
         // not know the hit count (no sync): the first frame of a context sizes the staging buffer from the pixel count,
@@ -931,6 +1000,7 @@ static int render_impl(ore_context* ctx, const ore_camera* cams, int n_frames, c
         if (ctx->n_lights == 0) {
             // nothing to launch
         } else if (!staged) {
+            if ((rc = join_band())) return rc;
             if ((rc = launch_sweep(ctx, prm, st, false, exh, fast_libm, stream))) return rc;
             ctx->last_launches++;
         } else {
@@ -944,14 +1014,6 @@ static int render_impl(ore_context* ctx, const ore_camera* cams, int n_frames, c
             if (n_chunks > n_chunks_max) n_chunks = n_chunks_max;
             int grid_a = 0;
             if (!fast_libm && (rc = grid_for(ctx, shade_setup_kernel, 0, &grid_a, STAGE_A_THREADS))) return rc;
-            if (n_chunks < n_chunks_max) {
-                // catch-all: hit-list blocks beyond the staged chunks (normally none: exits at once), one fused launch
-                StageArgs rest{};
-                rest.first_block = (uint32_t)((size_t)n_chunks * cap_blocks);
-                rest.nv = st.nv;
-                if ((rc = launch_sweep(ctx, prm, rest, false, exh, fast_libm, stream))) return rc;
-                ctx->last_launches++;
-            }
             for (int c = 0; c < n_chunks; c++) {
                 st.chunk = c;
                 st.first_block = (uint32_t)((size_t)c * cap_blocks);
@@ -961,11 +1023,21 @@ static int render_impl(ore_context* ctx, const ore_camera* cams, int n_frames, c
                     shade_setup_kernel<<<grid_a, STAGE_A_THREADS, 0, stream>>>(prm, st);
                     ORE_CUDA(ctx, cudaGetLastError());
                 }
+                if ((rc = join_band())) return rc;   // (band DMA: the first stage A ran beside the copy)
                 if ((rc = launch_sweep(ctx, prm, st, true, exh, fast_libm, stream))) return rc;
                 ctx->last_launches += 2;
             }
+            if (n_chunks < n_chunks_max) {
+                // catch-all: hit-list blocks beyond the staged chunks (normally none: exits at once), one fused launch
+                StageArgs rest{};
+                rest.first_block = (uint32_t)((size_t)n_chunks * cap_blocks);
+                rest.nv = st.nv;
+                if ((rc = launch_sweep(ctx, prm, rest, false, exh, fast_libm, stream))) return rc;
+                ctx->last_launches++;
+            }
         }
     }
+    if ((rc = join_band())) return rc;   // (no lights: nothing but the copy writes the frames)
     if (timing) ORE_CUDA(ctx, cudaEventRecord(ctx->ev[3], stream));
     // hint for the next frame of this context (see hits_hint): 8 bytes, no synchronisation
     ORE_CUDA(ctx, cudaMemcpyAsync(ctx->hits_hint, ctx->counters + CNT_HITS, sizeof(unsigned long long),

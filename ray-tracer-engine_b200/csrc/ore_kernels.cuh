@@ -121,7 +121,13 @@ struct FrameParams {
     int32_t* hit_ids;     // nearest primitive
     float* hit_ts;        // nearest t
     unsigned long long* counters;
-    uint32_t* pixels[MAX_BATCH];   // one framebuffer per frame of the batch
+    uint32_t* pixels[MAX_BATCH];   // one framebuffer per frame of the batch (hit pixels: shadow pass)
+    // Where the primary kernel stores its rows (sky pixels, 0 for hit pixels).  Normally the same place.  When the
+    // framebuffers are ANOTHER GPU's memory (a rank of a multi-GPU job storing into the presenter's frame) the rows go
+    // to a packed band buffer in local memory instead and a copy engine moves them over NVLink while the shadow pass
+    // runs (ore_capi.cu: "band DMA"); only the hit pixels are then stored remotely by the sweep.
+    uint32_t* sky_pixels[MAX_BATCH];
+    int sky_pitch, sky_global;
     // "next" primitives (kernel.cu:360-509): cube i = 3 float4 {bounds[0], bounds[1], orgin}, plane i = 2 float4
     // {orgin, normal}; hit ids continue after the spheres: cube i -> n_spheres + i, plane i -> n_spheres + n_cubes + i
     const float4* cubes;
@@ -186,6 +192,9 @@ __device__ __forceinline__ int image_row_rel(const FrameParams& prm, int k) {
 }
 __device__ __forceinline__ size_t out_index(const FrameParams& prm, int k, int x) {
     return (size_t)(prm.out_global ? image_row_rel(prm, k) : k) * prm.pitch + x;
+}
+__device__ __forceinline__ size_t sky_out_index(const FrameParams& prm, int k, int x) {
+    return (size_t)(prm.sky_global ? image_row_rel(prm, k) : k) * prm.sky_pitch + x;
 }
 
 // direction r of a bundle stored with `stride` floats between components (1: contiguous [10][3]; 32: a column of a

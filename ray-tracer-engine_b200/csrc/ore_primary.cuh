@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(PRIMARY_THREADS, ORE_PRIMARY_MIN_CTAS) primary
     const int batches_per_frame = (total_tiles + PRIMARY_WARPS - 1) / PRIMARY_WARPS;
     const int n_batches = batches_per_frame * prm.n_frames;
     const int n_sph = prm.n_spheres, n_leaf = prm.n_leaves, n_sup = prm.n_supers;
-    const bool pitch_ok = (prm.pitch & 3) == 0;
+    const bool pitch_ok = (prm.sky_pitch & 3) == 0;
     const SkyArgs sk = {prm.sky_r, prm.sky_g, prm.sky_b, prm.sky_w, prm.sky_h, prm.sky_radius, prm.ez};
     unsigned long long n_exact = 0;
     unsigned int n_steps = 0, n_sky_exact = 0;
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(PRIMARY_THREADS, ORE_PRIMARY_MIN_CTAS) primary
         const v3 O = mk(cam.Ox, cam.Oy, cam.Oz);
         const DirArgs da = {prm.ez, cam.cp, cam.sp, cam.cy, cam.sy};
         const float4* __restrict__ prim_rec = prm.prim_sorted + (size_t)frame * prm.n_sort;
-        uint32_t* const frame_px = prm.pixels[frame];
+        uint32_t* const frame_px = prm.sky_pixels[frame];
         const bool vec_ok = pitch_ok && ((reinterpret_cast<uintptr_t>(frame_px) & 15u) == 0);
         const int tile_id = (batch - frame * batches_per_frame) * PRIMARY_WARPS + warp;
         const bool tile_ok = tile_id < total_tiles;
@@ -516,7 +516,7 @@ __global__ void __launch_bounds__(PRIMARY_THREADS, ORE_PRIMARY_MIN_CTAS) primary
                 const int k = ty * P + pr;
                 if (k < prm.n_rows && x4 < prm.W) {
                     const uint4 v = *reinterpret_cast<const uint4*>(&tp[pr * 32 + 4 * (lane & 7)]);
-                    uint32_t* dst = frame_px + out_index(prm, k, x4);
+                    uint32_t* dst = frame_px + sky_out_index(prm, k, x4);
                     if (vec_ok && x4 + 3 < prm.W) {
                         *reinterpret_cast<uint4*>(dst) = v;  // 128-bit RGBA store
                     } else {

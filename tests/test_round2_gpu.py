@@ -475,3 +475,49 @@ def test_sky_texel_shortcut_equals_the_oracle_with_an_index_encoding_sky(case, r
         if libm_matches:
             assert np.array_equal(a, ref["pixels"]), (case, int(np.count_nonzero(a != ref["pixels"])))
     renderer.set_scene(base)
+
+
+# ---- band DMA: primary rows through a packed local buffer + a copy engine, hit pixels stored by the sweep ------------
+@pytest.mark.parametrize("world,H", [(3, 203), (8, 270), (2, 64), (5, 37)])
+def test_band_dma_rows_equal_direct_stores(world, H, renderer, pkg):
+    """ORE_FLAG_BAND_DMA (what a rank uses automatically when the frame lives on another GPU) forced onto local memory:
+    every rank's 8-row blocks, including a partial last block and ranks with no rows, land exactly where the direct
+    stores put them - for batches, single frames, the fused form, and a frame with no lights (copy only)"""
+    import torch
+    sc = pkg.scene.scaled_scene(64, 2)
+    renderer.set_scene(sc)
+    W = 333
+    cams = [pkg.scene.orbit_camera(sc, f) for f in (5, 90, 170)]
+    want = [renderer.render(c, W, H).copy() for c in cams]
+    F = pkg.capi
+    for flags in (F.ORE_FLAG_BAND_DMA, F.ORE_FLAG_BAND_DMA | F.ORE_FLAG_FUSED_SHADOW, F.ORE_FLAG_BAND_DMA | F.ORE_FLAG_FAST_LIBM):
+        ref = want if not (flags & F.ORE_FLAG_FAST_LIBM) else [renderer.render(c, W, H, flags=F.ORE_FLAG_FAST_LIBM).copy() for c in cams]
+        frames = torch.full((len(cams), H, W), 0x5A5A5A5A, dtype=torch.int32, device="cuda:0")
+        for rank in range(world):
+            b = pkg.multigpu.block_band(rank, world, H)
+            renderer.render_batch_device(cams, W, H, [frames[i].data_ptr() + 4 * W * b["y0"] for i in range(len(cams))],
+                                         out_pitch=W, flags=flags, **b)
+        renderer.synchronize()
+        got = frames.cpu().numpy().view(np.uint32)
+        for i in range(len(cams)):
+            assert np.array_equal(got[i], ref[i]), (flags, i, int(np.count_nonzero(got[i] != ref[i])))
+    # single frame per call, one rank at a time, rows of the other ranks must stay untouched
+    frame = torch.full((H, W), 0x5A5A5A5A, dtype=torch.int32, device="cuda:0")
+    b = pkg.multigpu.block_band(world - 1, world, H)
+    renderer.render_device(cams[0], W, H, out_ptr=frame.data_ptr() + 4 * W * b["y0"], out_pitch=W, flags=F.ORE_FLAG_BAND_DMA, **b)
+    renderer.synchronize()
+    got = frame.cpu().numpy().view(np.uint32)
+    mine = np.zeros(H, dtype=bool)
+    mine[pkg.multigpu.block_rows(world - 1, world, H)] = True
+    assert np.array_equal(got[mine], want[0][mine])
+    assert np.all(got[~mine] == 0x5A5A5A5A)
+    # no lights: the copy is the only writer of the frame
+    renderer.set_lights(sc.lights[:0])
+    dark = renderer.render(cams[1], W, H).copy()
+    frame = torch.full((H, W), 0x5A5A5A5A, dtype=torch.int32, device="cuda:0")
+    for rank in range(world):
+        b = pkg.multigpu.block_band(rank, world, H)
+        renderer.render_device(cams[1], W, H, out_ptr=frame.data_ptr() + 4 * W * b["y0"], out_pitch=W, flags=F.ORE_FLAG_BAND_DMA, **b)
+    renderer.synchronize()
+    assert np.array_equal(frame.cpu().numpy().view(np.uint32), dark)
+    renderer.set_lights(sc.lights)

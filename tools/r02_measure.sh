@@ -43,10 +43,11 @@ echo "launches rc=$?" | tee -a $OUT/${TAG}_status.txt
 echo "== ncu --set full (one launch per kernel, frame 2)" | tee -a $OUT/${TAG}_status.txt
 for K in primary_tile_kernel shade_setup_kernel shadow_sweep_kernel; do
   # the third frame's launch of each kernel (launch-skip counts matching launches only)
-  # frame 0 launches 3 chunk pairs + catch-all (no hit-count hint yet), later frames one pair + the (empty) catch-all
+  # frame 0 launches 2 chunk pairs + catch-all (no hit-count hint yet), later frames one pair + the (empty) catch-all;
+  # tools/ncu_summary.py summarises the longest launch of a report
   SKIP=2; COUNT=1
-  [ $K = shade_setup_kernel ] && SKIP=4
-  [ $K = shadow_sweep_kernel ] && SKIP=6 && COUNT=2
+  [ $K = shade_setup_kernel ] && SKIP=3
+  [ $K = shadow_sweep_kernel ] && SKIP=5 && COUNT=2
   timeout 600 ncu --set full --import-source on --clock-control none -k regex:$K --launch-skip $SKIP --launch-count $COUNT \
       -o $OUT/${TAG}_ncu_${K}_${WL} -f python tools/profile_target.py --workload $WL --frames 3 > $OUT/${TAG}_ncu_${K}.log 2>&1
   echo "ncu $K rc=$?" | tee -a $OUT/${TAG}_status.txt
