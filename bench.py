@@ -223,9 +223,9 @@ def main():
                     help="tool, single process only: render just the rows rank --emulate-rank of this many ranks would "
                          "render (isolates per-rank effects of short frames from NVLink effects); the line says so")
     ap.add_argument("--emulate-rank", type=int, default=0)
-    ap.add_argument("--no-band-dma", action="store_true",
-                    help="N > 1: store every pixel straight into the presenter's frame from the kernels (ORE_FLAG_NO_BAND_DMA) "
-                         "instead of moving the primary kernel's rows with a copy engine - the A/B switch of that design choice")
+    ap.add_argument("--band-dma", action="store_true",
+                    help="N > 1: move the primary kernel's rows to the presenter with a copy engine (ORE_FLAG_BAND_DMA) instead "
+                         "of storing every pixel from the kernels - the A/B switch of that design choice (default: off)")
     ap.add_argument("--diag-local-frames", action="store_true",
                     help="diagnostic, N > 1: every rank stores its rows into its own memory instead of the presenter's frame "
                          "(no NVLink stores; the frame is never assembled and the line says so)")
@@ -294,7 +294,7 @@ def main():
 
     n_batches_done = [0]
 
-    XF = F.ORE_FLAG_NO_BAND_DMA if args.no_band_dma else 0
+    XF = F.ORE_FLAG_BAND_DMA if (args.band_dma and world > 1) else 0
 
     def render_steps(f0, n, flags=F.ORE_FLAG_NO_KERNEL_TIMING):
         """device-resident steps f0 .. f0+n-1: this rank's rows of those frames into the presenter's ring, KB frames per
@@ -658,8 +658,8 @@ def main():
                 "frame_overlap": (f"{KB} frames (cameras) per launch set (ore_render_batch_device / ore_render_batch_async), {NF} launch sets "
                                   f"in flight per GPU (contexts/streams used round-robin), ring of {NRING} presenter frames; the same at every N"),
                 "parallelism": (f"row-bands x{world} (8-row blocks dealt round-robin), presenter = rank 0; rows land in the presenter's "
-                                f"ring over NVLink - " + ("every pixel stored by the kernels (--no-band-dma)" if args.no_band_dma else
-                                "the primary kernel's rows by copy engine behind the shadow pass, hit pixels stored by the sweep") +
+                                f"ring over NVLink - " + ("the primary kernel's rows by copy engine behind the shadow pass, hit pixels stored by the sweep (--band-dma)"
+                                                        if args.band_dma else "every pixel stored by the render kernels") +
                                 f"; completion = per-rank flags (no collective in the timed region)"
                                 if world > 1 else "1 GPU (same code path: frame ring + flags)"),
                 "emulated": (f"rows of rank {peer.band_rank} of {emulate} only, on ONE GPU: value counts the WHOLE frame's pixels, i.e. it is "

@@ -56,14 +56,13 @@ enum ore_flags {
     /* Do not record the per-kernel CUDA events behind ore_get_kernel_ms for this call (five event records per
      * frame; throughput loops set this, ore_get_kernel_ms then reports zeros). */
     ORE_FLAG_NO_KERNEL_TIMING = 64,
-    /* Band DMA.  When the output framebuffers of ore_render_device / ore_render_batch_device are ANOTHER GPU's memory
-     * (out_pitch == width: a rank storing its rows into the presenter's frame), the primary kernel writes its rows into
-     * a packed local band buffer, a copy engine moves them over NVLink while the shadow pass runs, and only the hit
-     * pixels are stored remotely by the kernels.  Chosen automatically for peer memory: eight ranks' simultaneous
-     * 128-bit sky stores would otherwise saturate the presenter's NVLink ingress and stall the primary kernels.
-     * ORE_FLAG_BAND_DMA forces the mode for local memory too (tests), ORE_FLAG_NO_BAND_DMA forces direct stores. */
-    ORE_FLAG_BAND_DMA = 128,
-    ORE_FLAG_NO_BAND_DMA = 256
+    /* Band DMA (opt-in; ore_render_device / ore_render_batch_device with out_pitch == width).  The primary kernel writes
+     * its rows into a packed local band buffer, a copy engine moves them to their place in the destination frames behind
+     * the primary kernel and beside stage A of the shadow pass, and only the hit pixels are stored by the sweep.  Meant
+     * for a rank whose frames live in ANOTHER GPU's memory.  Measured on 8 x B200 (profiles/r02_scaling.md) it is no
+     * faster than storing every pixel from the kernels - the presenter's NVLink ingress is the limit either way - so
+     * nothing selects it automatically. */
+    ORE_FLAG_BAND_DMA = 128
 };
 
 typedef struct ore_context ore_context; /* opaque; owns device buffers, streams, pinned staging */

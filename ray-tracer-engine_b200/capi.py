@@ -19,7 +19,6 @@ ORE_FLAG_FAST_LIBM = 16
 ORE_FLAG_FUSED_SHADOW = 32
 ORE_FLAG_NO_KERNEL_TIMING = 64
 ORE_FLAG_BAND_DMA = 128
-ORE_FLAG_NO_BAND_DMA = 256
 
 EXPORTS = [
     "ore_create", "ore_destroy", "ore_abi_version", "ore_last_error",

@@ -679,7 +679,7 @@ static int render_impl(ore_context* ctx, const ore_camera* cams, int n_frames, c
         (fr->out_pitch != 0 && fr->out_pitch < fr->width))
         return fail(ctx, ORE_ERR_INVALID, "ore_render: bad frame geometry");
     if (fr->flags & ~(uint32_t)(ORE_FLAG_EXHAUSTIVE | ORE_FLAG_COUNT_REFERENCE_TESTS | ORE_FLAG_FAST_LIBM | ORE_FLAG_FUSED_SHADOW |
-                                ORE_FLAG_NO_KERNEL_TIMING | ORE_FLAG_BAND_DMA | ORE_FLAG_NO_BAND_DMA))
+                                ORE_FLAG_NO_KERNEL_TIMING | ORE_FLAG_BAND_DMA))
         return fail(ctx, ORE_ERR_INVALID, "ore_render: unknown flag");
     if (!ctx->tex[0] || !ctx->sky[0]) return fail(ctx, ORE_ERR_INVALID, "ore_render: texture and sky must be set first");
     if (!ctx->sph_exact) {
@@ -759,18 +759,8 @@ static int render_impl(ore_context* ctx, const ore_camera* cams, int n_frames, c
     }
     prm.sky_pitch = prm.pitch;
     prm.sky_global = prm.out_global;
-    // Band DMA (include/ore_render.h): rows whose 8-row blocks are contiguous at the destination (pitch == width) and
-    // whose destination is another GPU's memory - or any memory when forced
-    bool band_dma = false;
-    if (prm.out_global && fr->out_pitch == W && !(fr->flags & ORE_FLAG_NO_BAND_DMA)) {
-        band_dma = (fr->flags & ORE_FLAG_BAND_DMA) != 0;
-        if (!band_dma) {
-            cudaPointerAttributes at;
-            if (cudaPointerGetAttributes(&at, outs[0]) == cudaSuccess)
-                band_dma = at.type == cudaMemoryTypeDevice && at.device != ctx->device;
-            (void)cudaGetLastError();
-        }
-    }
+    // Band DMA (include/ore_render.h; opt-in): rows whose 8-row blocks are contiguous at the destination (pitch == width)
+    const bool band_dma = prm.out_global && fr->out_pitch == W && (fr->flags & ORE_FLAG_BAND_DMA) != 0;
     if (band_dma) {
         if (n_px > ctx->band_cap || !ctx->band_buf) {
             if ((rc = wait_last_render(ctx))) return rc;
