@@ -45,7 +45,7 @@ enum ore_flags {
      * algorithmic rate.  Costs one extra kernel; off on the timed path. */
     ORE_FLAG_COUNT_REFERENCE_TESTS = 2,
     /* Use CUDA's own cosf/sinf/acosf/atan2f instead of the glibc-bit-compatible device functions of the default
-     * path (csrc/ore_libm.cuh).  ~20 % faster; ids and t unchanged; pixels within 1 LSB of the default on
+     * path (csrc/ore_libm.cuh).  ~10 % faster; ids and t unchanged; pixels within 1 LSB of the default on
      * >= 99.9 % (measured 99.999 %) instead of bit-identical to the host-compiled reference. */
     ORE_FLAG_FAST_LIBM = 16,
     /* Shadow pass as ONE kernel (shading set-up + light directions + sweep in one warp program) instead of the

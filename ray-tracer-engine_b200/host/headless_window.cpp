@@ -2,7 +2,12 @@
 // window.h callbacks and a main() that drives onStart()/update() like wWinMain (window.cpp:57-84) does,
 // with a scripted camera orbit instead of the message pump, and writes the last frame as a PPM.
 //
-//   ore_headless [width height frames spheres out.ppm mesh.obj|- pipelined(0|1)]
+//   ore_headless [width height frames spheres out.ppm mesh.obj|- pipelined(0|1) present(copy|pointer)]
+//
+// present = copy (default): setPixelBuff memcpy's the frame like window.cpp:130-132 (one host thread: ~10 GB/s, i.e. 13 ms
+// for an 8K frame - the reference's window, not this path, then bounds the frame rate).  present = pointer: the "window"
+// keeps the pointer it is handed (valid until the frame after next in pipelined mode) and reads the pixels when it needs
+// them - what a consumer that encodes or uploads the frame would do.
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -17,13 +22,18 @@ namespace {
 struct RenderState {  // window.cpp:8-17
     int width = 0, height = 0;
     std::vector<unsigned int> buffmemory;
+    const unsigned int* front = nullptr;   // present = pointer: the last frame handed over
+    bool copy = true;
 } render;
 }
 
 int getScreenHeight() { return render.height; }
 int getScreenWidth() { return render.width; }
 void setPixelBuff(unsigned int* pixels) {  // window.cpp:130-132
-    memcpy(render.buffmemory.data(), pixels, sizeof(unsigned int) * render.width * render.height);
+    if (render.copy)
+        memcpy(render.buffmemory.data(), pixels, sizeof(unsigned int) * render.width * render.height);
+    else
+        render.front = pixels;
 }
 
 int main(int argc, char** argv) {
@@ -34,6 +44,7 @@ int main(int argc, char** argv) {
     const char* out = argc > 5 ? argv[5] : nullptr;
     if (argc > 6 && strcmp(argv[6], "-") != 0) oreSetMeshFile(argv[6]);
     const int pipelined = argc > 7 ? atoi(argv[7]) : 0;
+    render.copy = !(argc > 8 && strcmp(argv[8], "pointer") == 0);
     oreConfigurePresentation(pipelined);
     render.buffmemory.assign((size_t)render.width * render.height, 0u);
 
@@ -52,12 +63,14 @@ int main(int argc, char** argv) {
     }
     oreFlush();  // pipelined mode: the last frame is still in flight
     const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (!render.copy && render.front)   // (outside the timed region: checksum / PPM of the last frame)
+        memcpy(render.buffmemory.data(), render.front, sizeof(unsigned int) * render.width * render.height);
     unsigned long long sum = 0;
     for (unsigned v : render.buffmemory) sum += v;
     printf("{\"width\": %d, \"height\": %d, \"frames\": %d, \"spheres\": %d, \"ms_per_frame\": %.3f, \"mrays_per_s\": %.1f, "
-           "\"checksum\": %llu, \"pipelined\": %d}\n",
+           "\"checksum\": %llu, \"pipelined\": %d, \"present\": \"%s\"}\n",
            render.width, render.height, frames, spheres, sec / frames * 1e3,
-           (double)render.width * render.height * frames / sec / 1e6, sum, pipelined);
+           (double)render.width * render.height * frames / sec / 1e6, sum, pipelined, render.copy ? "copy" : "pointer");
     if (out) {
         FILE* fp = fopen(out, "wb");
         if (fp) {

@@ -101,3 +101,17 @@ def test_sprite_loads_ppm_and_bmp_into_the_reference_plane_format(tmp_path):
         assert rc == 0 and (ww.value, hh.value) == (w, h), path
         for got, exp in zip(planes, want):
             assert np.array_equal(got, exp), path
+
+
+@pytest.mark.gpu
+def test_headless_present_by_pointer_shows_the_same_frames(tmp_path):
+    """present = pointer (the window keeps the pointer update() hands it instead of memcpy'ing the frame) ends on the
+    same last frame as the reference-style copy, synchronous and pipelined"""
+    outs = []
+    for pipelined, present in ((0, "copy"), (1, "copy"), (1, "pointer"), (0, "pointer")):
+        out = tmp_path / f"p{pipelined}_{present}.ppm"
+        res = subprocess.run([os.path.join(HOST, "ore_headless"), "320", "200", "5", "64", str(out), "-", str(pipelined), present],
+                             capture_output=True, text=True, timeout=120)
+        assert res.returncode == 0, res.stderr
+        outs.append(out.read_bytes())
+    assert outs[0] == outs[1] == outs[2] == outs[3]
