@@ -1,10 +1,13 @@
 // ore_clusters.h - host-only: shadow-sweep clusters of the sphere set (no CUDA types; also compiled by the CPU tests).
 //
-// The spheres in Morton order of their centres, 32 per cluster, one bounding sphere per cluster.  The any-hit result
-// of a shadow ray does not depend on the order spheres are visited in, so the beam kernel walks clusters first (one
-// per lane) and only opens the ones its beams can touch.  Soundness rests on one property, which
-// tests/test_clusters_cpu.py checks: every member ball (centre, R') lies inside its cluster's ball, or the cluster's
-// radius is +inf ("always open": a member with non-finite or >= 1e15 coordinates / radius).
+// The spheres in Morton order of their centres with two levels of bounding balls over them: LEAVES of 8 consecutive
+// spheres and SUPER-clusters of 32 consecutive leaves (build_hierarchy below; build_clusters also returns round 1's
+// 32-sphere cluster balls, which only the containment test still looks at).  Neither the any-hit result of a shadow ray
+// nor - with candidates adjudicated by (t, original index) - the nearest hit depends on the order spheres are visited in,
+// so the shadow sweep and the primary kernel test supers first, open the leaves of the survivors and only then single
+// spheres.  Soundness rests on one property, which tests/test_clusters_cpu.py checks: every member ball
+// (centre, R') lies inside the ball of its leaf AND inside the ball of its super-cluster, or that radius is +inf
+// ("always open": a member with non-finite or >= 1e15 coordinates / radius).
 #ifndef ORE_CLUSTERS_H
 #define ORE_CLUSTERS_H
 #include <algorithm>
