@@ -181,7 +181,8 @@ __device__ __forceinline__ SkyFast make_sky_fast(const CamP& cam, float fz, int 
     s.ev0 = fmaf(4e-6f, s.kv, fmaf(1e-6f, (float)h, 1e-4f));
     // the camera well inside a sky sphere of sane size: the near root is the negative one and |O| / R <= 0.5
     s.ok = (enabled && R2 >= 1.f && R2 < 1e30f && OO <= 0.25f * R2 && fabsf(cam.cp) <= 1.f && fabsf(cam.sp) <= 1.f &&
-            fabsf(cam.cy) <= 1.f && fabsf(cam.sy) <= 1.f && w > 0 && h > 0 && w <= 65536 && h <= 65536) ? 1 : 0;
+            fabsf(cam.cy) <= 1.f && fabsf(cam.sy) <= 1.f && w > 0 && h > 0 && w <= 65536 && h <= 65536 &&
+            (float)w * (float)h < 1.0e9f /* the texel index stays far inside int range */) ? 1 : 0;
     return s;
 }
 __device__ __forceinline__ float sqrt_approx(float x) {
