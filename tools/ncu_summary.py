@@ -15,6 +15,9 @@ KEEP = [
     "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
     "smsp__inst_executed.sum", "sm__cycles_elapsed.avg.per_second", "sm__inst_executed.avg.per_cycle_elapsed",
     "smsp__thread_inst_executed_per_inst_executed.ratio", "lts__t_bytes.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    # instruction caches: SM-level hit rate and the GPC-level cache's request rate against its peak
+    "sm__icc_request_hit_rate.pct", "sm__icc_requests.sum.pct_of_peak_sustained_elapsed",
+    "gcc__cache_requests_type_instruction.sum.pct_of_peak_sustained_elapsed", "gcc__average_cache_request_hit_rate.pct",
 ]
 
 
